@@ -1,0 +1,127 @@
+/* dtcsim C ABI -- the drop-in boundary of the B200-native DTC Floquet-circuit simulator.
+ *
+ * What it replaces.  The reference reaches its simulator through Python, not FFI:
+ *     backend = AerSimulator(noise_model=nm, device="GPU", cuStateVec_enable=True)   fast.py:156
+ *     result  = backend.run(circ_tnoise, shots=1024).result()                          fast.py:211
+ *     counts  = result.get_counts(circ_tnoise)                                         fast.py:212
+ * Everything below `run()` is qiskit-aer C++/CUDA (third party, not in the reference tree).  This
+ * header is the C boundary our Python host (package module backend.py, class DTCSimulator) binds
+ * with ctypes; a maintainer of the reference would bind the same symbols.
+ *
+ * Conventions.  Plain pointers and sizes only.  Device buffers are caller-owned (allocated by the
+ * host runtime, e.g. torch) and never freed here; host arrays are consumed before the call
+ * returns.  Every function returns 0 on success or a negative dtc_status and records a message
+ * retrievable with dtc_last_error() (thread-local).  `stream` is a cudaStream_t passed as void*.
+ * States are complex128, interleaved (re, im), basis index little-endian (qubit k = bit k), one
+ * state of 2^n amplitudes per trajectory, trajectories contiguous.
+ *
+ * Execution model.  A circuit is compiled on the host into an event list of
+ *   ROT(q, theta) = exp(-i theta X_q/2),  D1(q, a) = exp(-i a Z_q/2),  D2(i,j,b) = exp(-i b Z_i Z_j/2),
+ *   NOISE(q, pX,pY,pZ)
+ * grouped in layers  D_0 | R_1 D_1 | R_2 D_2 ...  A sampled Pauli never touches the state: it
+ * updates a per-trajectory Pauli frame F (psi_true = F psi'), which only flips signs of later
+ * angles.  dtc_program_run() samples the frames (Philox4x32-10), then streams the batch of states
+ * once per fused  R|S -> D -> R|S  pass.
+ */
+#ifndef DTCSIM_H
+#define DTCSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    DTC_OK = 0,
+    DTC_ERR_INVALID = -1,   /* bad argument / inconsistent program */
+    DTC_ERR_CUDA = -2,      /* CUDA runtime error (message has the CUDA string) */
+    DTC_ERR_UNSUPPORTED = -3,
+    DTC_ERR_NOMEM = -4
+} dtc_status;
+
+enum { DTC_EV_ROT = 0, DTC_EV_D1 = 1, DTC_EV_D2 = 2, DTC_EV_NOISE = 3 };
+enum { DTC_ENGINE_AUTO = 0, DTC_ENGINE_GENERIC = 1, DTC_ENGINE_TILE = 2 };
+
+typedef struct dtc_program dtc_program;   /* opaque compiled circuit */
+
+/* ---- library ------------------------------------------------------------------------------ */
+int dtc_version(void);                     /* 100*major + minor */
+const char *dtc_last_error(void);          /* replaces Python exceptions raised inside Aer's run() */
+int dtc_device_count(int *count);
+
+/* ---- program: the compiled form of one circuit (replaces Aer's internal circuit/op list that
+ *      backend.run() builds from the QuantumCircuit, fast.py:211) ------------------------------ */
+/* n_qubits: qubits of the full register (global index width); n_local: qubits held by this
+ * process' state (n_local == n_qubits unless the state is sharded on its top bits). */
+int dtc_program_create(int n_qubits, int n_layers, dtc_program **out);
+int dtc_program_destroy(dtc_program *p);
+/* Event arrays in circuit order (see plan.py): type[n], layer[n], q0[n], q1[n], slot[n]
+ * (D1: sign slot 0/1; D2: term index in its layer; NOISE: site id), val[n] (ROT theta, D1 a,
+ * D2 b), probs[n][3] (NOISE pX,pY,pZ).  global_phase: psi_true carries exp(+i global_phase). */
+int dtc_program_set_events(dtc_program *p, int64_t n_events, const int32_t *type, const int32_t *layer,
+                           const int32_t *q0, const int32_t *q1, const int32_t *slot,
+                           const double *val, const double *probs, double global_phase);
+/* Build layer tables and the pass schedule and upload them to `device`.
+ * engine: DTC_ENGINE_AUTO picks the fused tile engine when n_local >= 12. */
+int dtc_program_finalize(dtc_program *p, int device, int engine, int n_local);
+int dtc_program_num_passes(const dtc_program *p, int *n_passes);
+/* bytes of caller-owned device scratch dtc_program_run() needs for n_traj trajectories */
+int dtc_program_workspace_bytes(const dtc_program *p, int64_t n_traj, size_t *bytes);
+/* Evolve n_traj trajectories (global ids traj_offset .. traj_offset+n_traj-1) from the basis state
+ * `init_index` (per process: local index; rank_bits are the value of the global index bits above
+ * n_local).  state: device buffer of n_traj * 2^n_local complex128.  On return the buffer holds
+ * psi' (frame not applied); the final frames live in the workspace (dtc_program_frames).
+ * Replaces the per-shot statevector evolution inside AerSimulator.run() (fast.py:211). */
+int dtc_program_run(dtc_program *p, void *state, int64_t n_traj, int64_t traj_offset, uint64_t seed,
+                    uint64_t init_index, uint64_t rank_bits, void *workspace, size_t workspace_bytes,
+                    void *stream);
+/* Device pointers (inside the workspace) to the final frame of each trajectory:
+ * fx, fz: uint64[n_traj] bit masks; ph: int32[n_traj] power of i.  psi_true = i^ph X^fx Z^fz psi'. */
+int dtc_program_frames(const dtc_program *p, void *workspace, int64_t n_traj,
+                       uint64_t **fx, uint64_t **fz, int32_t **ph);
+
+/* ---- state utilities ---------------------------------------------------------------------- */
+/* In-place psi' -> psi_true for each trajectory (used for amplitude-level parity / save_statevector). */
+int dtc_materialize(void *state, int n_local, int64_t n_traj, const uint64_t *fx, const uint64_t *fz,
+                    const int32_t *ph, void *scratch_one_state, void *stream);
+/* Marginal probabilities of `k` (<= 12) qubits: out[n_traj][2^k] (device, double), bit i of the
+ * column index = qubit qubits[i]; frame x-bits (may be NULL) flip the outcome of their qubit.
+ * Replaces the measure sampling input of Aer (fast.py:211) and compute_z_expectation's p0/p1. */
+int dtc_probs(const void *state, int n_local, int64_t n_traj, int k, const int32_t *qubits,
+              const uint64_t *fx_or_null, double *out, void *stream);
+/* <Z_q> for every qubit: out[n_traj][n_local] (device, double).  (dtc_qasm.py:145 per-qubit <Z_i>) */
+int dtc_expect_z(const void *state, int n_local, int64_t n_traj, const uint64_t *fx_or_null,
+                 double *out, void *stream);
+/* Inverse-CDF sampling from rows of a probability table (device): row r of probs[n_rows][n_cols];
+ * sample s of row r uses u = philox(seed; index = s, stream 1, traj = traj_offset + r) and writes
+ * out[r * n_samples + s] (int32 column index).  Replaces Aer's measurement sampler. */
+int dtc_sample_rows(const double *probs, int64_t n_rows, int n_cols, int n_samples, uint64_t seed,
+                    int64_t traj_offset, int32_t *out, void *stream);
+/* One basis-state sample per trajectory drawn from |psi'|^2 in index order (stream 1, index 0),
+ * with the frame's x mask applied to the result: out[n_traj] (uint64).  For wide registers
+ * (dtc_qasm.py measure-all).  scratch: n_traj * 2^(n_local-12 or 0) doubles. */
+int dtc_sample_states(const void *state, int n_local, int64_t n_traj, uint64_t seed, int64_t traj_offset,
+                      const uint64_t *fx_or_null, double *scratch, uint64_t *out, void *stream);
+
+/* ---- density-matrix primitives (exact noisy evolution for small n; Aer method density_matrix).
+ *      rho is a 2n-qubit vector: index = row + 2^n * col.  n <= 13. ------------------------- */
+int dtc_dm_init(void *rho, int n, uint64_t basis_index, void *stream);
+int dtc_dm_rot(void *rho, int n, int qubit, double theta, void *stream);            /* RX(theta) rho RX^dag */
+int dtc_dm_diag(void *rho, int n, int n1, const int32_t *q1, const double *a,
+                int n2, const int32_t *qi, const int32_t *qj, const double *b, void *stream);
+int dtc_dm_pauli_channel(void *rho, int n, int qubit, double px, double py, double pz, void *stream);
+int dtc_dm_probs(const void *rho, int n, int k, const int32_t *qubits, double *out, void *stream);
+
+/* ---- sharded statevector support (top log2(P) qubits global) ------------------------------ */
+/* Pack / unpack for the all-to-all that exchanges the g = log2(P) global qubits with local qubits
+ * lq[0..g-1]: send chunk d (destined to rank d) = amplitudes whose lq bits spell d.
+ * pack: out[d][j] = state[insert bits]; unpack is the inverse after the exchange. */
+int dtc_shard_pack(const void *state, void *out, int n_local, int g, const int32_t *lq, void *stream);
+int dtc_shard_unpack(const void *in, void *state, int n_local, int g, const int32_t *lq, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTCSIM_H */

@@ -1,0 +1,297 @@
+// dtc_core.hpp -- host-side program object: layer tables + pass schedule (no CUDA calls here).
+// Shared by the CUDA library (dtcsim.cu) and the CPU emulation harness (tests/emul/emul.cpp).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "dtc_hd.cuh"
+
+struct DtcGenericStep {
+    int kind;      // 0: rotation on qubit q of `layer`, 1: diagonal of `layer`
+    int layer;
+    int q;
+    double t;      // tan(theta'/2)
+};
+
+struct DtcProgramHost {
+    int n_qubits = 0, n_layers = 0, n_local = 0, device = -1, engine = 0;
+    double global_phase = 0.0;
+    bool finalized = false;
+    int64_t n_sites = 0;
+    std::vector<DtcEvent> events;
+    std::vector<DtcLayer> layers;
+    std::vector<DtcTilePass> passes;
+    std::vector<DtcGenericStep> gsteps;
+};
+
+static inline int dtc_popc(u64 x) { return __builtin_popcountll(x); }
+
+// ---- raw event arrays -> staged DtcEvent list
+static inline bool dtc_stage_events(DtcProgramHost& P, int64_t n, const int32_t* type, const int32_t* layer,
+                                    const int32_t* q0, const int32_t* q1, const int32_t* slot, const double* val,
+                                    const double* probs, double global_phase, std::string& err) {
+    if (n < 0 || (n > 0 && (!type || !layer || !q0 || !q1 || !slot || !val || !probs))) {
+        err = "NULL event array";
+        return false;
+    }
+    P.events.resize((size_t)n);
+    for (int64_t e = 0; e < n; ++e) {
+        DtcEvent& E = P.events[(size_t)e];
+        E.type = type[e]; E.layer = layer[e]; E.q0 = q0[e]; E.q1 = q1[e]; E.slot = slot[e]; E.k = 0;
+        if (E.type == DTC_EVT_NOISE) {
+            const double px = probs[3 * e], py = probs[3 * e + 1], pz = probs[3 * e + 2];
+            if (px < 0 || py < 0 || pz < 0 || px + py + pz > 1.0 + 1e-12) {
+                err = "invalid Pauli probabilities";
+                return false;
+            }
+            E.c0 = px; E.c1 = px + py; E.c2 = px + py + pz;
+        } else {
+            E.c0 = val[e]; E.c1 = 0; E.c2 = 0;
+        }
+    }
+    P.global_phase = global_phase;
+    return true;
+}
+
+// ---- events -> layer tables ------------------------------------------------------------------
+static inline bool dtc_build_layers(DtcProgramHost& P, std::string& err) {
+    const int M = P.n_layers;
+    P.layers.assign(M, DtcLayer());
+    for (int j = 0; j < M; ++j) {
+        DtcLayer& L = P.layers[j];
+        memset(&L, 0, sizeof(L));
+        L.cr = 1.0;
+        for (int s = 0; s < 2; ++s)
+            for (int q = 0; q < DTC_MAXQ; ++q) L.c1[s][q] = 1.0;
+        for (int k = 0; k < DTC_MAXT; ++k) L.tc[k] = 1.0;
+    }
+    P.n_sites = 0;
+    char buf[256];
+    for (size_t e = 0; e < P.events.size(); ++e) {
+        DtcEvent& E = P.events[e];
+        if (E.q0 < 0 || E.q0 >= P.n_qubits || E.layer < 0 || E.layer >= M) {
+            snprintf(buf, sizeof buf, "event %zu: qubit %d / layer %d out of range", e, E.q0, E.layer);
+            err = buf;
+            return false;
+        }
+        DtcLayer& L = P.layers[E.layer];
+        if (E.type == DTC_EVT_ROT) {
+            const double theta = E.c0;          // staged by set_events
+            const double kk = nearbyint(theta / M_PI);
+            const double thp = theta - kk * M_PI;
+            long long k4 = ((long long)kk) % 4;
+            if (k4 < 0) k4 += 4;
+            E.k = (int)k4;
+            const double t = tan(0.5 * thp);
+            if (L.rot_any >> E.q0 & 1ull) {
+                snprintf(buf, sizeof buf, "event %zu: two rotations on qubit %d in layer %d", e, E.q0, E.layer);
+                err = buf;
+                return false;
+            }
+            if (t != 0.0) {
+                L.rtan[E.q0] = t;
+                L.rot_any |= 1ull << E.q0;
+                L.cr *= cos(0.5 * thp);
+            }
+        } else if (E.type == DTC_EVT_D1) {
+            if (E.slot < 0 || E.slot > 1 || (L.d1_any[E.slot] >> E.q0 & 1ull)) {
+                snprintf(buf, sizeof buf, "event %zu: bad or duplicate D1 slot", e);
+                err = buf;
+                return false;
+            }
+            L.c1[E.slot][E.q0] = cos(0.5 * E.c0);
+            L.s1[E.slot][E.q0] = sin(0.5 * E.c0);
+            L.d1_any[E.slot] |= 1ull << E.q0;
+        } else if (E.type == DTC_EVT_D2) {
+            if (E.slot < 0 || E.slot >= DTC_MAXT || E.q1 < 0 || E.q1 >= P.n_qubits || E.q1 == E.q0) {
+                snprintf(buf, sizeof buf, "event %zu: bad D2 term", e);
+                err = buf;
+                return false;
+            }
+            L.tc[E.slot] = cos(0.5 * E.c0);
+            L.ts[E.slot] = sin(0.5 * E.c0);
+            L.ti[E.slot] = E.q0;
+            L.tj[E.slot] = E.q1;
+            if (E.slot + 1 > L.n_terms) L.n_terms = E.slot + 1;
+        } else if (E.type == DTC_EVT_NOISE) {
+            P.n_sites++;
+        } else {
+            snprintf(buf, sizeof buf, "event %zu: unknown type %d", e, E.type);
+            err = buf;
+            return false;
+        }
+    }
+    // global phase goes into the first diagonal layer's constant
+    const double s = P.layers[0].cr;
+    P.layers[0].cr = s * cos(P.global_phase);
+    P.layers[0].ci = s * sin(P.global_phase);
+    return true;
+}
+
+// ---- tile selection ----------------------------------------------------------------------------
+// Choose 12 tile bits containing the active set S (<= 10 qubits) and global bits 0,1 such that S
+// fits in a window of 10 consecutive tile-local positions starting at s2_lo in {0,1,2}.
+static inline bool dtc_build_tile(u64 S, int n_local, int tb[DTC_TILE_BITS], int* s2_lo) {
+    const u64 all = (n_local >= 64) ? ~0ull : ((1ull << n_local) - 1);
+    if (dtc_popc(S) > 10 || (S & ~all)) return false;
+    const u64 must = S | 3ull;
+    const int need = DTC_TILE_BITS - dtc_popc(must);
+    if (need < 0) return false;
+    int top = -1;
+    for (int b = 0; b < n_local; ++b)
+        if ((S >> b) & 1ull) top = b;
+    for (int klow = need; klow >= 0; --klow) {
+        u64 tile = must;
+        int added = 0;
+        for (int b = 0; b < n_local && added < klow; ++b)          // lowest unused bits first
+            if (!((tile >> b) & 1ull)) { tile |= 1ull << b; ++added; }
+        for (int b = top + 1; b < n_local && added < need; ++b)     // then bits above the active set
+            if (!((tile >> b) & 1ull)) { tile |= 1ull << b; ++added; }
+        for (int b = top; b >= 0 && added < need; --b)              // then whatever is left below
+            if (!((tile >> b) & 1ull)) { tile |= 1ull << b; ++added; }
+        if (added < need) continue;
+        int pos = 0, minpos = 99, maxpos = -1;
+        for (int b = 0; b < n_local; ++b) {
+            if (!((tile >> b) & 1ull)) continue;
+            tb[pos] = b;
+            if ((S >> b) & 1ull) {
+                if (pos < minpos) minpos = pos;
+                if (pos > maxpos) maxpos = pos;
+            }
+            ++pos;
+        }
+        if (maxpos < 0) { *s2_lo = 0; return true; }
+        const int lo = (maxpos - 9 > 0) ? maxpos - 9 : 0;
+        const int hi = (minpos < 2) ? minpos : 2;
+        if (lo <= hi) { *s2_lo = lo; return true; }
+    }
+    return false;
+}
+
+static inline u64 dtc_lowest_bits(u64 m, int count) {
+    u64 out = 0;
+    while (m && count > 0) {
+        const u64 b = m & (~m + 1);
+        out |= b;
+        m ^= b;
+        --count;
+    }
+    return out;
+}
+
+static inline void dtc_classify_terms(DtcTilePass& T, const DtcLayer& L) {
+    int loc[DTC_MAXQ];
+    for (int q = 0; q < DTC_MAXQ; ++q) loc[q] = -1;
+    for (int l = 0; l < DTC_TILE_BITS; ++l) loc[T.tb[l]] = l;
+    const int S1 = T.s2_lo + 5;
+    T.nT1 = T.nT2 = T.nX = T.nC = T.nO = 0;
+    for (int k = 0; k < L.n_terms; ++k) {
+        if (L.ts[k] == 0.0 && L.tc[k] == 1.0) continue;      // unused slot
+        int a = loc[L.ti[k]], b = loc[L.tj[k]];
+        if (a >= 0 && b >= 0) {
+            if (a > b) { int t = a; a = b; b = t; }
+            if (b <= S1) { T.T1k[T.nT1] = k; T.T1a[T.nT1] = a; T.T1b[T.nT1] = b; ++T.nT1; }
+            else if (a >= S1) { T.T2k[T.nT2] = k; T.T2a[T.nT2] = a; T.T2b[T.nT2] = b; ++T.nT2; }
+            else { T.Xk[T.nX] = k; T.Xa[T.nX] = a; T.Xb[T.nX] = b; ++T.nX; }
+        } else if (a >= 0 || b >= 0) {
+            T.Ck[T.nC] = k;
+            T.Ca[T.nC] = (a >= 0) ? a : b;
+            T.Cb[T.nC] = (a >= 0) ? L.tj[k] : L.ti[k];
+            ++T.nC;
+        } else {
+            T.Ok[T.nO] = k; T.Oa[T.nO] = L.ti[k]; T.Ob[T.nO] = L.tj[k]; ++T.nO;
+        }
+    }
+}
+
+// ---- pass schedule -----------------------------------------------------------------------------
+static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
+    const int M = P.n_layers, n = P.n_local;
+    const u64 local_mask = (n >= 64) ? ~0ull : ((1ull << n) - 1);
+    P.passes.clear();
+    for (int j = 0; j < M; ++j)
+        if (P.layers[j].rot_any & ~local_mask) {
+            err = "rotation on a non-local (global) qubit: exchange qubits before this layer";
+            return false;
+        }
+    int j = 0;
+    u64 done = 0;
+    while (j < M) {
+        const DtcLayer& L = P.layers[j];
+        const u64 rem = L.rot_any & ~done;
+        u64 SA = dtc_lowest_bits(rem, 10);
+        const bool complete = (rem & ~SA) == 0;
+        u64 S = SA, SB = 0;
+        if (complete && j + 1 < M) {
+            const u64 next = P.layers[j + 1].rot_any;
+            u64 fill = dtc_lowest_bits(next & ~S, 10 - dtc_popc(S));
+            S |= fill;
+            SB = next & S;
+        }
+        DtcTilePass T;
+        memset(&T, 0, sizeof(T));
+        if (!dtc_build_tile(S, n, T.tb, &T.s2_lo)) {
+            // retry without look-ahead fill
+            S = SA;
+            SB = (complete && j + 1 < M) ? (P.layers[j + 1].rot_any & S) : 0;
+            if (!dtc_build_tile(S, n, T.tb, &T.s2_lo)) {
+                // last resort: a single active qubit always fits
+                SA = dtc_lowest_bits(rem, 1);
+                S = SA;
+                SB = 0;
+                if (!dtc_build_tile(S, n, T.tb, &T.s2_lo)) {
+                    err = "internal: cannot build a tile";
+                    return false;
+                }
+            }
+        }
+        const bool comp2 = (rem & ~SA) == 0;
+        T.n_local = n;
+        T.n_total = P.n_qubits;
+        T.layerA = SA ? j : -1;
+        T.layerD = comp2 ? j : -1;
+        T.layerB = (comp2 && SB) ? j + 1 : -1;
+        for (int l = 0; l < DTC_TILE_BITS; ++l) {
+            const int q = T.tb[l];
+            T.t1[l] = ((SA >> q) & 1ull) ? L.rtan[q] : 0.0;
+            T.t2[l] = (T.layerB >= 0 && ((SB >> q) & 1ull)) ? P.layers[j + 1].rtan[q] : 0.0;
+        }
+        if (T.layerD >= 0) dtc_classify_terms(T, L);
+        // sanity: active bits must sit inside the register windows
+        for (int l = 0; l < DTC_TILE_BITS; ++l)
+            if ((T.t1[l] != 0.0 || T.t2[l] != 0.0) && (l < T.s2_lo || l >= T.s2_lo + 10)) {
+                err = "internal: active qubit outside the tile window";
+                return false;
+            }
+        P.passes.push_back(T);
+        if (comp2) {
+            ++j;
+            done = (T.layerB >= 0) ? SB : 0;
+        } else {
+            done |= SA;
+        }
+    }
+    return true;
+}
+
+static inline void dtc_schedule_generic(DtcProgramHost& P) {
+    P.gsteps.clear();
+    for (int j = 0; j < P.n_layers; ++j) {
+        const DtcLayer& L = P.layers[j];
+        for (int q = 0; q < P.n_qubits; ++q)
+            if ((L.rot_any >> q) & 1ull) P.gsteps.push_back(DtcGenericStep{0, j, q, L.rtan[q]});
+        const bool trivial = L.n_terms == 0 && !L.d1_any[0] && !L.d1_any[1] && L.cr == 1.0 && L.ci == 0.0;
+        if (!trivial) P.gsteps.push_back(DtcGenericStep{1, j, -1, 0.0});
+    }
+}
+
+static inline size_t dtc_workspace_bytes(const DtcProgramHost& P, int64_t n_traj) {
+    size_t b = (size_t)(P.n_layers * 4 + 2) * (size_t)n_traj * sizeof(u64);
+    b += (size_t)n_traj * sizeof(int);
+    return (b + 255) & ~(size_t)255;
+}

@@ -1,0 +1,700 @@
+// dtcsim.cu -- sm_100a kernels + the C ABI declared in include/dtcsim.h.
+//
+// Kernel inventory (all complex128, HBM-bound; no tensor cores on this path -- see DESIGN.md):
+//   k_tile_pass<S2_LO>   fused  R_A|S -> D -> R_B|S  over 2^12-amplitude tiles: coalesced 16 B loads,
+//                        5-qubit register butterflies, two swizzled shared-memory transposes,
+//                        diagonal ZZ/Z phase as a product of two shared-memory tables.   (hot kernel)
+//   k_frames             Philox4x32-10 Pauli-frame walk, one thread per trajectory.
+//   k_probs / k_expect_z warp-shuffle reductions for read-out.
+//   k_generic_*          one-thread-per-element fallbacks (n < 12, cross-checks).
+//   k_dm_*               exact density-matrix primitives (small n).
+#include <cuda_runtime.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/dtcsim.h"
+#include "dtc_core.hpp"
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(DTC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+struct dtc_program {
+    DtcProgramHost h;
+    DtcEvent* d_events = nullptr;
+    DtcLayer* d_layers = nullptr;
+};
+
+// ------------------------------------------------------------------------------------ kernels
+__global__ void k_frames(const DtcEvent* __restrict__ ev, long long n_events, u64* __restrict__ masks,
+                         long long n_traj, long long traj_offset, u64 seed, u64* __restrict__ fx,
+                         u64* __restrict__ fz, int* __restrict__ ph) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_traj) return;
+    frame_walk((u64)(traj_offset + t), seed, ev, n_events, masks + t, n_traj, fx + t, fz + t, ph + t);
+}
+
+__global__ void k_init_basis(double2* __restrict__ state, int n_local, long long n_traj, u64 index) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_traj) state[((u64)t << n_local) + index] = make_double2(1.0, 0.0);
+}
+
+template <int S2_LO>
+__global__ void __launch_bounds__(DTC_THREADS, 3)
+k_tile_pass(double2* __restrict__ state, const __grid_constant__ DtcTilePass P,
+            const DtcLayer* __restrict__ layers, const u64* __restrict__ masks, long long n_traj,
+            u64 rank_bits) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    TileSmem& sm = *reinterpret_cast<TileSmem*>(smraw);
+    const int tid = threadIdx.x;
+    const int ntb = P.n_local - DTC_TILE_BITS;
+    const u64 tile = (u64)blockIdx.x & ((1ull << ntb) - 1);
+    const u64 traj = (u64)blockIdx.x >> ntb;
+    double2* __restrict__ st = state + (traj << P.n_local);
+    const u64 base = tile_base_index(tile, P.n_local, P.tb);
+    const TileMasks M = tile_load_masks(P, masks, n_traj, traj);
+
+    // phase 1: coalesced global loads straight into the register file (registers span S1)
+    u64 off, rs[5];
+    tile_global_offsets<S2_LO>(tid, base, P.tb, off, rs);
+    double2 a[DTC_NREG];
+    tile_gload(st, off, rs, a);
+    // diagonal-layer setup and tables overlap the loads in flight
+    if (P.layerD >= 0)
+        tile_setup_thread(tid, sm, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
+    __syncthreads();
+    if (P.layerD >= 0) tile_tables_thread<S2_LO>(tid, sm, P);
+    if (P.layerA >= 0) tile_rot_s1<S2_LO>(a, P.t1, P.tb, M.rmA);
+    tile_sm_store13<S2_LO>(tid, sm, a);
+    __syncthreads();
+
+    // phase 2: registers span S2:  R_A|S2, D, R_B|S2
+    tile_sm_load2<S2_LO>(tid, sm, a);
+    tile_phase2_compute<S2_LO>(tid, a, sm, P, M.rmA, M.rmB);
+    tile_sm_store2<S2_LO>(tid, sm, a);
+    __syncthreads();
+
+    // phase 3: registers span S1 again, coalesced stores
+    tile_sm_load13<S2_LO>(tid, sm, a);
+    if (P.layerB >= 0) tile_rot_s1<S2_LO>(a, P.t2, P.tb, M.rmB);
+    tile_gstore(st, off, rs, a);
+}
+
+// ---- generic engine
+__global__ void k_generic_rot(double2* __restrict__ state, int n_local, int q, double t,
+                              const u64* __restrict__ rmask, long long n_traj) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npairs = n_traj << (n_local - 1);
+    if (i >= npairs) return;
+    const u64 traj = (u64)i >> (n_local - 1);
+    const u64 p = (u64)i & ((1ull << (n_local - 1)) - 1);
+    const u64 lowm = (1ull << q) - 1;
+    const u64 i0 = ((p & ~lowm) << 1) | (p & lowm);
+    double2* st = state + (traj << n_local);
+    const double ts = ((rmask[traj] >> q) & 1ull) ? -t : t;
+    double2 x0 = st[i0], x1 = st[i0 | (1ull << q)];
+    rot_pair(x0, x1, ts);
+    st[i0] = x0;
+    st[i0 | (1ull << q)] = x1;
+}
+
+__global__ void k_generic_diag(double2* __restrict__ state, int n_local, const DtcLayer* __restrict__ L,
+                               const u64* __restrict__ masks, long long n_traj, u64 rank_bits) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n_traj << n_local)) return;
+    const u64 traj = (u64)i >> n_local;
+    const u64 x = (u64)i & ((1ull << n_local) - 1);
+    const u64 m1a = masks[1 * n_traj + traj], m1b = masks[2 * n_traj + traj], m2 = masks[3 * n_traj + traj];
+    const double2 ph = diag_phase(*L, x | (rank_bits << n_local), m1a, m1b, m2);
+    state[i] = cmul(state[i], ph);
+}
+
+// ---- read-out
+__global__ void k_materialize(double2* __restrict__ state, int n_local, long long n_traj,
+                              const u64* __restrict__ fx, const u64* __restrict__ fz, const int* __restrict__ ph) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n_traj << n_local)) return;
+    const u64 traj = (u64)i >> n_local;
+    const u64 y = (u64)i & ((1ull << n_local) - 1);
+    const u64 X = fx[traj], Z = fz[traj];
+    const u64 y2 = y ^ X;
+    if (X != 0 && y > y2) return;                 // the pair is handled by its smaller member
+    double2* st = state + (traj << n_local);
+    const int p = ph[traj] & 3;
+    auto phase = [p](double2 v, int neg) {
+        double2 r;
+        switch (p) {
+            case 0: r = v; break;
+            case 1: r = make_double2(-v.y, v.x); break;
+            case 2: r = make_double2(-v.x, -v.y); break;
+            default: r = make_double2(v.y, -v.x); break;
+        }
+        if (neg) { r.x = -r.x; r.y = -r.y; }
+        return r;
+    };
+    // psi_true(y) = i^ph (-1)^{popc((y^X)&Z)} psi'(y^X)
+    const double2 vy = st[y], vy2 = st[y2];
+    const double2 ny = phase(vy2, __popcll(y2 & Z) & 1);
+    st[y] = ny;
+    if (X != 0) st[y2] = phase(vy, __popcll(y & Z) & 1);
+}
+
+__global__ void k_probs(const double2* __restrict__ state, int n_local, long long n_traj, int k,
+                        const int* __restrict__ qubits, const u64* __restrict__ fx, double* __restrict__ out,
+                        int chunks_per_traj) {
+    extern __shared__ double sbins[];
+    const int nb = 1 << k;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) sbins[b] = 0.0;
+    __syncthreads();
+    const u64 traj = blockIdx.x / chunks_per_traj;
+    const u64 chunk = blockIdx.x % chunks_per_traj;
+    const u64 per = (1ull << n_local) / chunks_per_traj;
+    const double2* st = state + (traj << n_local);
+    int flip = 0;
+    if (fx) {
+        const u64 X = fx[traj];
+        for (int b = 0; b < k; ++b) flip |= (int)((X >> qubits[b]) & 1ull) << b;
+    }
+    if (k <= 2) {
+        double acc[4] = {0, 0, 0, 0};
+        for (u64 x = chunk * per + threadIdx.x; x < (chunk + 1) * per; x += blockDim.x) {
+            const double2 v = st[x];
+            const double p = v.x * v.x + v.y * v.y;
+            int bin = 0;
+            for (int b = 0; b < k; ++b) bin |= (int)((x >> qubits[b]) & 1ull) << b;
+            bin ^= flip;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] += (bin == c) ? p : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double v = acc[c];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0 && c < nb) atomicAdd(&sbins[c], v);
+        }
+    } else {
+        for (u64 x = chunk * per + threadIdx.x; x < (chunk + 1) * per; x += blockDim.x) {
+            const double2 v = st[x];
+            int bin = 0;
+            for (int b = 0; b < k; ++b) bin |= (int)((x >> qubits[b]) & 1ull) << b;
+            atomicAdd(&sbins[bin ^ flip], v.x * v.x + v.y * v.y);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) atomicAdd(&out[traj * nb + b], sbins[b]);
+}
+
+__global__ void k_expect_z(const double2* __restrict__ state, int n_local, long long n_traj,
+                           const u64* __restrict__ fx, double* __restrict__ out, int chunks_per_traj) {
+    __shared__ double sacc[DTC_MAXQ];
+    if (threadIdx.x < DTC_MAXQ) sacc[threadIdx.x] = 0.0;
+    __syncthreads();
+    const u64 traj = blockIdx.x / chunks_per_traj;
+    const u64 chunk = blockIdx.x % chunks_per_traj;
+    const u64 per = (1ull << n_local) / chunks_per_traj;
+    const double2* st = state + (traj << n_local);
+    double acc[DTC_MAXQ];
+#pragma unroll
+    for (int q = 0; q < DTC_MAXQ; ++q) acc[q] = 0.0;
+    for (u64 x = chunk * per + threadIdx.x; x < (chunk + 1) * per; x += blockDim.x) {
+        const double2 v = st[x];
+        const double p = v.x * v.x + v.y * v.y;
+#pragma unroll
+        for (int q = 0; q < DTC_MAXQ; ++q)
+            if (q < n_local) acc[q] += ((x >> q) & 1ull) ? -p : p;
+    }
+    const u64 X = fx ? fx[traj] : 0ull;
+#pragma unroll
+    for (int q = 0; q < DTC_MAXQ; ++q) {
+        if (q < n_local) {
+            double v = acc[q];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[q], ((X >> q) & 1ull) ? -v : v);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < n_local) atomicAdd(&out[traj * n_local + threadIdx.x], sacc[threadIdx.x]);
+}
+
+__global__ void k_sample_rows(const double* __restrict__ probs, long long n_rows, int n_cols, int n_samples,
+                              u64 seed, long long traj_offset, int* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * n_samples) return;
+    const long long r = i / n_samples;
+    const int s = (int)(i % n_samples);
+    const double u = philox_uniform(seed, (uint32_t)s, 1u, (u64)(traj_offset + r));
+    const double* p = probs + r * n_cols;
+    double cum = 0.0;
+    int pick = n_cols - 1;
+    for (int c = 0; c < n_cols; ++c) {
+        cum += p[c];
+        if (cum > u) { pick = c; break; }
+    }
+    out[i] = pick;
+}
+
+__global__ void k_chunk_norms(const double2* __restrict__ state, int n_local, int chunk_bits,
+                              double* __restrict__ sums) {
+    // one block per (traj, chunk)
+    __shared__ double wsum[32];
+    const u64 blk = blockIdx.x;
+    const double2* st = state + (blk << chunk_bits);
+    double acc = 0.0;
+    for (u64 x = threadIdx.x; x < (1ull << chunk_bits); x += blockDim.x) {
+        const double2 v = st[x];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wsum[w];
+        sums[blk] = s;
+    }
+}
+
+__global__ void k_sample_states(const double2* __restrict__ state, int n_local, int chunk_bits,
+                                const double* __restrict__ sums, long long n_traj, u64 seed,
+                                long long traj_offset, const u64* __restrict__ fx, u64* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_traj) return;
+    const u64 nchunks = 1ull << (n_local - chunk_bits);
+    const double* s = sums + (u64)t * nchunks;
+    double total = 0.0;
+    for (u64 c = 0; c < nchunks; ++c) total += s[c];
+    const double target = philox_uniform(seed, 0u, 1u, (u64)(traj_offset + t)) * total;
+    double cum = 0.0;
+    u64 c = 0;
+    for (; c + 1 < nchunks; ++c) {
+        if (cum + s[c] > target) break;
+        cum += s[c];
+    }
+    const double2* st = state + ((u64)t << n_local) + (c << chunk_bits);
+    u64 pick = (1ull << chunk_bits) - 1;
+    for (u64 x = 0; x < (1ull << chunk_bits); ++x) {
+        const double2 v = st[x];
+        cum += v.x * v.x + v.y * v.y;
+        if (cum > target) { pick = x; break; }
+    }
+    u64 idx = (c << chunk_bits) | pick;
+    if (fx) idx ^= fx[t];
+    out[t] = idx;
+}
+
+// ---- density matrix (2n-bit vector, index = row + 2^n col)
+__global__ void k_rot_cs(double2* __restrict__ v, int nbits, int bit, double c, double s) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1ll << (nbits - 1))) return;
+    const u64 lowm = (1ull << bit) - 1;
+    const u64 i0 = (((u64)i & ~lowm) << 1) | ((u64)i & lowm);
+    const u64 i1 = i0 | (1ull << bit);
+    const double2 x0 = v[i0], x1 = v[i1];
+    // [[c, -i s], [-i s, c]]
+    v[i0] = make_double2(c * x0.x + s * x1.y, c * x0.y - s * x1.x);
+    v[i1] = make_double2(c * x1.x + s * x0.y, c * x1.y - s * x0.x);
+}
+
+__global__ void k_dm_diag(double2* __restrict__ rho, int n, int n1, const int* __restrict__ q1,
+                          const double* __restrict__ a, int n2, const int* __restrict__ qi,
+                          const int* __restrict__ qj, const double* __restrict__ b) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1ll << (2 * n))) return;
+    const u64 r = (u64)i & ((1ull << n) - 1), c = (u64)i >> n;
+    double ang = 0.0;
+    for (int k = 0; k < n1; ++k) {
+        const int zr = 1 - 2 * (int)((r >> q1[k]) & 1ull), zc = 1 - 2 * (int)((c >> q1[k]) & 1ull);
+        ang += 0.5 * a[k] * (double)(zr - zc);
+    }
+    for (int k = 0; k < n2; ++k) {
+        const int zr = 1 - 2 * (int)(((r >> qi[k]) ^ (r >> qj[k])) & 1ull);
+        const int zc = 1 - 2 * (int)(((c >> qi[k]) ^ (c >> qj[k])) & 1ull);
+        ang += 0.5 * b[k] * (double)(zr - zc);
+    }
+    double sn, cs;
+    sincos(ang, &sn, &cs);
+    rho[i] = cmul(rho[i], make_double2(cs, -sn));
+}
+
+__global__ void k_dm_channel(double2* __restrict__ rho, int n, int q, double px, double py, double pz) {
+    // thread per group of 4 elements spanning (row bit q, col bit q)
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1ll << (2 * n - 2))) return;
+    const int b0 = q, b1 = q + n;
+    u64 x = (u64)i;
+    const u64 low0 = (1ull << b0) - 1;
+    x = ((x & ~low0) << 1) | (x & low0);
+    const u64 low1 = (1ull << b1) - 1;
+    x = ((x & ~low1) << 1) | (x & low1);
+    const u64 i00 = x, i11 = x | (1ull << b0) | (1ull << b1), i01 = x | (1ull << b0), i10 = x | (1ull << b1);
+    const double dA = 1.0 - px - py, dB = px + py;              // r_q == c_q
+    const double oA = 1.0 - px - py - 2.0 * pz, oB = px - py;   // r_q != c_q
+    const double2 e00 = rho[i00], e11 = rho[i11], e01 = rho[i01], e10 = rho[i10];
+    rho[i00] = make_double2(dA * e00.x + dB * e11.x, dA * e00.y + dB * e11.y);
+    rho[i11] = make_double2(dA * e11.x + dB * e00.x, dA * e11.y + dB * e00.y);
+    rho[i01] = make_double2(oA * e01.x + oB * e10.x, oA * e01.y + oB * e10.y);
+    rho[i10] = make_double2(oA * e10.x + oB * e01.x, oA * e10.y + oB * e01.y);
+}
+
+__global__ void k_dm_probs(const double2* __restrict__ rho, int n, int k, const int* __restrict__ qubits,
+                           double* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (1ll << n)) return;
+    int bin = 0;
+    for (int b = 0; b < k; ++b) bin |= (int)(((u64)r >> qubits[b]) & 1ull) << b;
+    atomicAdd(&out[bin], rho[(u64)r + ((u64)r << n)].x);
+}
+
+// ---- sharded state: gather/scatter for the global<->local qubit exchange
+__global__ void k_shard_pack(const double2* __restrict__ state, double2* __restrict__ out, int n_local, int g,
+                             const int* __restrict__ lq, int unpack) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1ll << n_local)) return;
+    // packed index = (d << (n_local-g)) | j ; state index = j with bits of d inserted at positions lq[]
+    const u64 d = (u64)i >> (n_local - g);
+    u64 j = (u64)i & ((1ull << (n_local - g)) - 1);
+    u64 used = 0;
+    for (int b = 0; b < g; ++b) used |= 1ull << lq[b];
+    u64 x = 0;
+    int src = 0;
+    for (int pos = 0; pos < n_local; ++pos) {
+        if ((used >> pos) & 1ull) continue;
+        if ((j >> src) & 1ull) x |= 1ull << pos;
+        ++src;
+    }
+    for (int b = 0; b < g; ++b)
+        if ((d >> b) & 1ull) x |= 1ull << lq[b];
+    if (unpack) ((double2*)state)[x] = out[i];
+    else out[i] = state[x];
+}
+
+// ------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int dtc_version(void) { return 100; }
+const char* dtc_last_error(void) { return g_err.c_str(); }
+
+int dtc_device_count(int* count) {
+    if (!count) return fail(DTC_ERR_INVALID, "count is NULL");
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return DTC_OK;
+}
+
+int dtc_program_create(int n_qubits, int n_layers, dtc_program** out) {
+    if (!out) return fail(DTC_ERR_INVALID, "out is NULL");
+    if (n_qubits < 1 || n_qubits > 62) return fail(DTC_ERR_INVALID, "n_qubits must be in [1, 62]");
+    if (n_layers < 1 || n_layers > (1 << 20)) return fail(DTC_ERR_INVALID, "n_layers out of range");
+    dtc_program* p = new (std::nothrow) dtc_program();
+    if (!p) return fail(DTC_ERR_NOMEM, "out of host memory");
+    p->h.n_qubits = n_qubits;
+    p->h.n_layers = n_layers;
+    *out = p;
+    return DTC_OK;
+}
+
+int dtc_program_destroy(dtc_program* p) {
+    if (!p) return DTC_OK;
+    if (p->d_events) cudaFree(p->d_events);
+    if (p->d_layers) cudaFree(p->d_layers);
+    delete p;
+    return DTC_OK;
+}
+
+int dtc_program_set_events(dtc_program* p, int64_t n, const int32_t* type, const int32_t* layer,
+                           const int32_t* q0, const int32_t* q1, const int32_t* slot, const double* val,
+                           const double* probs, double global_phase) {
+    if (!p) return fail(DTC_ERR_INVALID, "program is NULL");
+    if (p->h.finalized) return fail(DTC_ERR_INVALID, "program already finalized");
+    std::string err;
+    if (!dtc_stage_events(p->h, n, type, layer, q0, q1, slot, val, probs, global_phase, err))
+        return fail(DTC_ERR_INVALID, err);
+    return DTC_OK;
+}
+
+int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
+    if (!p) return fail(DTC_ERR_INVALID, "program is NULL");
+    if (p->h.finalized) return fail(DTC_ERR_INVALID, "program already finalized");
+    if (n_local < 1 || n_local > p->h.n_qubits) return fail(DTC_ERR_INVALID, "n_local out of range");
+    if (n_local > 40) return fail(DTC_ERR_INVALID, "n_local exceeds 40 qubits");
+    p->h.n_local = n_local;
+    p->h.device = device;
+    std::string err;
+    if (!dtc_build_layers(p->h, err)) return fail(DTC_ERR_INVALID, err);
+    if (engine == DTC_ENGINE_AUTO) engine = (n_local >= DTC_TILE_BITS) ? DTC_ENGINE_TILE : DTC_ENGINE_GENERIC;
+    if (engine == DTC_ENGINE_TILE && n_local < DTC_TILE_BITS)
+        return fail(DTC_ERR_INVALID, "tile engine needs n_local >= 12");
+    p->h.engine = engine;
+    if (engine == DTC_ENGINE_TILE) {
+        if (!dtc_schedule_tile(p->h, err)) return fail(DTC_ERR_INVALID, err);
+    } else if (engine == DTC_ENGINE_GENERIC) {
+        for (int j = 0; j < p->h.n_layers; ++j)
+            if (n_local < 64 && (p->h.layers[j].rot_any >> n_local))
+                return fail(DTC_ERR_INVALID, "rotation on a non-local qubit");
+        dtc_schedule_generic(p->h);
+    } else {
+        return fail(DTC_ERR_INVALID, "unknown engine");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t eb = p->h.events.size() * sizeof(DtcEvent), lb = p->h.layers.size() * sizeof(DtcLayer);
+    CUDA_TRY(cudaMalloc(&p->d_events, eb ? eb : 16));
+    CUDA_TRY(cudaMalloc(&p->d_layers, lb));
+    if (eb) CUDA_TRY(cudaMemcpy(p->d_events, p->h.events.data(), eb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p->d_layers, p->h.layers.data(), lb, cudaMemcpyHostToDevice));
+    static bool attr_set[16] = {false};
+    if (device >= 0 && device < 16 && !attr_set[device]) {
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+        attr_set[device] = true;
+    }
+    p->h.finalized = true;
+    return DTC_OK;
+}
+
+int dtc_program_num_passes(const dtc_program* p, int* n_passes) {
+    if (!p || !n_passes || !p->h.finalized) return fail(DTC_ERR_INVALID, "program not finalized");
+    *n_passes = (p->h.engine == DTC_ENGINE_TILE) ? (int)p->h.passes.size() : (int)p->h.gsteps.size();
+    return DTC_OK;
+}
+
+int dtc_program_workspace_bytes(const dtc_program* p, int64_t n_traj, size_t* bytes) {
+    if (!p || !bytes || n_traj < 1) return fail(DTC_ERR_INVALID, "bad argument");
+    *bytes = dtc_workspace_bytes(p->h, n_traj);
+    return DTC_OK;
+}
+
+static void ws_pointers(const DtcProgramHost& h, void* ws, int64_t n_traj, u64** masks, u64** fx, u64** fz, int** ph) {
+    u64* base = (u64*)ws;
+    *masks = base;
+    *fx = base + (size_t)h.n_layers * 4 * n_traj;
+    *fz = *fx + n_traj;
+    *ph = (int*)(*fz + n_traj);
+}
+
+int dtc_program_frames(const dtc_program* p, void* workspace, int64_t n_traj, uint64_t** fx, uint64_t** fz, int32_t** ph) {
+    if (!p || !workspace || !fx || !fz || !ph) return fail(DTC_ERR_INVALID, "bad argument");
+    u64 *m, *x, *z;
+    int* h;
+    ws_pointers(p->h, workspace, n_traj, &m, &x, &z, &h);
+    *fx = (uint64_t*)x; *fz = (uint64_t*)z; *ph = (int32_t*)h;
+    return DTC_OK;
+}
+
+int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_offset, uint64_t seed,
+                    uint64_t init_index, uint64_t rank_bits, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!p || !p->h.finalized) return fail(DTC_ERR_INVALID, "program not finalized");
+    if (!state || !workspace || n_traj < 1) return fail(DTC_ERR_INVALID, "bad argument");
+    const DtcProgramHost& h = p->h;
+    if (workspace_bytes < dtc_workspace_bytes(h, n_traj)) return fail(DTC_ERR_INVALID, "workspace too small");
+    if (init_index >> h.n_local) return fail(DTC_ERR_INVALID, "init_index out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(h.device));
+    u64 *masks, *fx, *fz;
+    int* ph;
+    ws_pointers(h, workspace, n_traj, &masks, &fx, &fz, &ph);
+    CUDA_TRY(cudaMemsetAsync(masks, 0, (size_t)h.n_layers * 4 * n_traj * sizeof(u64), s));
+    const int fb = 128;
+    k_frames<<<(unsigned)((n_traj + fb - 1) / fb), fb, 0, s>>>(p->d_events, (long long)h.events.size(), masks,
+                                                              n_traj, traj_offset, seed, fx, fz, ph);
+    const size_t sbytes = ((size_t)n_traj << h.n_local) * sizeof(double2);
+    CUDA_TRY(cudaMemsetAsync(state, 0, sbytes, s));
+    k_init_basis<<<(unsigned)((n_traj + 127) / 128), 128, 0, s>>>((double2*)state, h.n_local, n_traj, init_index);
+    if (h.engine == DTC_ENGINE_TILE) {
+        const long long grid = n_traj << (h.n_local - DTC_TILE_BITS);
+        if (grid > 0x7fffffffLL) return fail(DTC_ERR_INVALID, "batch too large for one launch");
+        for (const DtcTilePass& T : h.passes) {
+            switch (T.s2_lo) {
+                case 0: k_tile_pass<0><<<(unsigned)grid, DTC_THREADS, sizeof(TileSmem), s>>>((double2*)state, T, p->d_layers, masks, n_traj, rank_bits); break;
+                case 1: k_tile_pass<1><<<(unsigned)grid, DTC_THREADS, sizeof(TileSmem), s>>>((double2*)state, T, p->d_layers, masks, n_traj, rank_bits); break;
+                default: k_tile_pass<2><<<(unsigned)grid, DTC_THREADS, sizeof(TileSmem), s>>>((double2*)state, T, p->d_layers, masks, n_traj, rank_bits); break;
+            }
+        }
+    } else {
+        for (const DtcGenericStep& g : h.gsteps) {
+            if (g.kind == 0) {
+                const long long np = n_traj << (h.n_local - 1);
+                k_generic_rot<<<(unsigned)((np + 255) / 256), 256, 0, s>>>((double2*)state, h.n_local, g.q, g.t,
+                                                                         masks + (size_t)(g.layer * 4) * n_traj, n_traj);
+            } else {
+                const long long ne = n_traj << h.n_local;
+                k_generic_diag<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>((double2*)state, h.n_local, p->d_layers + g.layer,
+                                                                          masks + (size_t)(g.layer * 4) * n_traj, n_traj, rank_bits);
+            }
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+int dtc_materialize(void* state, int n_local, int64_t n_traj, const uint64_t* fx, const uint64_t* fz,
+                    const int32_t* ph, void* scratch, void* stream) {
+    (void)scratch;
+    if (!state || !fx || !fz || !ph) return fail(DTC_ERR_INVALID, "bad argument");
+    const long long ne = n_traj << n_local;
+    k_materialize<<<(unsigned)((ne + 255) / 256), 256, 0, (cudaStream_t)stream>>>((double2*)state, n_local, n_traj,
+                                                                                 (const u64*)fx, (const u64*)fz, ph);
+    CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+static int chunks_for(int n_local) {
+    int cb = n_local - 14;            // 2^14 amplitudes per block
+    if (cb < 0) cb = 0;
+    if (cb > 10) cb = 10;
+    return 1 << cb;
+}
+
+int dtc_probs(const void* state, int n_local, int64_t n_traj, int k, const int32_t* qubits,
+              const uint64_t* fx, double* out, void* stream) {
+    if (!state || !out || k < 0 || k > 12 || (k > 0 && !qubits)) return fail(DTC_ERR_INVALID, "bad argument (k <= 12)");
+    cudaStream_t s = (cudaStream_t)stream;
+    int* dq = nullptr;
+    CUDA_TRY(cudaMallocAsync(&dq, sizeof(int) * (k ? k : 1), s));
+    if (k) CUDA_TRY(cudaMemcpyAsync(dq, qubits, sizeof(int) * k, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * ((size_t)n_traj << k), s));
+    const int cpt = chunks_for(n_local);
+    k_probs<<<(unsigned)(n_traj * cpt), 256, sizeof(double) << k, s>>>((const double2*)state, n_local, n_traj, k, dq,
+                                                                     (const u64*)fx, out, cpt);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(dq, s));
+    return DTC_OK;
+}
+
+int dtc_expect_z(const void* state, int n_local, int64_t n_traj, const uint64_t* fx, double* out, void* stream) {
+    if (!state || !out || n_local > DTC_MAXQ) return fail(DTC_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)n_traj * n_local, s));
+    const int cpt = chunks_for(n_local);
+    k_expect_z<<<(unsigned)(n_traj * cpt), 128, 0, s>>>((const double2*)state, n_local, n_traj, (const u64*)fx, out, cpt);
+    CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+int dtc_sample_rows(const double* probs, int64_t n_rows, int n_cols, int n_samples, uint64_t seed,
+                    int64_t traj_offset, int32_t* out, void* stream) {
+    if (!probs || !out || n_rows < 1 || n_cols < 1 || n_samples < 1) return fail(DTC_ERR_INVALID, "bad argument");
+    const long long n = n_rows * n_samples;
+    k_sample_rows<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(probs, n_rows, n_cols, n_samples, seed,
+                                                                                traj_offset, out);
+    CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+int dtc_sample_states(const void* state, int n_local, int64_t n_traj, uint64_t seed, int64_t traj_offset,
+                      const uint64_t* fx, double* scratch, uint64_t* out, void* stream) {
+    if (!state || !scratch || !out) return fail(DTC_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int cb = n_local < 12 ? n_local : 12;
+    const long long nblk = n_traj << (n_local - cb);
+    k_chunk_norms<<<(unsigned)nblk, 128, 0, s>>>((const double2*)state, n_local, cb, scratch);
+    k_sample_states<<<(unsigned)((n_traj + 63) / 64), 64, 0, s>>>((const double2*)state, n_local, cb, scratch, n_traj, seed,
+                                                                 traj_offset, (const u64*)fx, (u64*)out);
+    CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+// ---- density matrix
+int dtc_dm_init(void* rho, int n, uint64_t basis_index, void* stream) {
+    if (!rho || n < 1 || n > 13 || (basis_index >> n)) return fail(DTC_ERR_INVALID, "bad argument (n <= 13)");
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(rho, 0, sizeof(double2) << (2 * n), s));
+    k_init_basis<<<1, 32, 0, s>>>((double2*)rho, 2 * n, 1, basis_index | (basis_index << n));
+    CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+int dtc_dm_rot(void* rho, int n, int qubit, double theta, void* stream) {
+    if (!rho || n < 1 || n > 13 || qubit < 0 || qubit >= n) return fail(DTC_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const double c = cos(0.5 * theta), sn = sin(0.5 * theta);
+    const long long np = 1ll << (2 * n - 1);
+    k_rot_cs<<<(unsigned)((np + 255) / 256), 256, 0, s>>>((double2*)rho, 2 * n, qubit, c, sn);       // rows: RX(theta)
+    k_rot_cs<<<(unsigned)((np + 255) / 256), 256, 0, s>>>((double2*)rho, 2 * n, qubit + n, c, -sn);  // cols: conj
+    CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+int dtc_dm_diag(void* rho, int n, int n1, const int32_t* q1, const double* a, int n2, const int32_t* qi,
+                const int32_t* qj, const double* b, void* stream) {
+    if (!rho || n < 1 || n > 13 || n1 < 0 || n2 < 0) return fail(DTC_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int *dq1 = nullptr, *dqi = nullptr, *dqj = nullptr;
+    double *da = nullptr, *db = nullptr;
+    CUDA_TRY(cudaMallocAsync(&dq1, sizeof(int) * (n1 + 1), s));
+    CUDA_TRY(cudaMallocAsync(&da, sizeof(double) * (n1 + 1), s));
+    CUDA_TRY(cudaMallocAsync(&dqi, sizeof(int) * (n2 + 1), s));
+    CUDA_TRY(cudaMallocAsync(&dqj, sizeof(int) * (n2 + 1), s));
+    CUDA_TRY(cudaMallocAsync(&db, sizeof(double) * (n2 + 1), s));
+    if (n1) {
+        CUDA_TRY(cudaMemcpyAsync(dq1, q1, sizeof(int) * n1, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(da, a, sizeof(double) * n1, cudaMemcpyHostToDevice, s));
+    }
+    if (n2) {
+        CUDA_TRY(cudaMemcpyAsync(dqi, qi, sizeof(int) * n2, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(dqj, qj, sizeof(int) * n2, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(db, b, sizeof(double) * n2, cudaMemcpyHostToDevice, s));
+    }
+    const long long ne = 1ll << (2 * n);
+    k_dm_diag<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>((double2*)rho, n, n1, dq1, da, n2, dqi, dqj, db);
+    CUDA_TRY(cudaGetLastError());
+    // host arrays were pageable: make sure the copies are done before the caller reuses them
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFreeAsync(dq1, s); cudaFreeAsync(da, s); cudaFreeAsync(dqi, s); cudaFreeAsync(dqj, s); cudaFreeAsync(db, s);
+    return DTC_OK;
+}
+
+int dtc_dm_pauli_channel(void* rho, int n, int qubit, double px, double py, double pz, void* stream) {
+    if (!rho || n < 1 || n > 13 || qubit < 0 || qubit >= n) return fail(DTC_ERR_INVALID, "bad argument");
+    const long long ng = 1ll << (2 * n - 2);
+    k_dm_channel<<<(unsigned)((ng + 255) / 256), 256, 0, (cudaStream_t)stream>>>((double2*)rho, n, qubit, px, py, pz);
+    CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+int dtc_dm_probs(const void* rho, int n, int k, const int32_t* qubits, double* out, void* stream) {
+    if (!rho || !out || n < 1 || n > 13 || k < 0 || k > n || (k > 0 && !qubits)) return fail(DTC_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int* dq = nullptr;
+    CUDA_TRY(cudaMallocAsync(&dq, sizeof(int) * (k + 1), s));
+    if (k) CUDA_TRY(cudaMemcpyAsync(dq, qubits, sizeof(int) * k, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) << k, s));
+    const long long nr = 1ll << n;
+    k_dm_probs<<<(unsigned)((nr + 127) / 128), 128, 0, s>>>((const double2*)rho, n, k, dq, out);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFreeAsync(dq, s);
+    return DTC_OK;
+}
+
+static int shard_move(const void* state, void* buf, int n_local, int g, const int32_t* lq, int unpack, void* stream) {
+    if (!state || !buf || g < 1 || g > 6 || g > n_local || !lq) return fail(DTC_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int* dl = nullptr;
+    CUDA_TRY(cudaMallocAsync(&dl, sizeof(int) * g, s));
+    CUDA_TRY(cudaMemcpyAsync(dl, lq, sizeof(int) * g, cudaMemcpyHostToDevice, s));
+    const long long ne = 1ll << n_local;
+    k_shard_pack<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>((const double2*)state, (double2*)buf, n_local, g, dl, unpack);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFreeAsync(dl, s);
+    return DTC_OK;
+}
+
+int dtc_shard_pack(const void* state, void* out, int n_local, int g, const int32_t* lq, void* stream) {
+    return shard_move(state, out, n_local, g, lq, 0, stream);
+}
+int dtc_shard_unpack(const void* in, void* state, int n_local, int g, const int32_t* lq, void* stream) {
+    return shard_move(state, (void*)in, n_local, g, lq, 1, stream);
+}
+
+}  // extern "C"

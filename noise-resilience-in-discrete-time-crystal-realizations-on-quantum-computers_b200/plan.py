@@ -1,0 +1,375 @@
+"""Layer compiler: transpiled op stream -> alternating rotation / diagonal layers + noise events.
+
+This is the host half of what qiskit-aer does inside ``backend.run`` (fast.py:211) before it
+touches the state: truncate idle qubits (the transpiled circuit is >= 31 qubits wide with only
+L+1 active), look up which gates carry noise (fast.py:85-86), and turn the
+gate list into device work.  Aer executes gate by gate; we do not.  Every supported gate is
+rewritten exactly into two primitives
+
+    ROT(q, theta)         = RX(theta) = exp(-i theta X_q / 2)
+    D1(q, a) / D2(i,j,b)  = exp(-i a Z_q / 2), exp(-i b Z_i Z_j / 2)        (diagonal)
+
+using  u3(t,p,l) = e^{i(p+l)/2} RZ(p+pi/2) RX(t) RZ(l-pi/2)  (so the reference's rx -> u3(t,-pi/2,pi/2)
+has *no* diagonal part), cz = e^{i pi/4} RZ(pi/2) x RZ(pi/2) x RZZ(-pi/2), cx(c,t) = RY(pi/2)_t CZ RY(-pi/2)_t
+and the peephole cx(a,b) rz(p)@b cx(a,b) = RZZ(p) (the transpiler's lowering of rzz, undone).
+Primitives are packed into layers  D_0 | R_1 D_1 | R_2 D_2 | ...  such that per-qubit order is
+preserved (all D terms commute).  The CUDA engine then streams the state once per R-D-R group.
+
+Pauli noise never touches the state: a sampled Pauli is pushed into a per-trajectory Pauli *frame*
+F (psi_true = F psi').  Because every primitive is exp(-i angle P/2) for a Pauli P, conjugation by
+the frame only flips the sign of its angle.  The frame kernel therefore walks the EVENT list below
+in circuit order and emits one sign bit per event and trajectory; NOISE events update the frame.
+A D1 term added after a frame change on its qubit needs its own sign bit, hence two D1 "slots"
+per (layer, qubit); if both are taken the qubit is advanced to the next layer.
+"""
+import math
+from collections import defaultdict
+
+import numpy as np
+
+from .ir import QuantumCircuit, as_circuit
+
+PI = math.pi
+EV_ROT, EV_D1, EV_D2, EV_NOISE = 0, 1, 2, 3
+MAX_D2_PER_LAYER = 64
+
+_U3_OF = {  # name -> (theta, phi, lam, extra global phase) with U = e^{i extra} u3(theta,phi,lam)
+    "h": lambda p: (PI / 2, 0.0, PI, 0.0),
+    "x": lambda p: (PI, 0.0, PI, 0.0),
+    "y": lambda p: (PI, PI / 2, PI / 2, 0.0),
+    "u2": lambda p: (PI / 2, p[0], p[1], 0.0),
+    "u3": lambda p: (p[0], p[1], p[2], 0.0),
+    "u": lambda p: (p[0], p[1], p[2], 0.0),
+    "ry": lambda p: (p[0], 0.0, 0.0, 0.0),
+}
+_DIAG_OF = {  # name -> (rz angle a, global phase) with U = e^{i phase} RZ(a)
+    "rz": lambda p: (p[0], 0.0),
+    "u1": lambda p: (p[0], p[0] / 2),
+    "p": lambda p: (p[0], p[0] / 2),
+    "z": lambda p: (PI, PI / 2),
+    "s": lambda p: (PI / 2, PI / 4),
+    "sdg": lambda p: (-PI / 2, -PI / 4),
+    "t": lambda p: (PI / 4, PI / 8),
+    "tdg": lambda p: (-PI / 4, -PI / 8),
+}
+ONE_QUBIT = set(_U3_OF) | set(_DIAG_OF) | {"rx", "sx", "sxdg", "id"}
+SUPPORTED = ONE_QUBIT | {"cx", "cz", "rzz", "swap", "measure", "barrier"}
+
+
+class Program:
+    """Compiled circuit: event arrays for the CUDA library + read-out description."""
+
+    def __init__(self):
+        self.n = 0
+        self.n_clbits = 0
+        self.active = []            # original (wide-circuit) index of each simulated qubit
+        self.n_layers = 1
+        self.ev_type = []
+        self.ev_layer = []
+        self.ev_q0 = []
+        self.ev_q1 = []
+        self.ev_slot = []           # D1: slot 0/1; D2: term index within its layer; NOISE: site id
+        self.ev_val = []            # ROT: theta; D1: a; D2: b
+        self.ev_probs = []          # NOISE: (px, py, pz); zeros otherwise
+        self.global_phase = 0.0     # psi_true carries e^{+i global_phase}
+        self.measures = []          # (simulated qubit, clbit)
+        self.n_sites = 0
+        self.dm_segments = []       # ordered segments for the density-matrix engine
+        self.rot_layers = 0         # number of non-empty rotation layers (for accounting)
+
+    def arrays(self):
+        ne = len(self.ev_type)
+        probs = np.zeros((ne, 3), dtype=np.float64)
+        for i, p in enumerate(self.ev_probs):
+            if p is not None:
+                probs[i] = p
+        return dict(
+            type=np.asarray(self.ev_type, dtype=np.int32), layer=np.asarray(self.ev_layer, dtype=np.int32),
+            q0=np.asarray(self.ev_q0, dtype=np.int32), q1=np.asarray(self.ev_q1, dtype=np.int32),
+            slot=np.asarray(self.ev_slot, dtype=np.int32), val=np.asarray(self.ev_val, dtype=np.float64),
+            probs=probs)
+
+    @property
+    def measured_qubits(self):
+        return [q for q, _ in self.measures]
+
+
+def compact(circ):
+    """Idle-qubit truncation (what Aer does to the 31-qubit-wide transpiled circuit)."""
+    used = sorted({q for op in circ.ops if op.name != "barrier" for q in op.qubits})
+    remap = {q: i for i, q in enumerate(used)}
+    return remap, used
+
+
+def _fuse_cx_rz_cx(ops, noisy):
+    """Peephole: cx(a,b) [diag 1q on b] cx(a,b) -> rzz-equivalent.  `noisy(op)` must be False for all three.
+
+    Only ops touching a or b are considered neighbours; diagonal 1q gates on the control a in
+    between commute with everything involved and are left in place.
+    """
+    out = []
+    i = 0
+    n = len(ops)
+    consumed = set()
+    while i < n:
+        if i in consumed:
+            i += 1
+            continue
+        op = ops[i]
+        if op.name == "cx" and not noisy(op):
+            a, b = op.qubits
+            mid = None
+            close = None
+            for j in range(i + 1, n):
+                if j in consumed:
+                    continue
+                o2 = ops[j]
+                if not (set(o2.qubits) & {a, b}):
+                    continue
+                if mid is None:
+                    if o2.name in _DIAG_OF and o2.qubits == (b,) and not noisy(o2):
+                        mid = j
+                        continue
+                    if o2.name in _DIAG_OF and o2.qubits == (a,) and not noisy(o2):
+                        continue            # commutes with the control of the cx pair
+                    break
+                if o2.name in _DIAG_OF and o2.qubits == (a,) and not noisy(o2):
+                    continue
+                if o2.name == "cx" and o2.qubits == (a, b) and not noisy(o2):
+                    close = j
+                break
+            if mid is not None and close is not None:
+                ang, ph = _DIAG_OF[ops[mid].name](ops[mid].params)
+                out.append(("rzz_fused", (a, b), ang, ph))
+                consumed.add(mid)
+                consumed.add(close)
+                i += 1
+                continue
+        out.append(op)
+        i += 1
+    return out
+
+
+class _Builder:
+    def __init__(self, n):
+        self.p = Program()
+        self.p.n = n
+        self.last_r = [0] * n
+        self.epoch = [0] * n
+        self.d1_slots = {}                    # (layer, q) -> [(epoch, event index), ...]
+        self.d2_terms = {}                    # (layer, i, j, epoch_i, epoch_j) -> event index
+        self.d2_count = defaultdict(int)
+        self.prims = []                       # linear primitive list for the DM engine
+
+    def _emit(self, typ, layer, q0, q1, slot, val, probs=None):
+        p = self.p
+        p.ev_type.append(typ)
+        p.ev_layer.append(layer)
+        p.ev_q0.append(q0)
+        p.ev_q1.append(q1)
+        p.ev_slot.append(slot)
+        p.ev_val.append(val)
+        p.ev_probs.append(probs)
+        return len(p.ev_type) - 1
+
+    def rot(self, q, theta):
+        if theta == 0.0:
+            return
+        self.prims.append(("R", (q,), theta))
+        self.last_r[q] += 1
+        self._emit(EV_ROT, self.last_r[q], q, -1, 0, theta)
+
+    def d1(self, q, a):
+        if a == 0.0:
+            return
+        self.prims.append(("D", (q,), a))
+        while True:
+            layer = self.last_r[q]
+            slots = self.d1_slots.setdefault((layer, q), [])
+            for ep, ev in slots:
+                if ep == self.epoch[q]:
+                    self.p.ev_val[ev] += a
+                    return
+            if len(slots) < 2:
+                ev = self._emit(EV_D1, layer, q, -1, len(slots), a)
+                slots.append((self.epoch[q], ev))
+                return
+            self.last_r[q] += 1               # both sign slots taken: advance q to the next layer
+
+    def d2(self, i, j, b):
+        if b == 0.0:
+            return
+        if i > j:
+            i, j = j, i
+        self.prims.append(("D", (i, j), b))
+        layer = max(self.last_r[i], self.last_r[j])
+        while True:
+            key = (layer, i, j, self.epoch[i], self.epoch[j])
+            ev = self.d2_terms.get(key)
+            if ev is not None:
+                self.p.ev_val[ev] += b
+                break
+            if self.d2_count[layer] < MAX_D2_PER_LAYER:
+                ev = self._emit(EV_D2, layer, i, j, self.d2_count[layer], b)
+                self.d2_count[layer] += 1
+                self.d2_terms[key] = ev
+                break
+            layer += 1
+        self.last_r[i] = self.last_r[j] = layer
+
+    def noise(self, q, probs):
+        self.prims.append(("N", (q,), tuple(probs)))
+        self._emit(EV_NOISE, self.last_r[q], q, -1, self.p.n_sites, 0.0, tuple(probs))
+        self.p.n_sites += 1
+        self.epoch[q] += 1
+
+    def u3(self, q, theta, phi, lam, extra=0.0):
+        self.p.global_phase += extra + (phi + lam) / 2
+        self.d1(q, lam - PI / 2)
+        self.rot(q, theta)
+        self.d1(q, phi + PI / 2)
+
+    def cz(self, a, b):
+        self.p.global_phase += PI / 4
+        self.d1(a, PI / 2)
+        self.d1(b, PI / 2)
+        self.d2(a, b, -PI / 2)
+
+    def ry(self, q, beta):
+        self.d1(q, -PI / 2)
+        self.rot(q, beta)
+        self.d1(q, PI / 2)
+
+    def cx(self, c, t):
+        self.ry(t, -PI / 2)
+        self.cz(c, t)
+        self.ry(t, PI / 2)
+
+
+def _segment_dm(prims):
+    """Greedy ASAP packing of primitives into typed segments (R / D / N) preserving per-qubit order."""
+    segs = []                                 # [type, payload]
+    last_seg = {}
+    last_typ = {}
+    for typ, qs, val in prims:
+        p0 = 0
+        for q in qs:
+            if q in last_seg:
+                share = (typ == "D" and last_typ[q] == "D")
+                p0 = max(p0, last_seg[q] if share else last_seg[q] + 1)
+        pos = None
+        for k in range(p0, len(segs)):
+            if segs[k][0] == typ:
+                pos = k
+                break
+        if pos is None:
+            segs.append([typ, []])
+            pos = len(segs) - 1
+        segs[pos][1].append((qs, val))
+        for q in qs:
+            last_seg[q] = pos
+            last_typ[q] = typ
+    out = []
+    for typ, items in segs:
+        if typ == "D":
+            d1 = defaultdict(float)
+            d2 = defaultdict(float)
+            for qs, val in items:
+                if len(qs) == 1:
+                    d1[qs[0]] += val
+                else:
+                    d2[qs] += val
+            out.append(("D", dict(d1), dict(d2)))
+        else:
+            out.append((typ, [(qs[0], val) for qs, val in items]))
+    return out
+
+
+def compile_circuit(circuit, noise_model=None, want_dm=False):
+    """Compile a (transpiled) circuit + noise model into a :class:`Program`.
+
+    Raises ValueError for anything the device path cannot execute exactly (unsupported gate,
+    noise on a multi-qubit gate, mid-circuit measurement) -- there is no CPU fallback.
+    """
+    circ = as_circuit(circuit)
+    for op in circ.ops:
+        if op.name not in SUPPORTED:
+            raise ValueError(f"unsupported instruction {op.name!r}")
+    remap, used = compact(circ)
+    n = len(used)
+    if n == 0:
+        raise ValueError("circuit has no active qubits")
+    if n > 62:
+        raise ValueError(f"{n} active qubits exceed the 62-qubit index limit")
+    b = _Builder(n)
+    prog = b.p
+    prog.active = used
+    prog.n_clbits = circ.num_clbits
+    prog.global_phase = float(circ.global_phase)
+
+    def probs_of(op):
+        if noise_model is None or op.name in ("measure", "barrier"):
+            return None
+        if len(op.qubits) != 1:
+            if any(noise_model.lookup(op.name, q) for q in op.qubits):
+                raise ValueError(f"noise on multi-qubit gate {op.name!r} is not supported")
+            return None
+        return noise_model.lookup(op.name, op.qubits[0])
+
+    ops = [o for o in circ.ops if o.name != "barrier"]
+    ops = _fuse_cx_rz_cx(ops, lambda o: probs_of(o) is not None)
+    measured = {}
+    finished = set()
+    for op in ops:
+        if isinstance(op, tuple):                      # fused cx-rz-cx
+            _, (a, c), ang, ph = op
+            qa, qc = remap[a], remap[c]
+            if qa in finished or qc in finished:
+                raise ValueError("gate after measurement (mid-circuit measurement is not supported)")
+            prog.global_phase += ph
+            b.d2(qa, qc, ang)
+            continue
+        nm = op.name
+        qs = [remap[q] for q in op.qubits]
+        if nm == "measure":
+            measured[op.clbits[0]] = qs[0]
+            finished.add(qs[0])
+            continue
+        if any(q in finished for q in qs):
+            raise ValueError("gate after measurement (mid-circuit measurement is not supported)")
+        if nm in _U3_OF:
+            th, ph, lam, extra = _U3_OF[nm](op.params)
+            b.u3(qs[0], th, ph, lam, extra)
+        elif nm in _DIAG_OF:
+            ang, ph = _DIAG_OF[nm](op.params)
+            prog.global_phase += ph
+            b.d1(qs[0], ang)
+        elif nm == "rx":
+            b.rot(qs[0], op.params[0])
+        elif nm == "sx":
+            prog.global_phase += PI / 4
+            b.rot(qs[0], PI / 2)
+        elif nm == "sxdg":
+            prog.global_phase -= PI / 4
+            b.rot(qs[0], -PI / 2)
+        elif nm == "id":
+            pass
+        elif nm == "rzz":
+            b.d2(qs[0], qs[1], op.params[0])
+        elif nm == "cz":
+            b.cz(qs[0], qs[1])
+        elif nm == "cx":
+            b.cx(qs[0], qs[1])
+        elif nm == "swap":
+            b.cx(qs[0], qs[1])
+            b.cx(qs[1], qs[0])
+            b.cx(qs[0], qs[1])
+        pr = probs_of(op)
+        if pr is not None:
+            b.noise(qs[0], pr)
+    prog.n_layers = max(b.last_r) + 1
+    prog.rot_layers = len({l for t, l in zip(prog.ev_type, prog.ev_layer) if t == EV_ROT})
+    prog.measures = sorted(((q, c) for c, q in measured.items()), key=lambda qc: qc[1])
+    if want_dm:
+        prog.dm_segments = _segment_dm(b.prims)
+    return prog

@@ -1,0 +1,155 @@
+// emul.cpp -- CPU emulation of the dtcsim kernels (TEST INFRASTRUCTURE, never shipped or timed).
+//
+// Compiles the *same* host/device headers as the CUDA library (csrc/dtc_hd.cuh, csrc/dtc_core.hpp)
+// with g++ and executes each CTA of k_tile_pass thread by thread, phase by phase (a phase ends where
+// the kernel has a __syncthreads), so the tile-engine logic -- index maps, swizzles, table
+// construction, sign masks, pass schedule -- is validated against the oracle without a GPU.
+#include <stdlib.h>
+
+#include <string>
+#include <vector>
+
+#include "../../noise-resilience-in-discrete-time-crystal-realizations-on-quantum-computers_b200/csrc/dtc_core.hpp"
+
+template <int S2_LO>
+static void emu_tile_pass(double2* state, const DtcTilePass& P, const DtcLayer* layers, const u64* masks,
+                          long long n_traj, u64 rank_bits, u64 block, TileSmem& sm,
+                          std::vector<double2>& regs) {
+    const int ntb = P.n_local - DTC_TILE_BITS;
+    const u64 tile = block & ((1ull << ntb) - 1);
+    const u64 traj = block >> ntb;
+    double2* st = state + (traj << P.n_local);
+    const u64 base = tile_base_index(tile, P.n_local, P.tb);
+    const TileMasks M = tile_load_masks(P, masks, n_traj, traj);
+    u64 off[DTC_THREADS], rs[DTC_THREADS][5];
+    // --- up to the first barrier
+    for (int tid = 0; tid < DTC_THREADS; ++tid) {
+        double2* a = &regs[(size_t)tid * DTC_NREG];
+        tile_global_offsets<S2_LO>(tid, base, P.tb, off[tid], rs[tid]);
+        tile_gload(st, off[tid], rs[tid], a);
+        if (P.layerD >= 0)
+            tile_setup_thread(tid, sm, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
+    }
+    // --- second segment
+    for (int tid = 0; tid < DTC_THREADS; ++tid) {
+        double2* a = &regs[(size_t)tid * DTC_NREG];
+        if (P.layerD >= 0) tile_tables_thread<S2_LO>(tid, sm, P);
+        if (P.layerA >= 0) tile_rot_s1<S2_LO>(a, P.t1, P.tb, M.rmA);
+        tile_sm_store13<S2_LO>(tid, sm, a);
+    }
+    // --- phase 2
+    for (int tid = 0; tid < DTC_THREADS; ++tid) {
+        double2 a[DTC_NREG];
+        tile_sm_load2<S2_LO>(tid, sm, a);
+        tile_phase2_compute<S2_LO>(tid, a, sm, P, M.rmA, M.rmB);
+        // a thread only rewrites the slots it read, so doing this without a barrier is faithful
+        tile_sm_store2<S2_LO>(tid, sm, a);
+    }
+    // --- phase 3
+    for (int tid = 0; tid < DTC_THREADS; ++tid) {
+        double2 a[DTC_NREG];
+        tile_sm_load13<S2_LO>(tid, sm, a);
+        if (P.layerB >= 0) tile_rot_s1<S2_LO>(a, P.t2, P.tb, M.rmB);
+        tile_gstore(st, off[tid], rs[tid], a);
+    }
+}
+
+extern "C" int emu_run(int n_qubits, int n_layers, int64_t n_events, const int32_t* type, const int32_t* layer,
+                       const int32_t* q0, const int32_t* q1, const int32_t* slot, const double* val,
+                       const double* probs, double global_phase, int engine, int n_local, int64_t n_traj,
+                       int64_t traj_offset, u64 seed, u64 init_index, u64 rank_bits, double* state_out,
+                       u64* fx, u64* fz, int* ph, int* n_passes, char* errbuf, int errlen) {
+    DtcProgramHost P;
+    P.n_qubits = n_qubits;
+    P.n_layers = n_layers;
+    P.n_local = n_local;
+    std::string err;
+    auto bail = [&](const std::string& m) {
+        snprintf(errbuf, errlen, "%s", m.c_str());
+        return -1;
+    };
+    if (!dtc_stage_events(P, n_events, type, layer, q0, q1, slot, val, probs, global_phase, err)) return bail(err);
+    if (!dtc_build_layers(P, err)) return bail(err);
+    if (engine == 0) engine = (n_local >= DTC_TILE_BITS) ? 2 : 1;
+    if (engine == 2) {
+        if (n_local < DTC_TILE_BITS) return bail("tile engine needs n_local >= 12");
+        if (!dtc_schedule_tile(P, err)) return bail(err);
+        *n_passes = (int)P.passes.size();
+    } else {
+        dtc_schedule_generic(P);
+        *n_passes = (int)P.gsteps.size();
+    }
+    std::vector<u64> masks((size_t)n_layers * 4 * n_traj, 0);
+    for (int64_t t = 0; t < n_traj; ++t)
+        frame_walk((u64)(traj_offset + t), seed, P.events.data(), (int64_t)P.events.size(), masks.data() + t, n_traj,
+                   fx + t, fz + t, ph + t);
+    double2* st = reinterpret_cast<double2*>(state_out);
+    const size_t ne = (size_t)n_traj << n_local;
+    for (size_t i = 0; i < ne; ++i) st[i] = make_double2(0.0, 0.0);
+    for (int64_t t = 0; t < n_traj; ++t) st[((u64)t << n_local) + init_index] = make_double2(1.0, 0.0);
+    if (engine == 2) {
+        TileSmem* sm = new TileSmem();
+        std::vector<double2> regs((size_t)DTC_THREADS * DTC_NREG);
+        const u64 grid = (u64)n_traj << (n_local - DTC_TILE_BITS);
+        for (const DtcTilePass& T : P.passes) {
+            for (u64 b = 0; b < grid; ++b) {
+                if (T.s2_lo == 0) emu_tile_pass<0>(st, T, P.layers.data(), masks.data(), n_traj, rank_bits, b, *sm, regs);
+                else if (T.s2_lo == 1) emu_tile_pass<1>(st, T, P.layers.data(), masks.data(), n_traj, rank_bits, b, *sm, regs);
+                else emu_tile_pass<2>(st, T, P.layers.data(), masks.data(), n_traj, rank_bits, b, *sm, regs);
+            }
+        }
+        delete sm;
+    } else {
+        for (const DtcGenericStep& g : P.gsteps) {
+            if (g.kind == 0) {
+                const u64 np = (u64)n_traj << (n_local - 1);
+                for (u64 i = 0; i < np; ++i) {
+                    const u64 traj = i >> (n_local - 1);
+                    const u64 p = i & ((1ull << (n_local - 1)) - 1);
+                    const u64 lowm = (1ull << g.q) - 1;
+                    const u64 i0 = ((p & ~lowm) << 1) | (p & lowm);
+                    double2* s2 = st + (traj << n_local);
+                    const u64 rm = masks[(size_t)(g.layer * 4) * n_traj + traj];
+                    const double ts = ((rm >> g.q) & 1ull) ? -g.t : g.t;
+                    rot_pair(s2[i0], s2[i0 | (1ull << g.q)], ts);
+                }
+            } else {
+                const DtcLayer& L = P.layers[g.layer];
+                for (u64 i = 0; i < ne; ++i) {
+                    const u64 traj = i >> n_local, x = i & ((1ull << n_local) - 1);
+                    const u64* m = masks.data() + (size_t)(g.layer * 4) * n_traj;
+                    st[i] = cmul(st[i], diag_phase(L, x | (rank_bits << n_local), m[1 * n_traj + traj],
+                                                   m[2 * n_traj + traj], m[3 * n_traj + traj]));
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+// expose the pass schedule for inspection by tests: fills up to `cap` rows of
+// [s2_lo, layerA, layerD, layerB, nT1, nT2, nX, nC, nO, tb0..tb11]
+extern "C" int emu_schedule(int n_qubits, int n_layers, int64_t n_events, const int32_t* type, const int32_t* layer,
+                            const int32_t* q0, const int32_t* q1, const int32_t* slot, const double* val,
+                            const double* probs, int n_local, int32_t* rows, int cap, char* errbuf, int errlen) {
+    DtcProgramHost P;
+    P.n_qubits = n_qubits;
+    P.n_layers = n_layers;
+    P.n_local = n_local;
+    std::string err;
+    if (!dtc_stage_events(P, n_events, type, layer, q0, q1, slot, val, probs, 0.0, err) || !dtc_build_layers(P, err) ||
+        !dtc_schedule_tile(P, err)) {
+        snprintf(errbuf, errlen, "%s", err.c_str());
+        return -1;
+    }
+    int n = 0;
+    for (const DtcTilePass& T : P.passes) {
+        if (n >= cap) break;
+        int32_t* r = rows + (size_t)n * 21;
+        r[0] = T.s2_lo; r[1] = T.layerA; r[2] = T.layerD; r[3] = T.layerB;
+        r[4] = T.nT1; r[5] = T.nT2; r[6] = T.nX; r[7] = T.nC; r[8] = T.nO;
+        for (int l = 0; l < 12; ++l) r[9 + l] = T.tb[l];
+        ++n;
+    }
+    return (int)P.passes.size();
+}
