@@ -1,0 +1,142 @@
+"""ctypes binding of the C ABI in include/dtcsim.h (libdtcsim.so, built in-tree by __graft_entry__.build()).
+
+There is no CPU fallback: if the CUDA library is missing or a call fails, a RuntimeError/ValueError is
+raised with the library's own message (the analogue of the exceptions Aer raises from run(), fast.py:211).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdtcsim.so")
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_i64 = ctypes.c_int64
+c_u64 = ctypes.c_uint64
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_vp = ctypes.c_void_p
+
+_SIGS = {
+    "dtc_version": (ctypes.c_int, []),
+    "dtc_last_error": (ctypes.c_char_p, []),
+    "dtc_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "dtc_program_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "dtc_program_destroy": (ctypes.c_int, [c_vp]),
+    "dtc_program_set_events": (ctypes.c_int, [c_vp, c_i64, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_f64p, c_f64p,
+                                              ctypes.c_double]),
+    "dtc_program_finalize": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "dtc_program_num_passes": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int)]),
+    "dtc_program_workspace_bytes": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(ctypes.c_size_t)]),
+    "dtc_program_run": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_u64, c_u64, c_u64, c_vp, ctypes.c_size_t, c_vp]),
+    "dtc_program_frames": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
+                                          ctypes.POINTER(c_vp)]),
+    "dtc_materialize": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dtc_probs": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_i32p, c_vp, c_vp, c_vp]),
+    "dtc_expect_z": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp]),
+    "dtc_sample_rows": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_u64, c_i64, c_vp, c_vp]),
+    "dtc_sample_states": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_u64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "dtc_dm_init": (ctypes.c_int, [c_vp, ctypes.c_int, c_u64, c_vp]),
+    "dtc_dm_rot": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_vp]),
+    "dtc_dm_diag": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_i32p, c_f64p, ctypes.c_int, c_i32p, c_i32p,
+                                   c_f64p, c_vp]),
+    "dtc_dm_pauli_channel": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                            ctypes.c_double, c_vp]),
+    "dtc_dm_probs": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_i32p, c_vp, c_vp]),
+    "dtc_shard_pack": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i32p, c_vp]),
+    "dtc_shard_unpack": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i32p, c_vp]),
+}
+EXPORTED = tuple(_SIGS)
+
+ENGINE_AUTO, ENGINE_GENERIC, ENGINE_TILE = 0, 1, 2
+_lib = None
+
+
+def load():
+    """Load libdtcsim.so; fail loudly if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"dtcsim CUDA library not found at {LIB_PATH}; build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().dtc_last_error().decode(errors="replace")
+        if rc in (-1, -3):
+            raise ValueError(f"dtcsim: {msg}")
+        raise RuntimeError(f"dtcsim (status {rc}): {msg}")
+
+
+def i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(c_i32p)
+
+
+def f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(c_f64p)
+
+
+class ProgramHandle:
+    """Owns a dtc_program*; created from a plan.Program."""
+
+    def __init__(self, prog, device, engine=ENGINE_AUTO, n_local=None):
+        lib = load()
+        self.prog = prog
+        self.n_local = prog.n if n_local is None else n_local
+        self.device = device
+        self._h = c_vp()
+        check(lib.dtc_program_create(prog.n, prog.n_layers, ctypes.byref(self._h)))
+        try:
+            ev = prog.arrays()
+            keep = [i32(ev["type"]), i32(ev["layer"]), i32(ev["q0"]), i32(ev["q1"]), i32(ev["slot"]),
+                    f64(ev["val"]), f64(ev["probs"])]
+            check(lib.dtc_program_set_events(self._h, len(ev["type"]), *[k[1] for k in keep],
+                                             float(prog.global_phase)))
+            check(lib.dtc_program_finalize(self._h, int(device), int(engine), int(self.n_local)))
+        except Exception:
+            self.close()
+            raise
+
+    @property
+    def num_passes(self):
+        n = ctypes.c_int(0)
+        check(load().dtc_program_num_passes(self._h, ctypes.byref(n)))
+        return n.value
+
+    def workspace_bytes(self, n_traj):
+        b = ctypes.c_size_t(0)
+        check(load().dtc_program_workspace_bytes(self._h, int(n_traj), ctypes.byref(b)))
+        return b.value
+
+    def run(self, state_ptr, n_traj, traj_offset, seed, ws_ptr, ws_bytes, stream, init_index=0, rank_bits=0):
+        check(load().dtc_program_run(self._h, state_ptr, int(n_traj), int(traj_offset),
+                                     int(seed) & 0xFFFFFFFFFFFFFFFF, int(init_index), int(rank_bits),
+                                     ws_ptr, ws_bytes, stream))
+
+    def frames(self, ws_ptr, n_traj):
+        fx, fz, ph = c_vp(), c_vp(), c_vp()
+        check(load().dtc_program_frames(self._h, ws_ptr, int(n_traj), ctypes.byref(fx), ctypes.byref(fz),
+                                        ctypes.byref(ph)))
+        return fx.value, fz.value, ph.value
+
+    def close(self):
+        if self._h:
+            load().dtc_program_destroy(self._h)
+            self._h = c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -210,6 +210,68 @@ static inline void dtc_classify_terms(DtcTilePass& T, const DtcLayer& L) {
 }
 
 // ---- pass schedule -----------------------------------------------------------------------------
+// Qubits are partitioned once into groups of <= 10 (index order over the frequently rotated qubits;
+// rarely rotated ones -- e.g. the Hadamard-test ancilla -- fill spare slots or get their own group).
+// A pass works on one group G: it applies the remaining rotations of layer j on G; if that completes
+// R_j it also applies D_j and, looking ahead, the rotations of R_{j+1} on G.  With two groups this is
+// one state sweep per layer:  R_j|B D_j R_{j+1}|B  then  R_{j+1}|A D_{j+1} R_{j+2}|A  ...
+struct DtcGroup {
+    u64 members;
+    int tb[DTC_TILE_BITS];
+    int s2_lo;
+};
+
+static inline void dtc_add_group(std::vector<DtcGroup>& out, u64 members, int n_local) {
+    if (!members) return;
+    DtcGroup g;
+    g.members = members;
+    if (dtc_build_tile(members, n_local, g.tb, &g.s2_lo)) {
+        out.push_back(g);
+        return;
+    }
+    const int half = dtc_popc(members) / 2;           // cannot happen for a single qubit
+    const u64 lo = dtc_lowest_bits(members, half);
+    dtc_add_group(out, lo, n_local);
+    dtc_add_group(out, members & ~lo, n_local);
+}
+
+static inline std::vector<DtcGroup> dtc_make_groups(const DtcProgramHost& P) {
+    const int n = P.n_local;
+    int count[DTC_MAXQ] = {0};
+    int maxc = 0;
+    for (const DtcLayer& L : P.layers)
+        for (int q = 0; q < n; ++q)
+            if ((L.rot_any >> q) & 1ull) { ++count[q]; if (count[q] > maxc) maxc = count[q]; }
+    std::vector<u64> chunks;
+    u64 cur = 0;
+    for (int q = 0; q < n; ++q) {
+        if (count[q] == 0 || count[q] * 2 <= maxc) continue;
+        cur |= 1ull << q;
+        if (dtc_popc(cur) == 10) { chunks.push_back(cur); cur = 0; }
+    }
+    if (cur) chunks.push_back(cur);
+    u64 rare = 0;
+    for (int q = 0; q < n; ++q) {
+        if (count[q] == 0 || count[q] * 2 > maxc) continue;
+        // nearest chunk with a free slot whose span would still fit a tile, else the "rare" group
+        bool placed = false;
+        for (size_t c = 0; c < chunks.size() && !placed; ++c) {
+            if (dtc_popc(chunks[c]) >= 10) continue;
+            int tb[DTC_TILE_BITS], s2;
+            if (dtc_build_tile(chunks[c] | (1ull << q), n, tb, &s2)) { chunks[c] |= 1ull << q; placed = true; }
+        }
+        if (!placed) {
+            rare |= 1ull << q;
+            if (dtc_popc(rare) == 10) { chunks.push_back(rare); rare = 0; }
+        }
+    }
+    if (rare) chunks.push_back(rare);
+    std::vector<DtcGroup> groups;
+    for (u64 c : chunks) dtc_add_group(groups, c, n);
+    if (groups.empty()) dtc_add_group(groups, 1ull, n);      // circuit without rotations
+    return groups;
+}
+
 static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
     const int M = P.n_layers, n = P.n_local;
     const u64 local_mask = (n >= 64) ? ~0ull : ((1ull << n) - 1);
@@ -219,59 +281,60 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
             err = "rotation on a non-local (global) qubit: exchange qubits before this layer";
             return false;
         }
+    const std::vector<DtcGroup> groups = dtc_make_groups(P);
     int j = 0;
     u64 done = 0;
     while (j < M) {
         const DtcLayer& L = P.layers[j];
         const u64 rem = L.rot_any & ~done;
-        u64 SA = dtc_lowest_bits(rem, 10);
-        const bool complete = (rem & ~SA) == 0;
-        u64 S = SA, SB = 0;
-        if (complete && j + 1 < M) {
-            const u64 next = P.layers[j + 1].rot_any;
-            u64 fill = dtc_lowest_bits(next & ~S, 10 - dtc_popc(S));
-            S |= fill;
-            SB = next & S;
+        const u64 next = (j + 1 < M) ? P.layers[j + 1].rot_any : 0ull;
+        // groups that still have work in this layer; the one kept for last gets D_j + look-ahead
+        int pick = -1, n_cand = 0, best_keep = -1;
+        for (size_t k = 0; k < groups.size(); ++k) {
+            if (!(rem & groups[k].members)) continue;
+            ++n_cand;
+            const int ov = dtc_popc(next & groups[k].members);
+            if (best_keep < 0 || ov > dtc_popc(next & groups[best_keep].members)) best_keep = (int)k;
         }
+        bool complete;
+        if (n_cand == 0) {                       // only D_j (+ look-ahead) left
+            complete = true;
+            for (size_t k = 0; k < groups.size(); ++k)
+                if (pick < 0 || dtc_popc(next & groups[k].members) > dtc_popc(next & groups[pick].members)) pick = (int)k;
+        } else if (n_cand == 1) {
+            complete = true;
+            pick = best_keep;
+        } else {
+            complete = false;
+            for (size_t k = 0; k < groups.size(); ++k)
+                if ((rem & groups[k].members) && (int)k != best_keep) { pick = (int)k; break; }
+        }
+        const DtcGroup& G = groups[pick];
+        const u64 SA = rem & G.members;
+        const u64 SB = complete ? (next & G.members) : 0ull;
         DtcTilePass T;
         memset(&T, 0, sizeof(T));
-        if (!dtc_build_tile(S, n, T.tb, &T.s2_lo)) {
-            // retry without look-ahead fill
-            S = SA;
-            SB = (complete && j + 1 < M) ? (P.layers[j + 1].rot_any & S) : 0;
-            if (!dtc_build_tile(S, n, T.tb, &T.s2_lo)) {
-                // last resort: a single active qubit always fits
-                SA = dtc_lowest_bits(rem, 1);
-                S = SA;
-                SB = 0;
-                if (!dtc_build_tile(S, n, T.tb, &T.s2_lo)) {
-                    err = "internal: cannot build a tile";
-                    return false;
-                }
-            }
-        }
-        const bool comp2 = (rem & ~SA) == 0;
+        memcpy(T.tb, G.tb, sizeof(T.tb));
+        T.s2_lo = G.s2_lo;
         T.n_local = n;
         T.n_total = P.n_qubits;
         T.layerA = SA ? j : -1;
-        T.layerD = comp2 ? j : -1;
-        T.layerB = (comp2 && SB) ? j + 1 : -1;
+        T.layerD = complete ? j : -1;
+        T.layerB = (complete && SB) ? j + 1 : -1;
         for (int l = 0; l < DTC_TILE_BITS; ++l) {
             const int q = T.tb[l];
             T.t1[l] = ((SA >> q) & 1ull) ? L.rtan[q] : 0.0;
-            T.t2[l] = (T.layerB >= 0 && ((SB >> q) & 1ull)) ? P.layers[j + 1].rtan[q] : 0.0;
-        }
-        if (T.layerD >= 0) dtc_classify_terms(T, L);
-        // sanity: active bits must sit inside the register windows
-        for (int l = 0; l < DTC_TILE_BITS; ++l)
+            T.t2[l] = ((SB >> q) & 1ull) ? P.layers[j + 1].rtan[q] : 0.0;
             if ((T.t1[l] != 0.0 || T.t2[l] != 0.0) && (l < T.s2_lo || l >= T.s2_lo + 10)) {
                 err = "internal: active qubit outside the tile window";
                 return false;
             }
+        }
+        if (T.layerD >= 0) dtc_classify_terms(T, L);
         P.passes.push_back(T);
-        if (comp2) {
+        if (complete) {
             ++j;
-            done = (T.layerB >= 0) ? SB : 0;
+            done = SB;
         } else {
             done |= SA;
         }

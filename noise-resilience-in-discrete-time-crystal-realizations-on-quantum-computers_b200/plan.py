@@ -62,7 +62,9 @@ class Program:
     def __init__(self):
         self.n = 0
         self.n_clbits = 0
-        self.active = []            # original (wide-circuit) index of each simulated qubit
+        self.active = []            # original (wide-circuit) index of each compacted qubit
+        self.order = []             # order[bit] = compacted qubit stored at index bit `bit`
+        self.bit_of = []            # bit_of[compacted qubit] = index bit
         self.n_layers = 1
         self.ev_type = []
         self.ev_layer = []
@@ -99,6 +101,50 @@ def compact(circ):
     used = sorted({q for op in circ.ops if op.name != "barrier" for q in op.qubits})
     remap = {q: i for i, q in enumerate(used)}
     return remap, used
+
+
+def choose_bit_order(n, pairs):
+    """Internal qubit -> index-bit assignment that keeps interacting qubits close (Cuthill-McKee).
+
+    The simulator is free to store qubit k at any bit of the basis index.  The fused kernel keeps
+    two-body phases in two shared-memory tables over *adjacent* tile bits, so a chain should occupy
+    consecutive bits (the snake layout of fast.py:177 scatters it).  Pendant qubits hanging off a
+    branching node (the Hadamard-test ancilla) go last so they do not split the chain.
+    Returns order[bit] = compacted qubit index.
+    """
+    adj = [set() for _ in range(n)]
+    for a, b in pairs:
+        if a != b:
+            adj[a].add(b)
+            adj[b].add(a)
+    deg = [len(a) for a in adj]
+    pend = [v for v in range(n) if deg[v] == 1 and deg[next(iter(adj[v]))] >= 3]
+    core = [v for v in range(n) if v not in pend]
+    cdeg = {v: len([w for w in adj[v] if w not in pend]) for v in core}
+    seen, order = set(), []
+    for start in sorted(core, key=lambda v: (cdeg[v] == 0, 0)):   # keep index order among components
+        if start in seen:
+            continue
+        # component of `start`, begin at its lowest-degree node (lowest index on ties)
+        comp, stack = [], [start]
+        cs = {start}
+        while stack:
+            v = stack.pop()
+            comp.append(v)
+            for w in adj[v]:
+                if w not in cs and w not in pend:
+                    cs.add(w)
+                    stack.append(w)
+        root = min(comp, key=lambda v: (cdeg[v], v))
+        queue = [root]
+        seen.add(root)
+        while queue:
+            v = queue.pop(0)
+            order.append(v)
+            for w in sorted((w for w in adj[v] if w not in seen and w not in pend), key=lambda w: (cdeg[w], w)):
+                seen.add(w)
+                queue.append(w)
+    return order + sorted(pend)
 
 
 def _fuse_cx_rz_cx(ops, noisy):
@@ -285,7 +331,7 @@ def _segment_dm(prims):
     return out
 
 
-def compile_circuit(circuit, noise_model=None, want_dm=False):
+def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True):
     """Compile a (transpiled) circuit + noise model into a :class:`Program`.
 
     Raises ValueError for anything the device path cannot execute exactly (unsupported gate,
@@ -295,15 +341,23 @@ def compile_circuit(circuit, noise_model=None, want_dm=False):
     for op in circ.ops:
         if op.name not in SUPPORTED:
             raise ValueError(f"unsupported instruction {op.name!r}")
-    remap, used = compact(circ)
+    cmap, used = compact(circ)
     n = len(used)
     if n == 0:
         raise ValueError("circuit has no active qubits")
     if n > 62:
         raise ValueError(f"{n} active qubits exceed the 62-qubit index limit")
+    pairs = [(cmap[o.qubits[0]], cmap[o.qubits[1]]) for o in circ.ops if len(o.qubits) == 2]
+    order = choose_bit_order(n, pairs) if reorder else list(range(n))
+    bit_of = [0] * n
+    for bit, cq in enumerate(order):
+        bit_of[cq] = bit
+    remap = {q: bit_of[c] for q, c in cmap.items()}
     b = _Builder(n)
     prog = b.p
     prog.active = used
+    prog.order = order
+    prog.bit_of = bit_of
     prog.n_clbits = circ.num_clbits
     prog.global_phase = float(circ.global_phase)
 

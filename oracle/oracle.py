@@ -360,3 +360,50 @@ def compute_z_expectation(counts, num_qubits):
         p0 = sum(c for b, c in counts.items() if b[::-1][k] == "0")
         out.append((p0 - (total - p0)) / total)
     return out
+
+
+# ----------------------------------------------------------------------------- light-cone exact values
+def lightcone_zq(L, g, hs, phis, t, q, p, echo=False, polarization="x", period_fn=None):
+    """Exact noisy <Z_q> after t periods (forward) or t forward + t inverse periods (echo) for a
+    vacuum start, computed on the sub-chain [q-r, q+r], r = n_periods-1.
+
+    RZ/RZZ commute with Z_q, so the support of the Heisenberg-evolved Z_q grows by one site per
+    period only through the kick layer; bonds leaving the sub-chain drop out exactly.  The Hadamard
+    test signal of fast.py:125-147 is (1-p)^6 * <Z_q> (six depolarized ancilla u2 gates).
+    period_fn(step) -> list of high-level gates on sites 1..L (defaults to dtc_circuits.uf_gates).
+    """
+    from . import dtc_circuits as C
+    n_periods = 2 * t if echo else t
+    if n_periods == 0:
+        return 1.0
+    r = n_periods - 1
+    lo, hi = max(0, q - r), min(L - 1, q + r)
+    sites = list(range(lo, hi + 1))
+    m = len(sites)
+    pos = {s: i for i, s in enumerate(sites)}
+
+    def restrict(gates):
+        out = []
+        for name, qs, params, cs in gates:
+            ss = [x - 1 for x in qs]                      # uf_gates uses circuit qubits 1..L
+            if all(s in pos for s in ss):
+                out.append((name, tuple(pos[s] for s in ss), params, cs))
+        return out
+
+    def period(step):
+        if period_fn is not None:
+            return period_fn(step)
+        return C.uf_gates(L, g, phis, hs, polarization, time_step=step)
+
+    ops = []
+    for step in range(t):
+        ops.extend(restrict(period(step)))
+    if echo:
+        for step in range(t - 1, -1, -1):
+            ops.extend(restrict(C.inverse_gates(period(step))))
+    low = C.lower_level0(ops)
+    noise = PauliNoise.depolarizing(p) if p else None
+    rho = run_density_matrix(low, m, noise)
+    diag = np.real(np.diag(rho))
+    z = 1.0 - 2.0 * _bit(m, pos[q])
+    return float(np.dot(diag, z))

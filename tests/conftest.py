@@ -1,0 +1,57 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+GOLDEN = os.path.join(HERE, "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def disorder():
+    out = {}
+    for L in (4, 20):
+        out[L] = (pd.read_csv(os.path.join(GOLDEN, f"hs_L{L}.csv")).values,
+                  pd.read_csv(os.path.join(GOLDEN, f"phis_L{L}.csv")).values)
+    return out
+
+
+@pytest.fixture(scope="session")
+def known():
+    with open(os.path.join(GOLDEN, "known_answers.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="session")
+def gate_counts():
+    with open(os.path.join(GOLDEN, "gate_counts.json")) as fh:
+        return json.load(fh)
+
+
+def golden_csv(name):
+    return pd.read_csv(os.path.join(GOLDEN, name))

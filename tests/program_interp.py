@@ -184,3 +184,22 @@ def run_dm(prog, n):
                 f = rho[0, partner]
                 rho = ((1 - px - py - pz) * e + px * f + py * s * f + pz * s * e)[None, :]
     return rho[0].reshape(d, d).T            # [row, col]
+
+
+def to_circuit_order(psi, prog):
+    """psi [..., 2^n] in the program's internal bit order -> compacted circuit qubit order."""
+    n = prog.n
+    if list(prog.order) == list(range(n)):
+        return psi
+    lead = psi.shape[:-1]
+    v = psi.reshape(lead + (2,) * n)                    # axis (len(lead) + n-1-b) <-> bit b
+    nl = len(lead)
+    # new bit c (compacted qubit c) takes old bit prog.bit_of[c]
+    axes = list(range(nl)) + [nl + n - 1 - prog.bit_of[n - 1 - k] for k in range(n)]
+    return np.ascontiguousarray(np.transpose(v, axes)).reshape(lead + (1 << n,))
+
+
+def dm_to_circuit_order(rho, prog):
+    n = prog.n
+    r = to_circuit_order(rho, prog)                     # columns
+    return to_circuit_order(r.T, prog).T                # rows

@@ -1,0 +1,107 @@
+"""The CUDA kernels' per-thread code executed on the CPU (tests/emul) against the oracle.
+
+dtc_hd.cuh / dtc_core.hpp are compiled with g++ and every CTA of k_tile_pass is run thread by thread,
+phase by phase.  This validates index maps, swizzles, phase tables, sign masks and the pass scheduler
+before any GPU time is spent; the -m gpu tests then check the real kernels through the C ABI.
+"""
+import numpy as np
+import pytest
+
+import dtcsim
+import emu
+import program_interp as PI
+import refcircuits as RC
+from dtcsim import compile_circuit
+from oracle import oracle as O
+from test_planner import _random_circuit
+
+
+def _check(circ, nm, onoise, seed, n_traj, engine, tol=1e-12, offset=3):
+    prog = compile_circuit(circ, nm)
+    oc, na, _ = O.compact_ops(RC.ops_of(circ), circ.num_qubits)
+    st, fx, fz, ph, npass = emu.run(prog, n_traj=n_traj, traj_offset=offset, seed=seed, engine=engine)
+    psi = PI.to_circuit_order(PI.materialize_frame(st, prog.n, fx, fz, ph), prog)
+    trajs = np.arange(offset, offset + n_traj)
+    ref = O.run_trajectories(oc, na, onoise, seed, trajs) if nm is not None else \
+        np.repeat(O.run_statevector(oc, na)[None], n_traj, 0)
+    assert np.abs(psi - ref).max() < tol
+    return prog, npass
+
+
+@pytest.mark.parametrize("L,t,echo,pol,layout,state", [
+    (11, 2, False, "x", True, "vacuum"),     # n = 12: one tile per state
+    (12, 3, True, "x", False, "neel"),       # natural qubit order
+    (13, 2, False, "xy", True, "vacuum"),    # two kick layers per period, snake layout
+    (13, 2, True, "y", True, "vacuum"),
+    (14, 1, True, "yx", True, "neel"),
+])
+def test_tile_engine_reference_circuits(disorder, L, t, echo, pol, layout, state):
+    hs, phis = disorder[20][0][1][:L], disorder[20][1][1][:L - 1]
+    circ = RC.transpiled(RC.qc_body(state, L, 0.97, hs, phis, t, L // 2, echo, pol), layout=layout)
+    _check(circ, RC.noise_model(0.05), O.PauliNoise.depolarizing(0.05), 77, 3, engine=2)
+    _check(circ, None, None, 0, 1, engine=2)
+
+
+def test_generic_engine_small(disorder):
+    hs, phis = disorder[4][0][0], disorder[4][1][0]
+    circ = RC.transpiled(RC.qc_body("vacuum", 4, 0.84, hs, phis, 3, 2, True))
+    _check(circ, RC.noise_model(0.05), O.PauliNoise.depolarizing(0.05), 5, 16, engine=1)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_tile_engine_random_circuits(seed):
+    """General gates: exercises extra / cross / outer two-body terms and odd active sets."""
+    rng = np.random.default_rng(100 + seed)
+    n = 12 + seed % 2
+    circ = _random_circuit(rng, n, 70)
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_quantum_error(dtcsim.depolarizing_error(0.3, 1), ["u1", "u2", "u3", "h"])
+    onoise = O.PauliNoise.depolarizing(0.3, names=("u1", "u2", "u3", "h"))
+    _check(circ, nm, onoise, seed, 2, engine=2, tol=1e-11)
+
+
+def test_heavy_noise_flips_every_sign(disorder):
+    """p = 1 (always a Pauli): every sign mask is exercised."""
+    L = 11
+    hs, phis = disorder[20][0][2][:L], disorder[20][1][2][:L - 1]
+    circ = RC.transpiled(RC.qc_body("vacuum", L, 0.97, hs, phis, 2, L // 2, True, "xy"))
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_quantum_error(dtcsim.pauli_error([("X", 0.3), ("Y", 0.3), ("Z", 0.4)]), ["u1", "u2", "u3"])
+    onoise = O.PauliNoise({k: (0.3, 0.3, 0.4) for k in ("u1", "u2", "u3")})
+    _check(circ, nm, onoise, 11, 3, engine=2)
+
+
+def test_schedule_one_pass_per_period(disorder):
+    """Bulk of the DTC circuit: each fused pass completes one layer (R|B D R'|B then R'|A D' R''|A ...)."""
+    L = 20
+    hs, phis = disorder[20][0][0], disorder[20][1][0]
+    circ = RC.transpiled(RC.qc_body("vacuum", L, 0.97, hs, phis, 29, 10, True))
+    prog = compile_circuit(circ, RC.noise_model())
+    rows, n = emu.schedule(prog)
+    assert n <= prog.n_layers + 10, (n, prog.n_layers)
+    bulk = rows[(rows[:, 1] >= 0) & (rows[:, 2] >= 0) & (rows[:, 3] >= 0)]
+    assert len(bulk) >= 50
+    assert (bulk[:, 6] == 0).sum() >= len(bulk) - 8      # chain bonds live in the two tables (no "extra" terms)
+
+
+def test_sharded_rank_bits(disorder):
+    """Top qubits global: diagonal terms on them need no communication (rank bits enter the phases)."""
+    rng = np.random.default_rng(5)
+    n, n_local = 14, 12
+    c = dtcsim.QuantumCircuit(n, 0)
+    for layer in range(3):
+        for q in range(n_local):
+            c.rx(rng.uniform(-3, 3), q)
+        for q in range(n - 1):
+            c.rzz(rng.uniform(-3, 3), q, q + 1)
+        for q in range(n):
+            c.rz(rng.uniform(-3, 3), q)
+        c.cz(13, 2)
+        c.rzz(0.7, 12, 13)
+    prog = compile_circuit(c, None, reorder=False)
+    ops = RC.ops_of(c)
+    for rank in range(4):
+        st, fx, fz, ph, _ = emu.run(prog, n_traj=1, n_local=n_local, rank_bits=rank)
+        st = PI.materialize_frame(st, n_local, fx, fz, ph)      # frames only touch local qubits here
+        ref = O.run_statevector(ops, n, init=rank << n_local)
+        assert np.abs(st[0] - ref[rank << n_local:(rank + 1) << n_local]).max() < 1e-12
