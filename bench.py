@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- Floquet periods/s on BASELINE.json config C2 (L=20 noisy forward+echo autocorrelation sweep,
+t = 0..29, 1024 Pauli trajectories per circuit, complex128) with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = the whole sweep: 60 independent circuits (fast.py:217-257) x `--trajectories` trajectories
+= 1305 x 1024 period applications.  `value` is device-resident throughput (programs compiled and
+uploaded, state buffers allocated; timed with CUDA events); `e2e` runs the same sweep through the
+public AerSimulator-compatible run() with host circuits in and counts out.  N > 1 (torchrun): weak
+scaling over disorder instances (config C4) -- rank r simulates row r of hs_L20/phis_L20 -- with one
+NCCL all-reduce of the autocorrelation sums at the end.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L, G, P_NOISE, QUBIT = 20, 0.97, 0.05, 10
+METRIC = "floquet_periods_per_s"
+
+
+# ------------------------------------------------------------------------------------------ workload
+def load_disorder(row):
+    import pandas as pd
+    g = os.path.join(ROOT, "tests", "golden")
+    hs = pd.read_csv(os.path.join(g, "hs_L20.csv")).values
+    phis = pd.read_csv(os.path.join(g, "phis_L20.csv")).values
+    return hs[row % len(hs)], phis[row % len(phis)]
+
+
+def qc_circuit(dtcsim, hs, phis, t, echo):
+    """The reference's qc_qiskit circuit body (fast.py:125-147) + its level-0 transpile (fast.py:176-190)."""
+    circ = dtcsim.QuantumCircuit(L + 1, 1)
+    circ.h(0)
+    circ.cz(QUBIT + 1, 0)
+    uf = dtcsim.QuantumCircuit(L + 1)
+    for i in range(L):
+        uf.rx(np.pi * G, i + 1)
+    for i in range(0, L - 1, 2):
+        uf.rzz(phis[i], i + 1, i + 2)
+    for i in range(1, L - 1, 2):
+        uf.rzz(phis[i], i + 1, i + 2)
+    for i in range(L):
+        uf.rz(hs[i], i + 1)
+    for _ in range(t):
+        circ.append(uf, range(L + 1))
+    if echo:
+        inv = uf.inverse()
+        for _ in range(t):
+            circ.append(inv, range(L + 1))
+    circ.cz(QUBIT + 1, 0)
+    circ.h(0)
+    circ.measure(0, 0)
+    pm = dtcsim.generate_preset_pass_manager(optimization_level=0, initial_layout=dtcsim.SNAKE_LAYOUT[:L + 1],
+                                             routing_method=None)
+    return pm.run(circ)
+
+
+def sweep_points(tmax):
+    return [(t, echo) for echo in (False, True) for t in range(tmax)]
+
+
+def periods_of(points):
+    return sum(t * (2 if echo else 1) for t, echo in points)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_sample(hs, phis, sample_points, seed=1234):
+    """The reference's CPU path restated (oracle/dtc_oracle.c): gate by gate, one trajectory per shot,
+    complex128, OpenMP over amplitudes.  Returns (periods, seconds, cores)."""
+    from oracle import c_oracle as CO
+    from oracle import dtc_circuits as C
+    from oracle import oracle as O
+    noise = O.PauliNoise.depolarizing(P_NOISE)
+    buf = np.empty(1 << (L + 1), dtype=np.complex128)
+    jobs = []
+    for t, echo in sample_points:
+        ops, _, _ = C.autocorr_gates("vacuum", L, G, hs, phis, t, QUBIT, echo)
+        oc, na, _ = O.compact_ops(C.lower_level0(ops, C.SNAKE_LAYOUT), 31)
+        jobs.append((oc, na))
+    t0 = time.perf_counter()
+    for i, (oc, na) in enumerate(jobs):
+        CO.run_trajectory(oc, na, noise, seed, i, out=buf)
+    dt = time.perf_counter() - t0
+    return periods_of(sample_points), dt, CO.threads()
+
+
+CPU_SAMPLE = [(5, False), (5, True), (15, False), (15, True), (25, False)]   # 85 periods, one trajectory each
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    hs, phis = load_disorder(0)
+    for _ in range(args.warmup):
+        cpu_sample(hs, phis, CPU_SAMPLE[:1])
+    tot_p, tot_s, cores = 0, 0.0, 1
+    for _ in range(args.steps):
+        p, s, cores = cpu_sample(hs, phis, CPU_SAMPLE)
+        tot_p += p
+        tot_s += s
+    val = tot_p / tot_s
+    sample = f"{len(CPU_SAMPLE)} circuits (t,echo)={CPU_SAMPLE}, 1 trajectory each, n=21, gate-by-gate"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "periods/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
+            "data": "synthetic", "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": "periods/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "periods/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"C2: L=20 (n=21) kicked-Ising DTC, g=0.97, depolarizing p=0.05 on u1/u2/u3, forward+echo "
+                        f"autocorr t=0..{args.tmax - 1} ({2 * args.tmax} circuits), {args.trajectories} Pauli trajectories each",
+            "tmax": args.tmax, "trajectories": args.trajectories, "state_bytes": 16 << (L + 1),
+            "l2_policy": "inputs larger than L2: each sweep streams trajectories x 32 MiB states",
+            "parallelism": f"disorder instances x{args.gpus} (weak), allreduce of sums"}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import dtcsim
+    from dtcsim import backend, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = backend.DeviceContext(local)
+    hs, phis = load_disorder(rank)                      # weak scaling: one disorder instance per rank (C4)
+    points = sweep_points(args.tmax)
+    noise = dtcsim.NoiseModel()
+    noise.add_all_qubit_quantum_error(dtcsim.depolarizing_error(P_NOISE, 1), ["u1", "u2", "u3"], warnings=False)
+    circuits = [qc_circuit(dtcsim, hs, phis, t, echo) for t, echo in points]
+    nm = dtcsim.as_noise_model(noise)
+    progs = [dtcsim.compile_circuit(c, nm) for c in circuits]
+    handles = [capi.ProgramHandle(p, ctx.index) for p in progs]
+    for h in handles:
+        h.set_profiling(True)
+    NT = args.trajectories
+    nmax = max(p.n for p in progs)
+    per = 16 << nmax
+    bt = max(1, min(NT, int(0.6 * ctx.free_bytes()) // per))
+    state = ctx.empty(bt << nmax, torch.complex128)
+    sums = torch.zeros(len(points), 2, dtype=torch.float64, device=ctx.device)
+    launches = [0]
+
+    def step(seed):
+        sums.zero_()
+        for i, (prog, h) in enumerate(zip(progs, handles)):
+            for a in range(0, NT, bt):
+                nt = min(bt, NT - a)
+                batch = backend.evolve(ctx, prog, nt, a, seed + i, handle=h, state=state)
+                pr = batch.probs([prog.measures[0][0]])
+                ez = pr[:, 0] - pr[:, 1]
+                sums[i, 0] += ez.sum()
+                sums[i, 1] += (ez * ez).sum()
+                launches[0] += 2 + h.num_passes + 1
+        if dist is not None:
+            dist.all_reduce(sums)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        step(1000 + w)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches[0] = 0
+    pass_ms, pass_n = 0.0, 0
+    e0.record()
+    for k in range(args.steps):
+        step(1234 + k)
+        if k == args.steps - 1:
+            e1.record()
+    sync_all()
+    for h, prog in zip(handles, progs):                 # kernel-only time of the last step's sweeps
+        if prog.n >= 12:
+            ms, n = h.pass_time()
+            pass_ms += ms
+            pass_n += n
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
+    if dist is not None:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total.item()) / args.steps
+    periods_step = periods_of(points) * NT * world
+    value = periods_step / (ms_step * 1e-3)
+    gpu_launches = launches[0]
+    autocorr = (sums[:, 0] / (NT * world)).cpu().numpy()
+
+    # ---- roofline of the dominant kernel (k_tile_pass): algorithmic bytes per launch / launch duration
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        with open(peaks_file) as fh:
+            peak, peak_src = float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    last_batch = NT - ((NT - 1) // bt) * bt              # pass_time() refers to each handle's last run
+    bytes_per_launch = 2 * 16 * (1 << nmax) * last_batch           # one read + one write of the batch of states
+    roof = None
+    if pass_n:
+        avg_ms = pass_ms / pass_n
+        ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": "k_tile_pass", "avg_launch_ms": avg_ms, "launches_timed": pass_n,
+                "bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
+                "periods_frac": (value / world) * (2 * 16 * (1 << (L + 1))) / (peak * 1e9)}
+
+    # ---- end to end through the public API (host circuits in, counts out)
+    e2e = None
+    if not args.no_e2e:
+        sim = dtcsim.AerSimulator(noise_model=noise, device="GPU", cuStateVec_enable=True, cuda_device=local)
+        h2d = sum(sum(a.nbytes for a in p.arrays().values()) + p.n_layers * 4616 for p in progs)
+        d2h = len(points) * NT * (4 + 16)
+
+        def e2e_pass(seed):
+            out = []
+            for c in circuits:
+                counts = sim.run(c, shots=NT, seed_simulator=seed).result().get_counts(c)
+                out.append(backend.compute_z_expectation(counts, 1)[0])
+            return out
+
+        e2e_pass(77)
+        sync_all()
+        t0 = time.perf_counter()
+        res = e2e_pass(1234)
+        sync_all()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=ctx.device)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": periods_step / float(dt.item()), "unit": "periods/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "seconds": float(dt.item()), "timer": "host wall clock around run() calls",
+               "autocorr_t1": res[1] if len(res) > 1 else None}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu:
+            p, s, cores = cpu_sample(hs, phis, CPU_SAMPLE)
+            cpu = {"value": p / s, "unit": "periods/s", "cores": cores, "kind": "port",
+                   "sample": f"{len(CPU_SAMPLE)} circuits {CPU_SAMPLE}, 1 trajectory each ({p} periods), n=21, gate-by-gate C/OpenMP oracle"}
+        line = {"metric": METRIC, "value": value, "unit": "periods/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "complex128", "data": "synthetic", "config": workload_config(args),
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+                "passes_per_sweep": int(sum(h.num_passes for h in handles)), "periods_per_sweep": periods_of(points),
+                "autocorr_forward_t1_t2": [float(autocorr[1]), float(autocorr[2])] if args.tmax > 2 else None}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--trajectories", type=int, default=1024)
+    ap.add_argument("--tmax", type=int, default=30, help="sweep t = 0..tmax-1 (30 = BASELINE config)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

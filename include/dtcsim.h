@@ -82,6 +82,12 @@ int dtc_program_run(dtc_program *p, void *state, int64_t n_traj, int64_t traj_of
 int dtc_program_frames(const dtc_program *p, void *workspace, int64_t n_traj,
                        uint64_t **fx, uint64_t **fz, int32_t **ph);
 
+/* Kernel timing for roofline accounting: when enabled, dtc_program_run() brackets its pass loop with
+ * CUDA events on the launching stream; dtc_program_pass_time() waits for the last run and returns the
+ * elapsed milliseconds and the number of state-sweep launches in that run. */
+int dtc_program_set_profiling(dtc_program *p, int enable);
+int dtc_program_pass_time(dtc_program *p, float *ms, int *n_launches);
+
 /* ---- state utilities ---------------------------------------------------------------------- */
 /* In-place psi' -> psi_true for each trajectory (used for amplitude-level parity / save_statevector). */
 int dtc_materialize(void *state, int n_local, int64_t n_traj, const uint64_t *fx, const uint64_t *fz,

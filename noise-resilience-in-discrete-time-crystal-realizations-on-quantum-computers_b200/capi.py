@@ -31,6 +31,8 @@ _SIGS = {
     "dtc_program_run": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_u64, c_u64, c_u64, c_vp, ctypes.c_size_t, c_vp]),
     "dtc_program_frames": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
                                           ctypes.POINTER(c_vp)]),
+    "dtc_program_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "dtc_program_pass_time": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "dtc_materialize": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dtc_probs": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_i32p, c_vp, c_vp, c_vp]),
     "dtc_expect_z": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp]),
@@ -123,6 +125,15 @@ class ProgramHandle:
         check(load().dtc_program_run(self._h, state_ptr, int(n_traj), int(traj_offset),
                                      int(seed) & 0xFFFFFFFFFFFFFFFF, int(init_index), int(rank_bits),
                                      ws_ptr, ws_bytes, stream))
+
+    def set_profiling(self, enable=True):
+        check(load().dtc_program_set_profiling(self._h, int(bool(enable))))
+
+    def pass_time(self):
+        """(milliseconds, launches) of the state-sweep loop of the last run (waits for it)."""
+        ms, n = ctypes.c_float(0), ctypes.c_int(0)
+        check(load().dtc_program_pass_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     def frames(self, ws_ptr, n_traj):
         fx, fz, ph = c_vp(), c_vp(), c_vp()

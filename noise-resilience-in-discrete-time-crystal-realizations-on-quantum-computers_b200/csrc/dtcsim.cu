@@ -33,6 +33,9 @@ struct dtc_program {
     DtcProgramHost h;
     DtcEvent* d_events = nullptr;
     DtcLayer* d_layers = nullptr;
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_launches = 0;
 };
 
 // ------------------------------------------------------------------------------------ kernels
@@ -406,6 +409,8 @@ int dtc_program_destroy(dtc_program* p) {
     if (!p) return DTC_OK;
     if (p->d_events) cudaFree(p->d_events);
     if (p->d_layers) cudaFree(p->d_layers);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
     delete p;
     return DTC_OK;
 }
@@ -509,6 +514,8 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     const size_t sbytes = ((size_t)n_traj << h.n_local) * sizeof(double2);
     CUDA_TRY(cudaMemsetAsync(state, 0, sbytes, s));
     k_init_basis<<<(unsigned)((n_traj + 127) / 128), 128, 0, s>>>((double2*)state, h.n_local, n_traj, init_index);
+    if (p->profiling) CUDA_TRY(cudaEventRecord(p->ev0, s));
+    p->last_launches = (h.engine == DTC_ENGINE_TILE) ? (int)h.passes.size() : (int)h.gsteps.size();
     if (h.engine == DTC_ENGINE_TILE) {
         const long long grid = n_traj << (h.n_local - DTC_TILE_BITS);
         if (grid > 0x7fffffffLL) return fail(DTC_ERR_INVALID, "batch too large for one launch");
@@ -532,7 +539,26 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
             }
         }
     }
+    if (p->profiling) CUDA_TRY(cudaEventRecord(p->ev1, s));
     CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+int dtc_program_set_profiling(dtc_program* p, int enable) {
+    if (!p) return fail(DTC_ERR_INVALID, "program is NULL");
+    if (enable && !p->ev0) {
+        CUDA_TRY(cudaEventCreate(&p->ev0));
+        CUDA_TRY(cudaEventCreate(&p->ev1));
+    }
+    p->profiling = enable != 0;
+    return DTC_OK;
+}
+
+int dtc_program_pass_time(dtc_program* p, float* ms, int* n_launches) {
+    if (!p || !ms || !n_launches || !p->ev1) return fail(DTC_ERR_INVALID, "profiling not enabled");
+    CUDA_TRY(cudaEventSynchronize(p->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    *n_launches = p->last_launches;
     return DTC_OK;
 }
 

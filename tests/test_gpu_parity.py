@@ -1,0 +1,314 @@
+"""GPU parity tests: the CUDA library (through its C ABI / the AerSimulator-compatible backend) against
+the CPU oracle on identical inputs.  Tolerances (BASELINE.json north_star): noiseless and per-trajectory
+statevector amplitudes 1e-10, density-matrix expectation values 1e-8, shot/trajectory estimates 3-4 sigma.
+"""
+import numpy as np
+import pytest
+
+import dtcsim
+import program_interp as PI
+import refcircuits as RC
+from conftest import golden_csv
+from dtcsim import compile_circuit
+from oracle import c_oracle as CO
+from oracle import dtc_circuits as C
+from oracle import oracle as O
+from test_planner import _random_circuit
+
+pytestmark = pytest.mark.gpu
+
+AMP_TOL = 1e-10
+DM_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from dtcsim import backend
+    return backend.DeviceContext(0)
+
+
+def _evolve_true(ctx, prog, n_traj, offset, seed, engine=0):
+    from dtcsim import backend
+    batch = backend.evolve(ctx, prog, n_traj, offset, seed, engine=engine)
+    psi = batch.materialize().cpu().numpy()
+    return PI.to_circuit_order(psi, prog), batch
+
+
+def test_frames_bit_exact_vs_spec(ctx, disorder):
+    """Philox4x32-10 Pauli sampling + frame walk on the device == the numpy specification, bit for bit."""
+    from dtcsim import backend
+    hs, phis = disorder[20][0][0][:12], disorder[20][1][0][:11]
+    circ = RC.transpiled(RC.qc_body("neel", 12, 0.97, hs, phis, 6, 6, True, "xy"))
+    prog = compile_circuit(circ, RC.noise_model(0.2))
+    batch = backend.evolve(ctx, prog, 300, 1000, 424242)
+    fx, fz, ph = batch.frames_host()
+    layers, k_of = PI.build_layers(prog)
+    _, rfx, rfz, rph = PI.frame_walk(prog, k_of, 424242, np.arange(1000, 1300))
+    assert np.array_equal(fx, rfx) and np.array_equal(fz, rfz) and np.array_equal(ph, rph.astype(np.int32))
+    assert (fx != 0).any() and (fz != 0).any()
+
+
+@pytest.mark.parametrize("L,t,echo,pol,layout,state", [
+    (11, 2, False, "x", True, "vacuum"),
+    (12, 3, True, "x", False, "neel"),
+    (13, 2, True, "xy", True, "vacuum"),
+    (15, 2, False, "y", True, "neel"),
+])
+def test_tile_engine_trajectories_vs_oracle(ctx, disorder, L, t, echo, pol, layout, state):
+    hs, phis = disorder[20][0][1][:L], disorder[20][1][1][:L - 1]
+    circ = RC.transpiled(RC.qc_body(state, L, 0.97, hs, phis, t, L // 2, echo, pol), layout=layout)
+    oc, na, _ = O.compact_ops(RC.ops_of(circ), circ.num_qubits)
+    prog = compile_circuit(circ, RC.noise_model(0.05))
+    psi, _ = _evolve_true(ctx, prog, 6, 40, 77, engine=2)
+    ref = O.run_trajectories(oc, na, O.PauliNoise.depolarizing(0.05), 77, np.arange(40, 46))
+    assert np.abs(psi - ref).max() < AMP_TOL
+    prog0 = compile_circuit(circ, None)
+    psi0, _ = _evolve_true(ctx, prog0, 1, 0, 0, engine=2)
+    assert np.abs(psi0[0] - O.run_statevector(oc, na)).max() < AMP_TOL
+
+
+def test_generic_engine_vs_oracle(ctx, disorder):
+    hs, phis = disorder[4][0][0], disorder[4][1][0]
+    circ = RC.transpiled(RC.qc_body("vacuum", 4, 0.84, hs, phis, 5, 2, True))
+    oc, na, _ = O.compact_ops(RC.ops_of(circ), 31)
+    prog = compile_circuit(circ, RC.noise_model(0.05))
+    psi, _ = _evolve_true(ctx, prog, 64, 0, 9)
+    ref = O.run_trajectories(oc, na, O.PauliNoise.depolarizing(0.05), 9, np.arange(64))
+    assert np.abs(psi - ref).max() < AMP_TOL
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_circuits(ctx, seed):
+    rng = np.random.default_rng(200 + seed)
+    n = 12 + seed
+    circ = _random_circuit(rng, n, 80)
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_quantum_error(dtcsim.depolarizing_error(0.3, 1), ["u1", "u2", "u3", "h"])
+    onoise = O.PauliNoise.depolarizing(0.3, names=("u1", "u2", "u3", "h"))
+    oc, na, _ = O.compact_ops(RC.ops_of(circ), n)
+    prog = compile_circuit(circ, nm)
+    psi, _ = _evolve_true(ctx, prog, 3, 5, seed, engine=2)
+    ref = O.run_trajectories(oc, na, onoise, seed, np.arange(5, 8))
+    assert np.abs(psi - ref).max() < AMP_TOL
+    psi_g, _ = _evolve_true(ctx, prog, 3, 5, seed, engine=1)
+    assert np.abs(psi_g - ref).max() < AMP_TOL
+
+
+def test_full_size_L20_trajectories_vs_c_oracle(ctx, disorder):
+    """BASELINE config C2 shape (n = 21, complex128): amplitude parity on whole 2^21 states."""
+    hs, phis = disorder[20][0][0], disorder[20][1][0]
+    circ = RC.transpiled(RC.qc_body("vacuum", 20, 0.97, hs, phis, 3, 10, True))
+    oc, na, _ = O.compact_ops(RC.ops_of(circ), 31)
+    prog = compile_circuit(circ, RC.noise_model(0.05))
+    assert prog.n == 21
+    psi, batch = _evolve_true(ctx, prog, 3, 17, 1234)
+    onoise = O.PauliNoise.depolarizing(0.05)
+    for i, tr in enumerate((17, 18, 19)):
+        ref = CO.run_trajectory(oc, na, onoise, 1234, tr)
+        assert np.abs(psi[i] - ref).max() < AMP_TOL
+
+
+def test_readout_kernels(ctx, disorder):
+    """dtc_probs / dtc_expect_z / dtc_sample_states against numpy on the same states."""
+    from dtcsim import backend
+    hs, phis = disorder[20][0][3][:13], disorder[20][1][3][:12]
+    circ = RC.transpiled(RC.qc_body("vacuum", 13, 0.9, hs, phis, 2, 6, False))
+    prog = compile_circuit(circ, RC.noise_model(0.3))
+    batch = backend.evolve(ctx, prog, 16, 0, 3)
+    pz = batch.expect_z().cpu().numpy()
+    q3 = [prog.measures[0][0], 2, 7]
+    p3 = batch.probs(q3).cpu().numpy()
+    p1 = batch.probs([prog.measures[0][0]]).cpu().numpy()
+    psi = batch.materialize().cpu().numpy()
+    pr = np.abs(psi) ** 2
+    idx = np.arange(1 << prog.n)
+    for q in range(prog.n):
+        assert np.abs(pz[:, q] - pr @ (1.0 - 2.0 * ((idx >> q) & 1))).max() < 1e-12
+    col = sum(((idx >> q) & 1) << i for i, q in enumerate(q3))
+    for r in range(16):
+        assert np.abs(p3[r] - np.bincount(col, weights=pr[r], minlength=8)).max() < 1e-12
+    assert np.abs(p1.sum(1) - 1).max() < 1e-12 and np.abs(p1[:, 1] - (1 - pz[:, q3[0]]) / 2).max() < 1e-12
+
+
+def test_sample_states_distribution(ctx):
+    from dtcsim import backend
+    c = dtcsim.QuantumCircuit(13, 13)
+    c.h(0)
+    for q in range(12):
+        c.cx(q, q + 1)
+    c.measure_all()
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_quantum_error(dtcsim.pauli_error([("X", 0.5), ("I", 0.5)]), ["h"])
+    prog = compile_circuit(c, nm)
+    batch = backend.evolve(ctx, prog, 4000, 0, 11)
+    idx = batch.sample_states(11).cpu().numpy()
+    assert set(np.unique(idx)) <= {0, (1 << 13) - 1}            # GHZ: all zeros or all ones
+    frac = (idx != 0).mean()
+    assert abs(frac - 0.5) < 4 * 0.5 / np.sqrt(4000)
+
+
+# ----------------------------------------------------------------------------------- density matrix
+def test_density_matrix_known_answers(disorder, known):
+    """Reference config C1 through run(): exact DM expectation vs SURVEY 8c values (1e-8)."""
+    hs, phis = disorder[4][0][0], disorder[4][1][0]
+    sim = dtcsim.AerSimulator(noise_model=RC.noise_model(0.05), device="GPU", cuStateVec_enable=True)
+    for t, (f, e) in known["survey_8c"]["L4_g0.84_p0.05"].items():
+        for echo, want in ((False, f), (True, e)):
+            circ = RC.transpiled(RC.qc_body("vacuum", 4, 0.84, hs, phis, int(t), 2, echo), backend=sim)
+            res = sim.run(circ, shots=1024, seed_simulator=5).result()
+            assert res.data()["method"] == "density_matrix"
+            assert abs(res.expectation_z()[0] - want) < DM_TOL
+
+
+def test_density_matrix_elementwise(ctx, disorder):
+    from dtcsim import backend
+    hs, phis = disorder[20][0][0][:6], disorder[20][1][0][:5]
+    circ = RC.transpiled(RC.qc_body("neel", 6, 0.9, hs, phis, 3, 3, True, "yx"))
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_quantum_error(dtcsim.pauli_error([("X", 0.05), ("Y", 0.02), ("Z", 0.1), ("I", 0.83)]), ["u2", "u3"])
+    prog = compile_circuit(circ, nm, want_dm=True)
+    rho = backend.run_density_matrix(ctx, prog).cpu().numpy()
+    d = 1 << prog.n
+    rho = PI.dm_to_circuit_order(rho.reshape(d, d).T, prog)
+    oc, na, _ = O.compact_ops(RC.ops_of(circ), 31)
+    ref = O.run_density_matrix(oc, na, O.PauliNoise({"u2": (0.05, 0.02, 0.1), "u3": (0.05, 0.02, 0.1)}))
+    assert np.abs(rho - ref).max() < 1e-12
+    assert abs(np.trace(rho) - 1) < 1e-12
+
+
+def test_density_matrix_L12_config(disorder):
+    """BASELINE config C3: L = 12 ancilla-free chain (rho has 2^24 entries), <Z_6> vs exact light cone."""
+    hs, phis = disorder[20][0][0][:12], disorder[20][1][0][:11]
+    sim = dtcsim.AerSimulator(noise_model=RC.noise_model(0.05), method="density_matrix")
+    for t in (1, 2, 3):
+        c = dtcsim.QuantumCircuit(12, 1)
+        for _ in range(t):
+            for i in range(12):
+                c.rx(np.pi * 0.97, i)
+            for i in range(0, 11, 2):
+                c.rzz(phis[i], i, i + 1)
+            for i in range(1, 11, 2):
+                c.rzz(phis[i], i, i + 1)
+            for i in range(12):
+                c.rz(hs[i], i)
+        c.measure(6, 0)
+        low = dtcsim.lower_level0(c)
+        res = sim.run(low, shots=100, seed_simulator=1).result()
+        want = O.lightcone_zq(12, 0.97, hs, phis, t, 6, 0.05)
+        assert abs(res.expectation_z()[0] - want) < DM_TOL
+    # 20 periods: trace preserved and |<Z>| <= 1
+    c = dtcsim.QuantumCircuit(12, 1)
+    for _ in range(20):
+        for i in range(12):
+            c.rx(np.pi * 0.97, i)
+        for i in range(0, 11, 2):
+            c.rzz(phis[i], i, i + 1)
+        for i in range(1, 11, 2):
+            c.rzz(phis[i], i, i + 1)
+        for i in range(12):
+            c.rz(hs[i], i)
+    c.measure(6, 0)
+    res = sim.run(dtcsim.lower_level0(c), shots=100, seed_simulator=1).result()
+    pr = res.data()["probabilities"]
+    assert abs(sum(pr.values()) - 1) < 1e-10 and abs(res.expectation_z()[0]) < 1
+
+
+# ----------------------------------------------------------------------------------- run() / counts
+def test_counts_bit_exact_vs_oracle(disorder):
+    """Same Philox contract on both sides: get_counts() equals the oracle's counts exactly."""
+    hs, phis = disorder[4][0][0], disorder[4][1][0]
+    sim = dtcsim.AerSimulator(noise_model=RC.noise_model(0.05), device="GPU", cuStateVec_enable=True)
+    onoise = O.PauliNoise.depolarizing(0.05)
+    for t, echo, shots in ((1, False, 1024), (3, True, 1024), (2, False, 16), (4, True, 30)):
+        circ = RC.transpiled(RC.qc_body("vacuum", 4, 0.84, hs, phis, t, 2, echo), backend=sim)
+        got = sim.run(circ, shots=shots, seed_simulator=1234).result().get_counts(circ)
+        want, info = O.run_counts(RC.ops_of(circ), 31, 1, shots=shots, noise=onoise, seed=1234)
+        assert got == want, (t, echo, shots, got, want, info["method"])
+    # ideal circuit: one statevector, `shots` samples
+    sim0 = dtcsim.AerSimulator()
+    circ = RC.transpiled(RC.qc_body("vacuum", 4, 0.84, hs, phis, 3, 2, False))
+    got = sim0.run(circ, shots=500, seed_simulator=7).result().get_counts()
+    want, _ = O.run_counts(RC.ops_of(circ), 31, 1, shots=500, noise=None, seed=7)
+    assert got == want
+    # trajectories at n = 12 (shots < 2^n)
+    hs, phis = disorder[20][0][0][:11], disorder[20][1][0][:10]
+    circ = RC.transpiled(RC.qc_body("vacuum", 11, 0.97, hs, phis, 2, 5, False))
+    got = sim.run(circ, shots=200, seed_simulator=99).result().get_counts()
+    want, info = O.run_counts(RC.ops_of(circ), 31, 1, shots=200, noise=onoise, seed=99)
+    assert info["method"] == "statevector" and got == want
+
+
+def test_multi_clbit_counts_dtc_qasm_shape(disorder):
+    """dtc_qasm.py circuit shape: L qubits, measure all; per-qubit <Z_i> from counts (dtc_qasm.py:145)."""
+    hs, phis = disorder[20][0][0][:6], disorder[20][1][0][:5]
+    ops, n, nc = C.dtc_qasm_gates("1", 6, 0.94, hs, phis, 3)
+    circ = dtcsim.QuantumCircuit(6, 6)
+    for nm_, qs, ps, cs in ops:
+        circ._add(nm_, qs, ps, cs)
+    sim = dtcsim.AerSimulator()
+    res = sim.run(circ, shots=4096, seed_simulator=3).result()
+    counts = res.get_counts()
+    want, info = O.run_counts(ops, 6, 6, shots=4096, noise=None, seed=3)
+    assert counts == want
+    ez = dtcsim.backend.compute_z_expectation(counts, 6)
+    psi = O.run_statevector(ops, 6)
+    idx = np.arange(64)
+    for q in range(6):
+        exact = float(np.sum(np.abs(psi) ** 2 * (1 - 2 * ((idx >> q) & 1))))
+        assert abs(ez[q] - exact) < 4 / np.sqrt(4096)
+        assert abs(res.expectation_z()[q] - exact) < 1e-10
+
+
+def test_L20_trajectory_statistics(disorder):
+    """C2-shaped point: 1024 Pauli trajectories at n = 21 within 4 sigma of the exact value and of the
+    reference's own committed Aer output (autocorr_data_L20_polarization/*polx*.csv)."""
+    hs, phis = disorder[20][0][0], disorder[20][1][0]
+    sim = dtcsim.AerSimulator(noise_model=RC.noise_model(0.05), device="GPU", cuStateVec_enable=True)
+    df = golden_csv("ref_L20_pol_x.csv")
+    for t, echo in ((2, False), (1, True)):
+        circ = RC.transpiled(RC.qc_body("vacuum", 20, 0.97, hs, phis, t, 10, echo), backend=sim)
+        res = sim.run(circ, shots=1024, seed_simulator=1234).result()
+        assert res.data()["method"] == "statevector" and res.data()["n_qubits"] == 21
+        counts = res.get_counts(circ)
+        ez = dtcsim.backend.compute_z_expectation(counts, 1)[0]
+        exact = 0.95 ** 6 * O.lightcone_zq(20, 0.97, hs, phis, t, 10, 0.05, echo=echo)
+        sig = np.sqrt((1 - exact ** 2) / 1024)
+        assert abs(ez - exact) < 4 * sig
+        assert abs(res.expectation_z()[0] - exact) < 4 * sig          # trajectory mean of exact probabilities
+        ref = df["av_autocorr_echo" if echo else "av_autocorr"][t]
+        assert abs(ez - ref) < 4 * np.sqrt(2) * sig
+
+
+def test_noiseless_echo_returns_to_start(disorder):
+    """Size-independent property at the full configuration: U^-t U^t = 1, so P(anc = 0) = 1."""
+    hs, phis = disorder[20][0][0], disorder[20][1][0]
+    sim = dtcsim.AerSimulator()
+    circ = RC.transpiled(RC.qc_body("vacuum", 20, 0.97, hs, phis, 7, 10, True))
+    res = sim.run(circ, shots=64, seed_simulator=1).result()
+    assert abs(res.expectation_z()[0] - 1.0) < 1e-10
+    assert res.get_counts() == {"0": 64}
+
+
+def test_norm_preserved_full_batch(ctx, disorder):
+    from dtcsim import backend
+    hs, phis = disorder[20][0][0], disorder[20][1][0]
+    circ = RC.transpiled(RC.qc_body("vacuum", 20, 0.97, hs, phis, 6, 10, True))
+    prog = compile_circuit(circ, RC.noise_model(0.05))
+    batch = backend.evolve(ctx, prog, 64, 0, 5)
+    p = batch.probs([prog.measures[0][0]]).cpu().numpy()
+    assert np.abs(p.sum(1) - 1).max() < 1e-11
+
+
+def test_error_paths(ctx):
+    sim = dtcsim.AerSimulator()
+    c = dtcsim.QuantumCircuit(2, 1)
+    c.h(0)
+    with pytest.raises(ValueError):
+        sim.run(c, shots=10).result()            # nothing measured
+    with pytest.raises(ValueError):
+        sim.run(c, shots=0)
+    from dtcsim import capi
+    import ctypes
+    h = ctypes.c_void_p()
+    assert capi.load().dtc_program_create(0, 1, ctypes.byref(h)) == -1
+    assert b"n_qubits" in capi.load().dtc_last_error()
