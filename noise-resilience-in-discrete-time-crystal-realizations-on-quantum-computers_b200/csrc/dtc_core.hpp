@@ -331,6 +331,12 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
             }
         }
         if (T.layerD >= 0) dtc_classify_terms(T, L);
+        for (int r = 0; r < DTC_NREG; ++r) {
+            u64 o = 0;
+            for (int k = 0; k < 5; ++k)
+                if ((r >> k) & 1) o += 1ull << T.tb[T.s2_lo + 5 + k];
+            T.roff[r] = o;
+        }
         P.passes.push_back(T);
         if (complete) {
             ++j;

@@ -67,6 +67,7 @@ struct DtcTilePass {
     int tb[DTC_TILE_BITS];         // global bit position of tile-local bit l (ascending)
     double t1[DTC_TILE_BITS];      // tan for R_A on local bit l (0: none in this pass)
     double t2[DTC_TILE_BITS];      // tan for R_B
+    u64 roff[DTC_NREG];            // global offset of register r in phases 1/3 (sum of S1 strides)
     // classification of D_layerD's two-body terms relative to this tile
     int nT1, nT2, nX, nC, nO;
     unsigned char T1k[DTC_MAXT], T1a[DTC_MAXT], T1b[DTC_MAXT];   // both ends in local [0, s1_lo]
@@ -198,6 +199,8 @@ struct TileSmem {
     double2 E[DTC_TILE_BITS][2];
     double2 B[DTC_MAXT][2];
     double2 C;
+    u64 base;          // global index of tile-local index 0 (kept here, not in registers, across phases)
+    u64 rmA, rmB;      // rotation sign masks of the trajectory
 };
 
 DTC_HD int tile_swz(int l) { return l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9)) & 7); }
@@ -329,40 +332,77 @@ DTC_HD void tile_signed_t(const double* tbase, const int* tb, int lo, u64 rmask,
     }
 }
 
-// phase 2 body on the register file: R_A|S2, D, R_B|S2
-template <int S2_LO>
+#if defined(__CUDA_ARCH__)
+#define DTC_SCHED_FENCE() asm volatile("" ::: "memory")
+#else
+#define DTC_SCHED_FENCE() ((void)0)
+#endif
+
+// rotations on register bits [0, nb) only
+DTC_HD void tile_rot_bits(double2 a[DTC_NREG], const double t[5], int kbeg, int kend) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        if (k < kbeg || k >= kend) continue;
+        const double tk = t[k];
+        if (tk != 0.0) {
+#pragma unroll
+            for (int i = 0; i < DTC_NREG; ++i) {
+                if (!((i >> k) & 1)) rot_pair(a[i], a[i | (1 << k)], tk);
+            }
+        }
+    }
+}
+
+// phase 2 body on the register file: R_A|S2, D, R_B|S2.
+// The diagonal multiply is fused into the pair loop of the top register bit (R_A bit 4 -> D -> R_B bit 4
+// per pair) so that only two phase-table entries are live at a time.
+template <int S2_LO, bool HAS_X>
 DTC_HD void tile_phase2_compute(int tid, double2 a[DTC_NREG], const TileSmem& sm, const DtcTilePass& P,
                                 u64 rmA, u64 rmB) {
     constexpr int S1 = S2_LO + 5;
     constexpr int NH = 7 - S2_LO;
-    double t[5];
-    if (P.layerA >= 0) {
-        tile_signed_t(P.t1, P.tb, S2_LO, rmA, t);
-        tile_rot5(a, t);
-    }
+    double tA[5] = {0, 0, 0, 0, 0}, tB[5] = {0, 0, 0, 0, 0};
+    if (P.layerA >= 0) tile_signed_t(P.t1, P.tb, S2_LO, rmA, tA);
+    if (P.layerB >= 0) tile_signed_t(P.t2, P.tb, S2_LO, rmB, tB);
+    tile_rot_bits(a, tA, 0, 4);
     if (P.layerD >= 0) {
         const int idx2 = tid & ((1 << NH) - 1);
         const double2 cthr = cmul(sm.C, sm.T2[idx2]);
         const int low = (tid >> NH) | ((tid & 1) << S1);          // passive low bits + bit S1_LO
         const int sw = (tid & 1) << 2;
+        if (!HAS_X) {
 #pragma unroll
-        for (int r = 0; r < DTC_NREG; ++r) {
-            const double2 ph = cmul(sm.T1[(low | (r << S2_LO)) ^ sw], cthr);
-            a[r] = cmul(a[r], ph);
-        }
-        for (int c = 0; c < P.nX; ++c) {                          // terms outside both tables (rare)
-            const double2 b0 = sm.B[P.Xk[c]][0], b1 = sm.B[P.Xk[c]][1];
+            for (int i = 0; i < 16; ++i) {
+                if (tA[4] != 0.0) rot_pair(a[i], a[i | 16], tA[4]);
+                const double2 p0 = cmul(sm.T1[(low | (i << S2_LO)) ^ sw], cthr);
+                const double2 p1 = cmul(sm.T1[(low | ((i | 16) << S2_LO)) ^ sw], cthr);
+                a[i] = cmul(a[i], p0);
+                a[i | 16] = cmul(a[i | 16], p1);
+                if (tB[4] != 0.0) rot_pair(a[i], a[i | 16], tB[4]);
+                DTC_SCHED_FENCE();
+            }
+        } else {
+            tile_rot_bits(a, tA, 4, 5);
 #pragma unroll
             for (int r = 0; r < DTC_NREG; ++r) {
-                const int l = tile_local_p2<S2_LO>(tid, r);
-                a[r] = cmul(a[r], (((l >> P.Xa[c]) ^ (l >> P.Xb[c])) & 1) ? b1 : b0);
+                const double2 ph = cmul(sm.T1[(low | (r << S2_LO)) ^ sw], cthr);
+                a[r] = cmul(a[r], ph);
             }
+            for (int c = 0; c < P.nX; ++c) {                      // terms outside both tables (rare)
+                const double2 b0 = sm.B[P.Xk[c]][0], b1 = sm.B[P.Xk[c]][1];
+#pragma unroll
+                for (int r = 0; r < DTC_NREG; ++r) {
+                    const int l = tile_local_p2<S2_LO>(tid, r);
+                    a[r] = cmul(a[r], (((l >> P.Xa[c]) ^ (l >> P.Xb[c])) & 1) ? b1 : b0);
+                }
+            }
+            tile_rot_bits(a, tB, 4, 5);
         }
+    } else {
+        tile_rot_bits(a, tA, 4, 5);
+        tile_rot_bits(a, tB, 4, 5);
     }
-    if (P.layerB >= 0) {
-        tile_signed_t(P.t2, P.tb, S2_LO, rmB, t);
-        tile_rot5(a, t);
-    }
+    tile_rot_bits(a, tB, 0, 4);
 }
 
 // ---- data movement of the three phases (shared with the CPU emulation harness)
@@ -375,29 +415,19 @@ DTC_HD void tile_phase2_compute(int tid, double2 a[DTC_NREG], const TileSmem& sm
 #endif
 
 template <int S2_LO>
-DTC_HD void tile_global_offsets(int tid, u64 base, const int* tb, u64& off, u64 rs[5]) {
-    constexpr int S1 = S2_LO + 5;
-    off = base | tile_deposit_local(tile_local_p13<S2_LO>(tid, 0), tb);
-#pragma unroll
-    for (int k = 0; k < 5; ++k) rs[k] = 1ull << tb[S1 + k];
+DTC_HD u64 tile_thread_offset(int tid, u64 base, const int* tb) {
+    return base | tile_deposit_local(tile_local_p13<S2_LO>(tid, 0), tb);
 }
 
-DTC_HD u64 tile_reg_offset(int r, u64 off, const u64 rs[5]) {
-    u64 o = off;
+// register offsets come from the pass descriptor (constant bank), so no address registers stay live
+DTC_HD void tile_gload(const double2* st, u64 off, const DtcTilePass& P, double2 a[DTC_NREG]) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k)
-        if ((r >> k) & 1) o += rs[k];
-    return o;
+    for (int r = 0; r < DTC_NREG; ++r) a[r] = DTC_LDG(st + (off + P.roff[r]));
 }
 
-DTC_HD void tile_gload(const double2* st, u64 off, const u64 rs[5], double2 a[DTC_NREG]) {
+DTC_HD void tile_gstore(double2* st, u64 off, const DtcTilePass& P, const double2 a[DTC_NREG]) {
 #pragma unroll
-    for (int r = 0; r < DTC_NREG; ++r) a[r] = DTC_LDG(st + tile_reg_offset(r, off, rs));
-}
-
-DTC_HD void tile_gstore(double2* st, u64 off, const u64 rs[5], const double2 a[DTC_NREG]) {
-#pragma unroll
-    for (int r = 0; r < DTC_NREG; ++r) DTC_STG(st + tile_reg_offset(r, off, rs), a[r]);
+    for (int r = 0; r < DTC_NREG; ++r) DTC_STG(st + (off + P.roff[r]), a[r]);
 }
 
 template <int S2_LO>
@@ -444,4 +474,16 @@ DTC_HD TileMasks tile_load_masks(const DtcTilePass& P, const u64* masks, long lo
         m.m2 = masks[(long long)(P.layerD * 4 + 3) * n_traj + traj];
     }
     return m;
+}
+
+// L2 prefetch of the tile a later CTA will load (one request per 64 B run)
+#if defined(__CUDA_ARCH__)
+#define DTC_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#else
+#define DTC_PREFETCH_L2(p) ((void)(p))
+#endif
+
+DTC_HD void tile_prefetch(const double2* st, u64 off, const DtcTilePass& P) {
+#pragma unroll
+    for (int r = 0; r < DTC_NREG; ++r) DTC_PREFETCH_L2(st + (off + P.roff[r]));
 }

@@ -9,6 +9,7 @@
 //   k_generic_*          one-thread-per-element fallbacks (n < 12, cross-checks).
 //   k_dm_*               exact density-matrix primitives (small n).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include <new>
 #include <string>
@@ -52,45 +53,54 @@ __global__ void k_init_basis(double2* __restrict__ state, int n_local, long long
     if (t < n_traj) state[((u64)t << n_local) + index] = make_double2(1.0, 0.0);
 }
 
-template <int S2_LO>
+template <int S2_LO, bool HAS_X>
 __global__ void __launch_bounds__(DTC_THREADS, 3)
 k_tile_pass(double2* __restrict__ state, const __grid_constant__ DtcTilePass P,
             const DtcLayer* __restrict__ layers, const u64* __restrict__ masks, long long n_traj,
-            u64 rank_bits) {
+            u64 rank_bits, int pf_blocks) {
     extern __shared__ __align__(16) unsigned char smraw[];
     TileSmem& sm = *reinterpret_cast<TileSmem*>(smraw);
     const int tid = threadIdx.x;
     const int ntb = P.n_local - DTC_TILE_BITS;
-    const u64 tile = (u64)blockIdx.x & ((1ull << ntb) - 1);
-    const u64 traj = (u64)blockIdx.x >> ntb;
-    double2* __restrict__ st = state + (traj << P.n_local);
-    const u64 base = tile_base_index(tile, P.n_local, P.tb);
-    const TileMasks M = tile_load_masks(P, masks, n_traj, traj);
-
-    // phase 1: coalesced global loads straight into the register file (registers span S1)
-    u64 off, rs[5];
-    tile_global_offsets<S2_LO>(tid, base, P.tb, off, rs);
     double2 a[DTC_NREG];
-    tile_gload(st, off, rs, a);
-    // diagonal-layer setup and tables overlap the loads in flight
-    if (P.layerD >= 0)
-        tile_setup_thread(tid, sm, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
+    {
+        // phase 1: coalesced global loads straight into the register file (registers span S1)
+        const u64 tile = (u64)blockIdx.x & ((1ull << ntb) - 1);
+        const u64 traj = (u64)blockIdx.x >> ntb;
+        const u64 base = tile_base_index(tile, P.n_local, P.tb);
+        tile_gload(state + (traj << P.n_local), tile_thread_offset<S2_LO>(tid, base, P.tb), P, a);
+        // warm L2 with the tile a CTA of the next wave will load (one lane per 64 B run)
+        const u64 b2 = (u64)blockIdx.x + (u64)pf_blocks;
+        if (pf_blocks > 0 && b2 < gridDim.x && (tid & 3) == 0) {
+            const u64 base2 = tile_base_index(b2 & ((1ull << ntb) - 1), P.n_local, P.tb);
+            tile_prefetch(state + ((b2 >> ntb) << P.n_local), tile_thread_offset<S2_LO>(tid, base2, P.tb), P);
+        }
+        const TileMasks M = tile_load_masks(P, masks, n_traj, traj);
+        if (tid == 0) {
+            sm.base = base;
+            sm.rmA = M.rmA;
+            sm.rmB = M.rmB;
+        }
+        // diagonal-layer setup overlaps the loads in flight
+        if (P.layerD >= 0)
+            tile_setup_thread(tid, sm, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
+    }
     __syncthreads();
-    if (P.layerD >= 0) tile_tables_thread<S2_LO>(tid, sm, P);
-    if (P.layerA >= 0) tile_rot_s1<S2_LO>(a, P.t1, P.tb, M.rmA);
+    if (P.layerA >= 0) tile_rot_s1<S2_LO>(a, P.t1, P.tb, sm.rmA);
     tile_sm_store13<S2_LO>(tid, sm, a);
+    if (P.layerD >= 0) tile_tables_thread<S2_LO>(tid, sm, P);     // after the stores: a[] is dead here
     __syncthreads();
 
     // phase 2: registers span S2:  R_A|S2, D, R_B|S2
     tile_sm_load2<S2_LO>(tid, sm, a);
-    tile_phase2_compute<S2_LO>(tid, a, sm, P, M.rmA, M.rmB);
+    tile_phase2_compute<S2_LO, HAS_X>(tid, a, sm, P, sm.rmA, sm.rmB);
     tile_sm_store2<S2_LO>(tid, sm, a);
     __syncthreads();
 
     // phase 3: registers span S1 again, coalesced stores
     tile_sm_load13<S2_LO>(tid, sm, a);
-    if (P.layerB >= 0) tile_rot_s1<S2_LO>(a, P.t2, P.tb, M.rmB);
-    tile_gstore(st, off, rs, a);
+    if (P.layerB >= 0) tile_rot_s1<S2_LO>(a, P.t2, P.tb, sm.rmB);
+    tile_gstore(state + (((u64)blockIdx.x >> ntb) << P.n_local), tile_thread_offset<S2_LO>(tid, sm.base, P.tb), P, a);
 }
 
 // ---- generic engine
@@ -457,9 +467,13 @@ int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
     CUDA_TRY(cudaMemcpy(p->d_layers, p->h.layers.data(), lb, cudaMemcpyHostToDevice));
     static bool attr_set[16] = {false};
     if (device >= 0 && device < 16 && !attr_set[device]) {
-        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
-        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
-        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+        const int smb = (int)sizeof(TileSmem);
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
         attr_set[device] = true;
     }
     p->h.finalized = true;
@@ -519,12 +533,24 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     if (h.engine == DTC_ENGINE_TILE) {
         const long long grid = n_traj << (h.n_local - DTC_TILE_BITS);
         if (grid > 0x7fffffffLL) return fail(DTC_ERR_INVALID, "batch too large for one launch");
+        static const int pf = []() {
+            const char* e = getenv("DTCSIM_PREFETCH_BLOCKS");      // tuning knob; default one wave of 148 x 3 CTAs
+            return e ? atoi(e) : 444;
+        }();
         for (const DtcTilePass& T : h.passes) {
-            switch (T.s2_lo) {
-                case 0: k_tile_pass<0><<<(unsigned)grid, DTC_THREADS, sizeof(TileSmem), s>>>((double2*)state, T, p->d_layers, masks, n_traj, rank_bits); break;
-                case 1: k_tile_pass<1><<<(unsigned)grid, DTC_THREADS, sizeof(TileSmem), s>>>((double2*)state, T, p->d_layers, masks, n_traj, rank_bits); break;
-                default: k_tile_pass<2><<<(unsigned)grid, DTC_THREADS, sizeof(TileSmem), s>>>((double2*)state, T, p->d_layers, masks, n_traj, rank_bits); break;
+            const bool hx = T.layerD >= 0 && T.nX > 0;
+#define DTC_LAUNCH(S, X)                                                                               \
+    k_tile_pass<S, X><<<(unsigned)grid, DTC_THREADS, sizeof(TileSmem), s>>>((double2*)state, T, p->d_layers, masks, \
+                                                                            n_traj, rank_bits, pf)
+            switch (T.s2_lo * 2 + (hx ? 1 : 0)) {
+                case 0: DTC_LAUNCH(0, false); break;
+                case 1: DTC_LAUNCH(0, true); break;
+                case 2: DTC_LAUNCH(1, false); break;
+                case 3: DTC_LAUNCH(1, true); break;
+                case 4: DTC_LAUNCH(2, false); break;
+                default: DTC_LAUNCH(2, true); break;
             }
+#undef DTC_LAUNCH
         }
     } else {
         for (const DtcGenericStep& g : h.gsteps) {

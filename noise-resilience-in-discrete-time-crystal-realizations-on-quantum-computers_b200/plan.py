@@ -95,6 +95,18 @@ class Program:
     def measured_qubits(self):
         return [q for q, _ in self.measures]
 
+    def to_circuit_order(self, psi):
+        """Statevector(s) [..., 2^n] in the internal bit order -> compacted circuit-qubit order
+        (qubit k of the truncated circuit = bit k), the order Aer's save_statevector would use."""
+        n = self.n
+        if list(self.order) == list(range(n)):
+            return psi
+        lead = psi.shape[:-1]
+        nl = len(lead)
+        v = psi.reshape(lead + (2,) * n)                 # axis nl + n-1-b <-> bit b
+        axes = list(range(nl)) + [nl + n - 1 - self.bit_of[n - 1 - k] for k in range(n)]
+        return np.ascontiguousarray(np.transpose(v, axes)).reshape(lead + (1 << n,))
+
 
 def compact(circ):
     """Idle-qubit truncation (what Aer does to the 31-qubit-wide transpiled circuit)."""

@@ -21,27 +21,28 @@ static void emu_tile_pass(double2* state, const DtcTilePass& P, const DtcLayer* 
     double2* st = state + (traj << P.n_local);
     const u64 base = tile_base_index(tile, P.n_local, P.tb);
     const TileMasks M = tile_load_masks(P, masks, n_traj, traj);
-    u64 off[DTC_THREADS], rs[DTC_THREADS][5];
+    u64 off[DTC_THREADS];
     // --- up to the first barrier
     for (int tid = 0; tid < DTC_THREADS; ++tid) {
         double2* a = &regs[(size_t)tid * DTC_NREG];
-        tile_global_offsets<S2_LO>(tid, base, P.tb, off[tid], rs[tid]);
-        tile_gload(st, off[tid], rs[tid], a);
+        off[tid] = tile_thread_offset<S2_LO>(tid, base, P.tb);
+        tile_gload(st, off[tid], P, a);
         if (P.layerD >= 0)
             tile_setup_thread(tid, sm, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
     }
     // --- second segment
     for (int tid = 0; tid < DTC_THREADS; ++tid) {
         double2* a = &regs[(size_t)tid * DTC_NREG];
-        if (P.layerD >= 0) tile_tables_thread<S2_LO>(tid, sm, P);
         if (P.layerA >= 0) tile_rot_s1<S2_LO>(a, P.t1, P.tb, M.rmA);
         tile_sm_store13<S2_LO>(tid, sm, a);
+        if (P.layerD >= 0) tile_tables_thread<S2_LO>(tid, sm, P);
     }
     // --- phase 2
     for (int tid = 0; tid < DTC_THREADS; ++tid) {
         double2 a[DTC_NREG];
         tile_sm_load2<S2_LO>(tid, sm, a);
-        tile_phase2_compute<S2_LO>(tid, a, sm, P, M.rmA, M.rmB);
+        if (P.layerD >= 0 && P.nX > 0) tile_phase2_compute<S2_LO, true>(tid, a, sm, P, M.rmA, M.rmB);
+        else tile_phase2_compute<S2_LO, false>(tid, a, sm, P, M.rmA, M.rmB);
         // a thread only rewrites the slots it read, so doing this without a barrier is faithful
         tile_sm_store2<S2_LO>(tid, sm, a);
     }
@@ -50,7 +51,7 @@ static void emu_tile_pass(double2* state, const DtcTilePass& P, const DtcLayer* 
         double2 a[DTC_NREG];
         tile_sm_load13<S2_LO>(tid, sm, a);
         if (P.layerB >= 0) tile_rot_s1<S2_LO>(a, P.t2, P.tb, M.rmB);
-        tile_gstore(st, off[tid], rs[tid], a);
+        tile_gstore(st, off[tid], P, a);
     }
 }
 
