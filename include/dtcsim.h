@@ -41,7 +41,7 @@ typedef enum {
     DTC_ERR_NOMEM = -4
 } dtc_status;
 
-enum { DTC_EV_ROT = 0, DTC_EV_D1 = 1, DTC_EV_D2 = 2, DTC_EV_NOISE = 3 };
+enum { DTC_EV_ROT = 0, DTC_EV_D1 = 1, DTC_EV_D2 = 2, DTC_EV_NOISE = 3, DTC_EV_D2C = 4 };
 enum { DTC_ENGINE_AUTO = 0, DTC_ENGINE_GENERIC = 1, DTC_ENGINE_TILE = 2 };
 
 typedef struct dtc_program dtc_program;   /* opaque compiled circuit */
@@ -63,6 +63,10 @@ int dtc_program_destroy(dtc_program *p);
 int dtc_program_set_events(dtc_program *p, int64_t n_events, const int32_t *type, const int32_t *layer,
                            const int32_t *q0, const int32_t *q1, const int32_t *slot,
                            const double *val, const double *probs, double global_phase);
+/* Only layers [0, n_exec_layers) are executed on the state; later ("virtual") layers still get sign masks
+ * from the frame walk -- the host uses them for the small read-out simulation (plan.py, optimize=True).
+ * DTC_EV_D2C is a D2 term whose partner q1 is still |0> in psi': sign from (q0,q1), phase one-body on q0. */
+int dtc_program_set_exec_layers(dtc_program *p, int n_exec_layers);
 /* Build layer tables and the pass schedule and upload them to `device`.
  * engine: DTC_ENGINE_AUTO picks the fused tile engine when n_local >= 12. */
 int dtc_program_finalize(dtc_program *p, int device, int engine, int n_local);
@@ -97,6 +101,10 @@ int dtc_materialize(void *state, int n_local, int64_t n_traj, const uint64_t *fx
  * Replaces the measure sampling input of Aer (fast.py:211) and compute_z_expectation's p0/p1. */
 int dtc_probs(const void *state, int n_local, int64_t n_traj, int k, const int32_t *qubits,
               const uint64_t *fx_or_null, double *out, void *stream);
+/* Reduced density matrix of k (<= 2) qubits of psi': out[n_traj][2^k][2^k] complex128 (device, row-major,
+ * rho[a][b] = sum_rest psi(a,rest) conj psi(b,rest); bit i of a = qubit qubits[i]).  Read-out of the
+ * Hadamard-test signal without carrying the ancilla in the register (SURVEY.md 8a identity). */
+int dtc_rdm(const void *state, int n_local, int64_t n_traj, int k, const int32_t *qubits, void *out, void *stream);
 /* <Z_q> for every qubit: out[n_traj][n_local] (device, double).  (dtc_qasm.py:145 per-qubit <Z_i>) */
 int dtc_expect_z(const void *state, int n_local, int64_t n_traj, const uint64_t *fx_or_null,
                  double *out, void *stream);

@@ -20,7 +20,7 @@ import time
 
 import numpy as np
 
-from . import capi
+from . import capi, readout
 from .ir import as_circuit
 from .noise import as_noise_model
 from .plan import compile_circuit
@@ -89,6 +89,37 @@ class TrajectoryBatch:
         capi.check(capi.load().dtc_probs(self.state.data_ptr(), self.n, self.n_traj, k, qp,
                                          self.fx if apply_frame else None, out.data_ptr(), self.ctx.stream))
         return out.view(self.n_traj, 1 << k)
+
+    def rdm(self, bits):
+        """[n_traj, 2^k, 2^k] reduced density matrices of psi' on `bits` (k <= 2), torch complex128."""
+        torch = self.ctx.torch
+        k = len(bits)
+        out = self.ctx.empty(self.n_traj << (2 * k), torch.complex128)
+        _, qp = capi.i32(list(bits) if k else [0])
+        capi.check(capi.load().dtc_rdm(self.state.data_ptr(), self.n, self.n_traj, k, qp, out.data_ptr(),
+                                       self.ctx.stream))
+        return out.view(self.n_traj, 1 << k, 1 << k)
+
+    def masks_host(self, first_layer=0):
+        """Sign masks [n_layers - first_layer, 4, n_traj] (uint64) written by the device frame walk."""
+        torch = self.ctx.torch
+        nl, n = self.handle.prog.n_layers, self.n_traj
+        m = self.ws[: nl * 4 * n * 8].view(torch.int64).view(nl, 4, n)[first_layer:]
+        return m.cpu().numpy().view(np.uint64)
+
+    def outcome_probs(self, rdm=None):
+        """Per-trajectory probabilities of the measured qubits [n_traj, 2^m] (frame applied), on the device.
+        Uses the read-out factorisation when the program was compiled with it (rdm: result of an earlier
+        self.rdm(reg_bits) call, so the state buffer may already have been reused)."""
+        prog = self.handle.prog
+        torch = self.ctx.torch
+        if prog.small is None:
+            return self.probs([q for q, _ in prog.measures])
+        rdm = (self.rdm(prog.small["reg_bits"]) if rdm is None else rdm).cpu().numpy()
+        masks = self.masks_host(prog.small["first_layer"])
+        fx, _, _ = self.frames_host()
+        pr = readout.simulate_small(prog, rdm, masks, fx, first_mask_layer=prog.small["first_layer"])
+        return torch.from_numpy(np.ascontiguousarray(pr)).to(self.ctx.device)
 
     def expect_z(self, apply_frame=True):
         torch = self.ctx.torch
@@ -255,13 +286,14 @@ class DTCSimulator:
 
     def __init__(self, noise_model=None, method="automatic", device="GPU", cuStateVec_enable=False,
                  seed_simulator=None, shots=1024, cuda_device=None, max_memory_bytes=None, engine="auto",
-                 **ignored):
+                 optimize=True, **ignored):
         self.noise_model = noise_model
         self.method = method
         self.seed_simulator = seed_simulator
         self.default_shots = shots
         self.cuda_device = cuda_device
         self.max_memory_bytes = max_memory_bytes
+        self.optimize = bool(optimize)       # read-out factorisation (plan.compile_circuit(optimize=True))
         self.engine = {"auto": capi.ENGINE_AUTO, "generic": capi.ENGINE_GENERIC, "tile": capi.ENGINE_TILE}[engine]
         self.options = dict(device=device, cuStateVec_enable=cuStateVec_enable, **ignored)
         self._ctx = None
@@ -312,7 +344,7 @@ class DTCSimulator:
         t0 = time.time()
         torch = self.ctx.torch
         ctx = self.ctx
-        prog0 = compile_circuit(circ, nm, want_dm=False)
+        prog0 = compile_circuit(circ, nm, want_dm=False, optimize=self.optimize)
         n = prog0.n
         method = self._choose_method(method, n, shots, nm)
         meas = prog0.measures
@@ -329,7 +361,8 @@ class DTCSimulator:
                 vals |= ((cols >> i) & 1) << cbits[i]
             return vals
 
-        data = {"method": method, "n_qubits": n, "active_qubits": prog0.active, "seed_simulator": seed}
+        data = {"method": method, "n_qubits": n, "register_qubits": prog0.n_main, "active_qubits": prog0.active,
+                "seed_simulator": seed}
         if method == "density_matrix":
             prog = compile_circuit(circ, nm, want_dm=True)
             rho = run_density_matrix(ctx, prog)
@@ -344,24 +377,25 @@ class DTCSimulator:
             if k > MAX_PROB_QUBITS:
                 raise ValueError(f"ideal circuits measuring more than {MAX_PROB_QUBITS} qubits are not supported yet")
             batch = evolve(ctx, prog0, 1, 0, seed, self.engine)
-            probs = batch.probs(mq)
+            probs = batch.outcome_probs()
             cols = sample_rows(ctx, probs, shots, seed, 0).cpu().numpy()[0]
             data["probabilities"] = self._clbit_probs(probs.cpu().numpy()[0], to_clbits, prog0.n_clbits)
             data["num_passes"] = batch.handle.num_passes
             vals = to_clbits(cols)
         else:
             handle = capi.ProgramHandle(prog0, ctx.index, self.engine)
-            per = 16 << n
+            nm_ = prog0.n_main
+            per = 16 << nm_
             budget = self.max_memory_bytes or int(0.7 * ctx.free_bytes())
             bt = max(1, min(shots, budget // per))
-            state = ctx.empty(bt << n, torch.complex128)
+            state = ctx.empty(bt << nm_, torch.complex128)
             vals = np.zeros(shots, dtype=np.int64)
             psum = None
             for a in range(0, shots, bt):
                 nt = min(bt, shots - a)
                 batch = evolve(ctx, prog0, nt, a, seed, handle=handle, state=state)
                 if k <= MAX_PROB_QUBITS:
-                    probs = batch.probs(mq)
+                    probs = batch.outcome_probs()
                     cols = sample_rows(ctx, probs, 1, seed, a).cpu().numpy()[:, 0]
                     ps = probs.sum(dim=0).cpu().numpy()
                     psum = ps if psum is None else psum + ps

@@ -25,6 +25,7 @@ _SIGS = {
     "dtc_program_destroy": (ctypes.c_int, [c_vp]),
     "dtc_program_set_events": (ctypes.c_int, [c_vp, c_i64, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_f64p, c_f64p,
                                               ctypes.c_double]),
+    "dtc_program_set_exec_layers": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "dtc_program_finalize": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "dtc_program_num_passes": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_workspace_bytes": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(ctypes.c_size_t)]),
@@ -35,6 +36,7 @@ _SIGS = {
     "dtc_program_pass_time": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "dtc_materialize": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dtc_probs": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_i32p, c_vp, c_vp, c_vp]),
+    "dtc_rdm": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_i32p, c_vp, c_vp]),
     "dtc_expect_z": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp]),
     "dtc_sample_rows": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_u64, c_i64, c_vp, c_vp]),
     "dtc_sample_states": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_u64, c_i64, c_vp, c_vp, c_vp, c_vp]),
@@ -95,7 +97,7 @@ class ProgramHandle:
     def __init__(self, prog, device, engine=ENGINE_AUTO, n_local=None):
         lib = load()
         self.prog = prog
-        self.n_local = prog.n if n_local is None else n_local
+        self.n_local = prog.n_main if n_local is None else n_local
         self.device = device
         self._h = c_vp()
         check(lib.dtc_program_create(prog.n, prog.n_layers, ctypes.byref(self._h)))
@@ -105,6 +107,7 @@ class ProgramHandle:
                     f64(ev["val"]), f64(ev["probs"])]
             check(lib.dtc_program_set_events(self._h, len(ev["type"]), *[k[1] for k in keep],
                                              float(prog.global_phase)))
+            check(lib.dtc_program_set_exec_layers(self._h, int(prog.n_exec_layers)))
             check(lib.dtc_program_finalize(self._h, int(device), int(engine), int(self.n_local)))
         except Exception:
             self.close()

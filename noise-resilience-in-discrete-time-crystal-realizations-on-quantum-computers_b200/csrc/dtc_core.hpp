@@ -19,7 +19,7 @@ struct DtcGenericStep {
 };
 
 struct DtcProgramHost {
-    int n_qubits = 0, n_layers = 0, n_local = 0, device = -1, engine = 0;
+    int n_qubits = 0, n_layers = 0, n_exec_layers = 0, n_local = 0, device = -1, engine = 0;
     double global_phase = 0.0;
     bool finalized = false;
     int64_t n_sites = 0;
@@ -88,12 +88,13 @@ static inline bool dtc_build_layers(DtcProgramHost& P, std::string& err) {
             if (k4 < 0) k4 += 4;
             E.k = (int)k4;
             const double t = tan(0.5 * thp);
-            if (L.rot_any >> E.q0 & 1ull) {
-                snprintf(buf, sizeof buf, "event %zu: two rotations on qubit %d in layer %d", e, E.q0, E.layer);
-                err = buf;
-                return false;
-            }
+            E.slot = (t == 0.0) ? 1 : 0;        // slot 1: pure Pauli RX(k pi), frame update only, no sign bit
             if (t != 0.0) {
+                if (L.rot_any >> E.q0 & 1ull) {
+                    snprintf(buf, sizeof buf, "event %zu: two rotations on qubit %d in layer %d", e, E.q0, E.layer);
+                    err = buf;
+                    return false;
+                }
                 L.rtan[E.q0] = t;
                 L.rot_any |= 1ull << E.q0;
                 L.cr *= cos(0.5 * thp);
@@ -107,7 +108,7 @@ static inline bool dtc_build_layers(DtcProgramHost& P, std::string& err) {
             L.c1[E.slot][E.q0] = cos(0.5 * E.c0);
             L.s1[E.slot][E.q0] = sin(0.5 * E.c0);
             L.d1_any[E.slot] |= 1ull << E.q0;
-        } else if (E.type == DTC_EVT_D2) {
+        } else if (E.type == DTC_EVT_D2 || E.type == DTC_EVT_D2C) {
             if (E.slot < 0 || E.slot >= DTC_MAXT || E.q1 < 0 || E.q1 >= P.n_qubits || E.q1 == E.q0) {
                 snprintf(buf, sizeof buf, "event %zu: bad D2 term", e);
                 err = buf;
@@ -116,7 +117,7 @@ static inline bool dtc_build_layers(DtcProgramHost& P, std::string& err) {
             L.tc[E.slot] = cos(0.5 * E.c0);
             L.ts[E.slot] = sin(0.5 * E.c0);
             L.ti[E.slot] = E.q0;
-            L.tj[E.slot] = E.q1;
+            L.tj[E.slot] = (E.type == DTC_EVT_D2C) ? DTC_VIRTUAL_QUBIT : E.q1;
             if (E.slot + 1 > L.n_terms) L.n_terms = E.slot + 1;
         } else if (E.type == DTC_EVT_NOISE) {
             P.n_sites++;
@@ -239,9 +240,11 @@ static inline std::vector<DtcGroup> dtc_make_groups(const DtcProgramHost& P) {
     const int n = P.n_local;
     int count[DTC_MAXQ] = {0};
     int maxc = 0;
-    for (const DtcLayer& L : P.layers)
+    for (int j = 0; j < P.n_exec_layers; ++j) {
+        const DtcLayer& L = P.layers[j];
         for (int q = 0; q < n; ++q)
             if ((L.rot_any >> q) & 1ull) { ++count[q]; if (count[q] > maxc) maxc = count[q]; }
+    }
     std::vector<u64> chunks;
     u64 cur = 0;
     for (int q = 0; q < n; ++q) {
@@ -273,7 +276,7 @@ static inline std::vector<DtcGroup> dtc_make_groups(const DtcProgramHost& P) {
 }
 
 static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
-    const int M = P.n_layers, n = P.n_local;
+    const int M = P.n_exec_layers, n = P.n_local;
     const u64 local_mask = (n >= 64) ? ~0ull : ((1ull << n) - 1);
     P.passes.clear();
     for (int j = 0; j < M; ++j)
@@ -350,7 +353,7 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
 
 static inline void dtc_schedule_generic(DtcProgramHost& P) {
     P.gsteps.clear();
-    for (int j = 0; j < P.n_layers; ++j) {
+    for (int j = 0; j < P.n_exec_layers; ++j) {
         const DtcLayer& L = P.layers[j];
         for (int q = 0; q < P.n_qubits; ++q)
             if ((L.rot_any >> q) & 1ull) P.gsteps.push_back(DtcGenericStep{0, j, q, L.rtan[q]});

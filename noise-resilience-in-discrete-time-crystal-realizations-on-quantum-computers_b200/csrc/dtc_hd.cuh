@@ -38,7 +38,8 @@ typedef unsigned long long u64;
 #define DTC_NREG 32
 #define DTC_THREADS 128
 
-enum { DTC_EVT_ROT = 0, DTC_EVT_D1 = 1, DTC_EVT_D2 = 2, DTC_EVT_NOISE = 3 };
+enum { DTC_EVT_ROT = 0, DTC_EVT_D1 = 1, DTC_EVT_D2 = 2, DTC_EVT_NOISE = 3, DTC_EVT_D2C = 4 };
+#define DTC_VIRTUAL_QUBIT 63   // table partner of D2C terms (partner qubit still |0> in psi'): index bit always 0
 
 // Per-layer tables (R_j followed by D_j), device resident, shared by all trajectories.
 struct DtcLayer {
@@ -118,12 +119,12 @@ DTC_HD void frame_walk(u64 traj_global, u64 seed, const DtcEvent* ev, int64_t n_
         const DtcEvent E = ev[e];
         const int q = E.q0;
         if (E.type == DTC_EVT_ROT) {
-            if ((fz >> q) & 1ull) masks[(int64_t)(E.layer * 4 + 0) * mstride] |= 1ull << q;
+            if (E.slot == 0 && ((fz >> q) & 1ull)) masks[(int64_t)(E.layer * 4 + 0) * mstride] |= 1ull << q;
             if (E.k & 1) fx ^= 1ull << q;
             ph += 3 * E.k;
         } else if (E.type == DTC_EVT_D1) {
             if ((fx >> q) & 1ull) masks[(int64_t)(E.layer * 4 + 1 + E.slot) * mstride] |= 1ull << q;
-        } else if (E.type == DTC_EVT_D2) {
+        } else if (E.type == DTC_EVT_D2 || E.type == DTC_EVT_D2C) {
             if (((fx >> q) ^ (fx >> E.q1)) & 1ull) masks[(int64_t)(E.layer * 4 + 3) * mstride] |= 1ull << E.slot;
         } else {
             const double u = philox_uniform(seed, (uint32_t)E.slot, 0u, traj_global);

@@ -239,6 +239,70 @@ __global__ void k_expect_z(const double2* __restrict__ state, int n_local, long 
     if (threadIdx.x < n_local) atomicAdd(&out[traj * n_local + threadIdx.x], sacc[threadIdx.x]);
 }
 
+template <int K>
+__global__ void k_rdm(const double2* __restrict__ state, int n_local, long long n_traj, const int* __restrict__ qubits,
+                      double2* __restrict__ out, int chunks_per_traj) {
+    constexpr int D = 1 << K;
+    const u64 traj = blockIdx.x / chunks_per_traj;
+    const u64 chunk = blockIdx.x % chunks_per_traj;
+    const u64 nrest = 1ull << (n_local - K);
+    const u64 per = nrest / chunks_per_traj;
+    const double2* st = state + (traj << n_local);
+    int qs[K > 0 ? K : 1];
+    for (int i = 0; i < K; ++i) qs[i] = qubits[i];
+    double2 acc[D][D];
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int b = 0; b < D; ++b) acc[a][b] = make_double2(0.0, 0.0);
+    for (u64 r = chunk * per + threadIdx.x; r < (chunk + 1) * per; r += blockDim.x) {
+        // insert zero bits at the (ascending) qubit positions
+        u64 x = r;
+        for (int i = 0; i < K; ++i) {
+            int q = qs[0];
+            if (K == 2) q = (i == 0) ? (qs[0] < qs[1] ? qs[0] : qs[1]) : (qs[0] < qs[1] ? qs[1] : qs[0]);
+            const u64 low = (1ull << q) - 1;
+            x = ((x & ~low) << 1) | (x & low);
+        }
+        double2 v[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            u64 o = x;
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+                if ((a >> i) & 1) o |= 1ull << qs[i];
+            v[a] = st[o];
+        }
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = a; b < D; ++b) {       // v[a] * conj(v[b])
+                acc[a][b].x += v[a].x * v[b].x + v[a].y * v[b].y;
+                acc[a][b].y += v[a].y * v[b].x - v[a].x * v[b].y;
+            }
+    }
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int b = a; b < D; ++b) {
+            double re = acc[a][b].x, im = acc[a][b].y;
+            for (int o = 16; o > 0; o >>= 1) {
+                re += __shfl_xor_sync(0xffffffffu, re, o);
+                im += __shfl_xor_sync(0xffffffffu, im, o);
+            }
+            if ((threadIdx.x & 31) == 0) {
+                double* dst = (double*)(out + (traj * D + a) * D + b);
+                atomicAdd(dst, re);
+                if (a != b) {
+                    atomicAdd(dst + 1, im);
+                    double* dst2 = (double*)(out + (traj * D + b) * D + a);
+                    atomicAdd(dst2, re);
+                    atomicAdd(dst2 + 1, -im);
+                }
+            }
+        }
+}
+
 __global__ void k_sample_rows(const double* __restrict__ probs, long long n_rows, int n_cols, int n_samples,
                               u64 seed, long long traj_offset, int* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -411,6 +475,7 @@ int dtc_program_create(int n_qubits, int n_layers, dtc_program** out) {
     if (!p) return fail(DTC_ERR_NOMEM, "out of host memory");
     p->h.n_qubits = n_qubits;
     p->h.n_layers = n_layers;
+    p->h.n_exec_layers = n_layers;
     *out = p;
     return DTC_OK;
 }
@@ -436,6 +501,13 @@ int dtc_program_set_events(dtc_program* p, int64_t n, const int32_t* type, const
     return DTC_OK;
 }
 
+int dtc_program_set_exec_layers(dtc_program* p, int n_exec_layers) {
+    if (!p || p->h.finalized) return fail(DTC_ERR_INVALID, "program is NULL or finalized");
+    if (n_exec_layers < 1 || n_exec_layers > p->h.n_layers) return fail(DTC_ERR_INVALID, "n_exec_layers out of range");
+    p->h.n_exec_layers = n_exec_layers;
+    return DTC_OK;
+}
+
 int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
     if (!p) return fail(DTC_ERR_INVALID, "program is NULL");
     if (p->h.finalized) return fail(DTC_ERR_INVALID, "program already finalized");
@@ -452,7 +524,7 @@ int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
     if (engine == DTC_ENGINE_TILE) {
         if (!dtc_schedule_tile(p->h, err)) return fail(DTC_ERR_INVALID, err);
     } else if (engine == DTC_ENGINE_GENERIC) {
-        for (int j = 0; j < p->h.n_layers; ++j)
+        for (int j = 0; j < p->h.n_exec_layers; ++j)
             if (n_local < 64 && (p->h.layers[j].rot_any >> n_local))
                 return fail(DTC_ERR_INVALID, "rotation on a non-local qubit");
         dtc_schedule_generic(p->h);
@@ -534,8 +606,8 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
         const long long grid = n_traj << (h.n_local - DTC_TILE_BITS);
         if (grid > 0x7fffffffLL) return fail(DTC_ERR_INVALID, "batch too large for one launch");
         static const int pf = []() {
-            const char* e = getenv("DTCSIM_PREFETCH_BLOCKS");      // tuning knob; default one wave of 148 x 3 CTAs
-            return e ? atoi(e) : 444;
+            const char* e = getenv("DTCSIM_PREFETCH_BLOCKS");      // tuning knob; default 148 CTAs ahead (measured best on B200)
+            return e ? atoi(e) : 148;
         }();
         for (const DtcTilePass& T : h.passes) {
             const bool hx = T.layerD >= 0 && T.nX > 0;
@@ -617,6 +689,27 @@ int dtc_probs(const void* state, int n_local, int64_t n_traj, int k, const int32
     const int cpt = chunks_for(n_local);
     k_probs<<<(unsigned)(n_traj * cpt), 256, sizeof(double) << k, s>>>((const double2*)state, n_local, n_traj, k, dq,
                                                                      (const u64*)fx, out, cpt);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(dq, s));
+    return DTC_OK;
+}
+
+int dtc_rdm(const void* state, int n_local, int64_t n_traj, int k, const int32_t* qubits, void* out, void* stream) {
+    if (!state || !out || k < 0 || k > 2 || k > n_local || (k > 0 && !qubits)) return fail(DTC_ERR_INVALID, "bad argument (k <= 2)");
+    if (k == 2 && qubits[0] == qubits[1]) return fail(DTC_ERR_INVALID, "duplicate qubit");
+    cudaStream_t s = (cudaStream_t)stream;
+    int* dq = nullptr;
+    CUDA_TRY(cudaMallocAsync(&dq, sizeof(int) * 2, s));
+    if (k) CUDA_TRY(cudaMemcpyAsync(dq, qubits, sizeof(int) * k, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double2) * ((size_t)n_traj << (2 * k)), s));
+    int cb = n_local - k - 13;
+    if (cb < 0) cb = 0;
+    if (cb > 8) cb = 8;
+    const int cpt = 1 << cb;
+    const unsigned grid = (unsigned)(n_traj * cpt);
+    if (k == 0) k_rdm<0><<<grid, 256, 0, s>>>((const double2*)state, n_local, n_traj, dq, (double2*)out, cpt);
+    else if (k == 1) k_rdm<1><<<grid, 256, 0, s>>>((const double2*)state, n_local, n_traj, dq, (double2*)out, cpt);
+    else k_rdm<2><<<grid, 256, 0, s>>>((const double2*)state, n_local, n_traj, dq, (double2*)out, cpt);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaFreeAsync(dq, s));
     return DTC_OK;

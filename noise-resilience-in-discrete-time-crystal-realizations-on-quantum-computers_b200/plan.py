@@ -30,7 +30,8 @@ import numpy as np
 from .ir import QuantumCircuit, as_circuit
 
 PI = math.pi
-EV_ROT, EV_D1, EV_D2, EV_NOISE = 0, 1, 2, 3
+EV_ROT, EV_D1, EV_D2, EV_NOISE, EV_D2C = 0, 1, 2, 3, 4
+VIRTUAL_QUBIT = 63        # table partner of D2C terms: an index bit that is always 0
 MAX_D2_PER_LAYER = 64
 
 _U3_OF = {  # name -> (theta, phi, lam, extra global phase) with U = e^{i extra} u3(theta,phi,lam)
@@ -60,7 +61,10 @@ class Program:
     """Compiled circuit: event arrays for the CUDA library + read-out description."""
 
     def __init__(self):
-        self.n = 0
+        self.n = 0                  # all active qubits
+        self.n_main = 0             # qubits held in the device register (< n when optimize eliminates some)
+        self.n_exec_layers = 1      # layers the device executes; layers beyond belong to prog.small
+        self.small = None           # read-out factorisation plan (see compile_circuit)
         self.n_clbits = 0
         self.active = []            # original (wide-circuit) index of each compacted qubit
         self.order = []             # order[bit] = compacted qubit stored at index bit `bit`
@@ -208,87 +212,36 @@ def _fuse_cx_rz_cx(ops, noisy):
     return out
 
 
-class _Builder:
-    def __init__(self, n):
-        self.p = Program()
-        self.p.n = n
-        self.last_r = [0] * n
-        self.epoch = [0] * n
-        self.d1_slots = {}                    # (layer, q) -> [(epoch, event index), ...]
-        self.d2_terms = {}                    # (layer, i, j, epoch_i, epoch_j) -> event index
-        self.d2_count = defaultdict(int)
-        self.prims = []                       # linear primitive list for the DM engine
+class _Prims:
+    """Lowers gates to the primitive list ("R"|"D"|"N", qubits, value) in circuit order (compacted qubits)."""
 
-    def _emit(self, typ, layer, q0, q1, slot, val, probs=None):
-        p = self.p
-        p.ev_type.append(typ)
-        p.ev_layer.append(layer)
-        p.ev_q0.append(q0)
-        p.ev_q1.append(q1)
-        p.ev_slot.append(slot)
-        p.ev_val.append(val)
-        p.ev_probs.append(probs)
-        return len(p.ev_type) - 1
+    def __init__(self):
+        self.prims = []
+        self.global_phase = 0.0
 
     def rot(self, q, theta):
-        if theta == 0.0:
-            return
-        self.prims.append(("R", (q,), theta))
-        self.last_r[q] += 1
-        self._emit(EV_ROT, self.last_r[q], q, -1, 0, theta)
+        if theta != 0.0:
+            self.prims.append(("R", (q,), theta))
 
     def d1(self, q, a):
-        if a == 0.0:
-            return
-        self.prims.append(("D", (q,), a))
-        while True:
-            layer = self.last_r[q]
-            slots = self.d1_slots.setdefault((layer, q), [])
-            for ep, ev in slots:
-                if ep == self.epoch[q]:
-                    self.p.ev_val[ev] += a
-                    return
-            if len(slots) < 2:
-                ev = self._emit(EV_D1, layer, q, -1, len(slots), a)
-                slots.append((self.epoch[q], ev))
-                return
-            self.last_r[q] += 1               # both sign slots taken: advance q to the next layer
+        if a != 0.0:
+            self.prims.append(("D", (q,), a))
 
     def d2(self, i, j, b):
-        if b == 0.0:
-            return
-        if i > j:
-            i, j = j, i
-        self.prims.append(("D", (i, j), b))
-        layer = max(self.last_r[i], self.last_r[j])
-        while True:
-            key = (layer, i, j, self.epoch[i], self.epoch[j])
-            ev = self.d2_terms.get(key)
-            if ev is not None:
-                self.p.ev_val[ev] += b
-                break
-            if self.d2_count[layer] < MAX_D2_PER_LAYER:
-                ev = self._emit(EV_D2, layer, i, j, self.d2_count[layer], b)
-                self.d2_count[layer] += 1
-                self.d2_terms[key] = ev
-                break
-            layer += 1
-        self.last_r[i] = self.last_r[j] = layer
+        if b != 0.0:
+            self.prims.append(("D", (min(i, j), max(i, j)), b))
 
     def noise(self, q, probs):
         self.prims.append(("N", (q,), tuple(probs)))
-        self._emit(EV_NOISE, self.last_r[q], q, -1, self.p.n_sites, 0.0, tuple(probs))
-        self.p.n_sites += 1
-        self.epoch[q] += 1
 
     def u3(self, q, theta, phi, lam, extra=0.0):
-        self.p.global_phase += extra + (phi + lam) / 2
+        self.global_phase += extra + (phi + lam) / 2
         self.d1(q, lam - PI / 2)
         self.rot(q, theta)
         self.d1(q, phi + PI / 2)
 
     def cz(self, a, b):
-        self.p.global_phase += PI / 4
+        self.global_phase += PI / 4
         self.d1(a, PI / 2)
         self.d1(b, PI / 2)
         self.d2(a, b, -PI / 2)
@@ -302,6 +255,141 @@ class _Builder:
         self.ry(t, -PI / 2)
         self.cz(c, t)
         self.ry(t, PI / 2)
+
+
+def _is_pauli_rotation(theta):
+    """RX(k pi) is a Pauli up to phase: it goes to the frame and leaves psi' untouched."""
+    k = round(theta / PI)
+    return theta - k * PI == 0.0
+
+
+class _Layerer:
+    """Assigns primitives of one domain (main register or the small read-out simulation) to layers and
+    appends the corresponding events to the program."""
+
+    def __init__(self, prog, n):
+        self.p = prog
+        self.last_r = [0] * n
+        self.epoch = [0] * n
+        self.d1_slots = {}
+        self.d2_terms = {}
+        self.d2_count = defaultdict(int)
+        self.events = []                      # indices of the events this domain emitted
+
+    def _emit(self, typ, layer, q0, q1, slot, val, probs=None):
+        p = self.p
+        p.ev_type.append(typ)
+        p.ev_layer.append(layer)
+        p.ev_q0.append(q0)
+        p.ev_q1.append(q1)
+        p.ev_slot.append(slot)
+        p.ev_val.append(val)
+        p.ev_probs.append(probs)
+        self.events.append(len(p.ev_type) - 1)
+        return len(p.ev_type) - 1
+
+    def rot(self, q, theta):
+        if _is_pauli_rotation(theta):
+            # RX(k pi) only updates the frame: no state layer, but later D1 terms need a fresh sign slot
+            self._emit(EV_ROT, self.last_r[q], q, -1, 0, theta)
+            self.epoch[q] += 1
+            return
+        self.last_r[q] += 1
+        self._emit(EV_ROT, self.last_r[q], q, -1, 0, theta)
+
+    def d1(self, q, a):
+        while True:
+            layer = self.last_r[q]
+            slots = self.d1_slots.setdefault((layer, q), [])
+            for ep, ev in slots:
+                if ep == self.epoch[q]:
+                    self.p.ev_val[ev] += a
+                    return
+            if len(slots) < 2:
+                ev = self._emit(EV_D1, layer, q, -1, len(slots), a)
+                slots.append((self.epoch[q], ev))
+                return
+            self.last_r[q] += 1               # both sign slots taken: advance q to the next layer
+
+    def d2(self, i, j, b, classical_partner=False):
+        """classical_partner: j is still |0> in psi' -> the term is a one-body phase on i (event D2C)."""
+        layer = self.last_r[i] if classical_partner else max(self.last_r[i], self.last_r[j])
+        while True:
+            key = (layer, i, j, self.epoch[i], self.epoch[j], classical_partner)
+            ev = self.d2_terms.get(key)
+            if ev is not None:
+                self.p.ev_val[ev] += b
+                break
+            if self.d2_count[layer] < MAX_D2_PER_LAYER:
+                ev = self._emit(EV_D2C if classical_partner else EV_D2, layer, i, j, self.d2_count[layer], b)
+                self.d2_count[layer] += 1
+                self.d2_terms[key] = ev
+                break
+            layer += 1
+        self.last_r[i] = layer
+        if not classical_partner:
+            self.last_r[j] = layer
+
+    def noise(self, q, probs, site):
+        self._emit(EV_NOISE, self.last_r[q], q, -1, site, 0.0, tuple(probs))
+        self.epoch[q] += 1
+
+
+def _analyse_readout(prims, n, measured):
+    """Find (E, K, cut): qubits E that never need to enter the big register and the suffix prims[cut:]
+    that touches only the small set K (the Hadamard-test ancilla factorises).
+
+    A D2 term whose partner is still classical (never rotated: |0> in psi') is a one-body phase on the
+    other qubit.  Qubit a is eliminable if every genuinely two-body term on it lies in a suffix of the
+    circuit that touches at most 3 qubits K containing all measured qubits.  Then the state on the other
+    qubits is evolved alone, its reduced density matrix on K \\ E is read back, and the few suffix
+    operations are applied to a |K|-qubit density matrix per trajectory on the host.
+    Returns (E, K_reg, cut, kinds) or None; kinds[idx] = (quantum side, classical partner) for D2 prims.
+    """
+    classical = [True] * n
+    kinds = {}
+    for idx, (typ, qs, val) in enumerate(prims):
+        if typ == "R":
+            if not _is_pauli_rotation(val):
+                classical[qs[0]] = False
+        elif typ == "D" and len(qs) == 2:
+            i, j = qs
+            if classical[j]:
+                kinds[idx] = (i, j)
+            elif classical[i]:
+                kinds[idx] = (j, i)
+    if not measured or len(set(measured)) > 3:
+        return None
+    K0 = set(measured)
+    partners = set()
+    for idx, (typ, qs, val) in enumerate(prims):
+        if typ == "D" and len(qs) == 2 and idx not in kinds and (set(qs) & K0):
+            partners |= set(qs)
+    for K in ([K0 | partners] if len(K0 | partners) <= 3 else []) + [K0]:
+        cut = 0
+        for idx, (typ, qs, val) in enumerate(prims):
+            touched = set(qs) if idx not in kinds else {kinds[idx][0]}
+            if touched - K:
+                cut = idx + 1
+        E = set()
+        for a in K:
+            ok = True
+            for idx, (typ, qs, val) in enumerate(prims[:cut]):
+                if a not in qs:
+                    continue
+                if typ == "D" and len(qs) == 2 and (idx not in kinds or kinds[idx][0] != a):
+                    ok = False            # entangling term (or a is the classical side) before the cut
+                    break
+            if ok:
+                E.add(a)
+        # a classical partner of an eliminated qubit must not itself be eliminated
+        for idx, (side, part) in kinds.items():
+            if side in E and part in E:
+                E.discard(part)
+        K_reg = K - E
+        if E and len(K_reg) <= 2 and len(E) < n:
+            return sorted(E), sorted(K_reg), cut, kinds
+    return None
 
 
 def _segment_dm(prims):
@@ -343,8 +431,14 @@ def _segment_dm(prims):
     return out
 
 
-def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True):
+def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True, optimize=False):
     """Compile a (transpiled) circuit + noise model into a :class:`Program`.
+
+    optimize=True enables the read-out factorisation (see _analyse_readout): qubits that only couple to
+    the rest through a small measured suffix are kept out of the big register (prog.n_main < prog.n)
+    and the suffix runs on a tiny density matrix per trajectory (prog.small).  Counts and expectation
+    values are unchanged; the full statevector is then not available, so amplitude-level consumers
+    compile with optimize=False.
 
     Raises ValueError for anything the device path cannot execute exactly (unsupported gate,
     noise on a multi-qubit gate, mid-circuit measurement) -- there is no CPU fallback.
@@ -359,19 +453,6 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True):
         raise ValueError("circuit has no active qubits")
     if n > 62:
         raise ValueError(f"{n} active qubits exceed the 62-qubit index limit")
-    pairs = [(cmap[o.qubits[0]], cmap[o.qubits[1]]) for o in circ.ops if len(o.qubits) == 2]
-    order = choose_bit_order(n, pairs) if reorder else list(range(n))
-    bit_of = [0] * n
-    for bit, cq in enumerate(order):
-        bit_of[cq] = bit
-    remap = {q: bit_of[c] for q, c in cmap.items()}
-    b = _Builder(n)
-    prog = b.p
-    prog.active = used
-    prog.order = order
-    prog.bit_of = bit_of
-    prog.n_clbits = circ.num_clbits
-    prog.global_phase = float(circ.global_phase)
 
     def probs_of(op):
         if noise_model is None or op.name in ("measure", "barrier"):
@@ -382,6 +463,9 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True):
             return None
         return noise_model.lookup(op.name, op.qubits[0])
 
+    # ---- stage 1: gates -> primitives on compacted qubit indices
+    b = _Prims()
+    b.global_phase = float(circ.global_phase)
     ops = [o for o in circ.ops if o.name != "barrier"]
     ops = _fuse_cx_rz_cx(ops, lambda o: probs_of(o) is not None)
     measured = {}
@@ -389,14 +473,14 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True):
     for op in ops:
         if isinstance(op, tuple):                      # fused cx-rz-cx
             _, (a, c), ang, ph = op
-            qa, qc = remap[a], remap[c]
+            qa, qc = cmap[a], cmap[c]
             if qa in finished or qc in finished:
                 raise ValueError("gate after measurement (mid-circuit measurement is not supported)")
-            prog.global_phase += ph
+            b.global_phase += ph
             b.d2(qa, qc, ang)
             continue
         nm = op.name
-        qs = [remap[q] for q in op.qubits]
+        qs = [cmap[q] for q in op.qubits]
         if nm == "measure":
             measured[op.clbits[0]] = qs[0]
             finished.add(qs[0])
@@ -408,15 +492,15 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True):
             b.u3(qs[0], th, ph, lam, extra)
         elif nm in _DIAG_OF:
             ang, ph = _DIAG_OF[nm](op.params)
-            prog.global_phase += ph
+            b.global_phase += ph
             b.d1(qs[0], ang)
         elif nm == "rx":
             b.rot(qs[0], op.params[0])
         elif nm == "sx":
-            prog.global_phase += PI / 4
+            b.global_phase += PI / 4
             b.rot(qs[0], PI / 2)
         elif nm == "sxdg":
-            prog.global_phase -= PI / 4
+            b.global_phase -= PI / 4
             b.rot(qs[0], -PI / 2)
         elif nm == "id":
             pass
@@ -433,9 +517,60 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True):
         pr = probs_of(op)
         if pr is not None:
             b.noise(qs[0], pr)
-    prog.n_layers = max(b.last_r) + 1
-    prog.rot_layers = len({l for t, l in zip(prog.ev_type, prog.ev_layer) if t == EV_ROT})
-    prog.measures = sorted(((q, c) for c, q in measured.items()), key=lambda qc: qc[1])
+    prims = b.prims
+
+    # ---- stage 2: read-out analysis and internal bit order (eliminated qubits become the top bits)
+    plan = _analyse_readout(prims, n, sorted(set(measured.values()))) if optimize else None
+    elim = plan[0] if plan else []
+    pairs = [qs for typ, qs, _ in prims if typ == "D" and len(qs) == 2]
+    order = choose_bit_order(n, pairs) if reorder else list(range(n))
+    order = [q for q in order if q not in elim] + [q for q in order if q in elim]
+    bit_of = [0] * n
+    for bit, cq in enumerate(order):
+        bit_of[cq] = bit
+
+    prog = Program()
+    prog.n = n
+    prog.n_main = n - len(elim)
+    prog.active = used
+    prog.order = order
+    prog.bit_of = bit_of
+    prog.n_clbits = circ.num_clbits
+    prog.global_phase = b.global_phase
+
+    # ---- stage 3: primitives -> layered events (main register, then the small read-out domain)
+    main = _Layerer(prog, n)
+    small = _Layerer(prog, n)
+    cut = plan[2] if plan else len(prims)
+    kinds = plan[3] if plan else {}
+    E = set(elim)
+    for idx, (typ, qs, val) in enumerate(prims):
+        in_small = bool(plan) and (idx >= cut or bool(set(qs) & E and (idx not in kinds or kinds[idx][0] in E)))
+        dom = small if in_small else main
+        bq = tuple(bit_of[q] for q in qs)
+        if typ == "R":
+            dom.rot(bq[0], val)
+        elif typ == "N":
+            dom.noise(bq[0], val, prog.n_sites)
+            prog.n_sites += 1
+        elif len(qs) == 1:
+            dom.d1(bq[0], val)
+        elif idx in kinds:                                # partner still classical: one-body phase
+            side, part = kinds[idx]
+            dom.d2(bit_of[side], bit_of[part], val, classical_partner=True)
+        else:
+            dom.d2(min(bq), max(bq), val)
+    prog.n_exec_layers = max(main.last_r) + 1
+    n_small_layers = max(small.last_r) + 1 if small.events else 0
+    for e in small.events:
+        prog.ev_layer[e] += prog.n_exec_layers
+    prog.n_layers = prog.n_exec_layers + n_small_layers
+    prog.rot_layers = len({prog.ev_layer[e] for e in main.events if prog.ev_type[e] == EV_ROT})
+    prog.measures = sorted(((bit_of[q], c) for c, q in measured.items()), key=lambda qc: qc[1])
+    if plan:
+        prog.small = dict(events=sorted(small.events), elim_bits=sorted(bit_of[q] for q in elim),
+                          reg_bits=sorted(bit_of[q] for q in plan[1]), first_layer=prog.n_exec_layers,
+                          n_layers=n_small_layers)
     if want_dm:
-        prog.dm_segments = _segment_dm(b.prims)
+        prog.dm_segments = _segment_dm([(t, tuple(bit_of[q] for q in qs), v) for t, qs, v in prims])
     return prog

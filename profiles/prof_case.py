@@ -13,20 +13,20 @@ import dtcsim  # noqa: E402
 from dtcsim import backend, capi  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-ntraj = int(sys.argv[2]) if len(sys.argv) > 2 else 96
+ntraj = int(sys.argv[2]) if len(sys.argv) > 2 else 192
 hs, phis = bench.load_disorder(0)
 noise = dtcsim.NoiseModel()
 noise.add_all_qubit_quantum_error(dtcsim.depolarizing_error(0.05, 1), ["u1", "u2", "u3"])
 circ = bench.qc_circuit(dtcsim, hs, phis, 8, False)
-prog = dtcsim.compile_circuit(circ, dtcsim.as_noise_model(noise))
+prog = dtcsim.compile_circuit(circ, dtcsim.as_noise_model(noise), optimize=True)
 ctx = backend.DeviceContext(0)
 h = capi.ProgramHandle(prog, 0)
 h.set_profiling(True)
-state = ctx.empty(ntraj << prog.n, torch.complex128)
+state = ctx.empty(ntraj << prog.n_main, torch.complex128)
 for r in range(reps):
     b = backend.evolve(ctx, prog, ntraj, 0, 1 + r, handle=h, state=state)
     ms, n = h.pass_time()
-    gbs = n * 2 * 16 * (1 << prog.n) * ntraj / (ms * 1e-3) / 1e9
+    gbs = n * 2 * 16 * (1 << prog.n_main) * ntraj / (ms * 1e-3) / 1e9
     print(f"rep {r}: {n} passes in {ms:.3f} ms -> {ms / n * 1e3:.1f} us/pass, {gbs:.0f} GB/s algorithmic")
-p = b.probs([prog.measures[0][0]]).cpu().numpy()
+p = b.outcome_probs().cpu().numpy()
 print("mean <Z>", float((p[:, 0] - p[:, 1]).mean()))

@@ -37,7 +37,7 @@ def _p(a, ct):
 def run(prog, n_traj=1, traj_offset=0, seed=0, init_index=0, engine=0, n_local=None, rank_bits=0):
     """Execute a compiled Program on the emulator. Returns (psi' [T,2^n_local], fx, fz, ph, n_passes)."""
     ev = prog.arrays()
-    n_local = prog.n if n_local is None else n_local
+    n_local = prog.n_main if n_local is None else n_local
     state = np.zeros((n_traj, 1 << n_local), dtype=np.complex128)
     fx = np.zeros(n_traj, dtype=np.uint64)
     fz = np.zeros(n_traj, dtype=np.uint64)
@@ -49,7 +49,7 @@ def run(prog, n_traj=1, traj_offset=0, seed=0, init_index=0, engine=0, n_local=N
         _p(ev["type"], ctypes.c_int32), _p(ev["layer"], ctypes.c_int32), _p(ev["q0"], ctypes.c_int32),
         _p(ev["q1"], ctypes.c_int32), _p(ev["slot"], ctypes.c_int32), _p(ev["val"], ctypes.c_double),
         _p(ev["probs"], ctypes.c_double), ctypes.c_double(prog.global_phase), ctypes.c_int(engine),
-        ctypes.c_int(n_local), ctypes.c_int64(n_traj), ctypes.c_int64(traj_offset), ctypes.c_uint64(seed),
+        ctypes.c_int(n_local), ctypes.c_int(prog.n_exec_layers), ctypes.c_int64(n_traj), ctypes.c_int64(traj_offset), ctypes.c_uint64(seed),
         ctypes.c_uint64(init_index), ctypes.c_uint64(rank_bits),
         state.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _p(fx, ctypes.c_uint64), _p(fz, ctypes.c_uint64),
         _p(ph, ctypes.c_int32), ctypes.byref(npass), err, ctypes.c_int(512))
@@ -60,14 +60,14 @@ def run(prog, n_traj=1, traj_offset=0, seed=0, init_index=0, engine=0, n_local=N
 
 def schedule(prog, n_local=None, cap=4096):
     ev = prog.arrays()
-    n_local = prog.n if n_local is None else n_local
+    n_local = prog.n_main if n_local is None else n_local
     rows = np.zeros((cap, 21), dtype=np.int32)
     err = ctypes.create_string_buffer(512)
     n = lib().emu_schedule(
         ctypes.c_int(prog.n), ctypes.c_int(prog.n_layers), ctypes.c_int64(len(ev["type"])),
         _p(ev["type"], ctypes.c_int32), _p(ev["layer"], ctypes.c_int32), _p(ev["q0"], ctypes.c_int32),
         _p(ev["q1"], ctypes.c_int32), _p(ev["slot"], ctypes.c_int32), _p(ev["val"], ctypes.c_double),
-        _p(ev["probs"], ctypes.c_double), ctypes.c_int(n_local), _p(rows, ctypes.c_int32), ctypes.c_int(cap),
+        _p(ev["probs"], ctypes.c_double), ctypes.c_int(n_local), ctypes.c_int(prog.n_exec_layers), _p(rows, ctypes.c_int32), ctypes.c_int(cap),
         err, ctypes.c_int(512))
     if n < 0:
         raise ValueError(err.value.decode())

@@ -57,12 +57,13 @@ static void emu_tile_pass(double2* state, const DtcTilePass& P, const DtcLayer* 
 
 extern "C" int emu_run(int n_qubits, int n_layers, int64_t n_events, const int32_t* type, const int32_t* layer,
                        const int32_t* q0, const int32_t* q1, const int32_t* slot, const double* val,
-                       const double* probs, double global_phase, int engine, int n_local, int64_t n_traj,
+                       const double* probs, double global_phase, int engine, int n_local, int n_exec_layers, int64_t n_traj,
                        int64_t traj_offset, u64 seed, u64 init_index, u64 rank_bits, double* state_out,
                        u64* fx, u64* fz, int* ph, int* n_passes, char* errbuf, int errlen) {
     DtcProgramHost P;
     P.n_qubits = n_qubits;
     P.n_layers = n_layers;
+    P.n_exec_layers = n_exec_layers > 0 ? n_exec_layers : n_layers;
     P.n_local = n_local;
     std::string err;
     auto bail = [&](const std::string& m) {
@@ -132,10 +133,11 @@ extern "C" int emu_run(int n_qubits, int n_layers, int64_t n_events, const int32
 // [s2_lo, layerA, layerD, layerB, nT1, nT2, nX, nC, nO, tb0..tb11]
 extern "C" int emu_schedule(int n_qubits, int n_layers, int64_t n_events, const int32_t* type, const int32_t* layer,
                             const int32_t* q0, const int32_t* q1, const int32_t* slot, const double* val,
-                            const double* probs, int n_local, int32_t* rows, int cap, char* errbuf, int errlen) {
+                            const double* probs, int n_local, int n_exec_layers, int32_t* rows, int cap, char* errbuf, int errlen) {
     DtcProgramHost P;
     P.n_qubits = n_qubits;
     P.n_layers = n_layers;
+    P.n_exec_layers = n_exec_layers > 0 ? n_exec_layers : n_layers;
     P.n_local = n_local;
     std::string err;
     if (!dtc_stage_events(P, n_events, type, layer, q0, q1, slot, val, probs, 0.0, err) || !dtc_build_layers(P, err) ||

@@ -11,13 +11,14 @@ import numpy as np
 
 from oracle import philox
 
-EV_ROT, EV_D1, EV_D2, EV_NOISE = 0, 1, 2, 3
+EV_ROT, EV_D1, EV_D2, EV_NOISE, EV_D2C = 0, 1, 2, 3, 4
 
 
 def build_layers(prog):
     """Host-side table prep (mirrors dtc_program_finalize)."""
     n, M = prog.n, prog.n_layers
     L = [dict(tan=np.zeros(n), scale=1.0, a=np.zeros((2, n)), terms=[]) for _ in range(M)]
+    nm = prog.n_main
     ev = prog.arrays()
     k_of = np.zeros(len(ev["type"]), dtype=np.int64)
     for e in range(len(ev["type"])):
@@ -26,15 +27,18 @@ def build_layers(prog):
         if t == EV_ROT:
             k = int(np.rint(val / math.pi))
             th = val - k * math.pi
-            assert L[lay]["tan"][q0] == 0.0, "two rotations on one qubit in one layer"
-            L[lay]["tan"][q0] = math.tan(th / 2)
-            L[lay]["scale"] *= math.cos(th / 2)
-            k_of[e] = k % 4
+            if math.tan(th / 2) != 0.0:
+                assert L[lay]["tan"][q0] == 0.0, "two rotations on one qubit in one layer"
+                L[lay]["tan"][q0] = math.tan(th / 2)
+                L[lay]["scale"] *= math.cos(th / 2)
+                k_of[e] = k % 4
+            else:
+                k_of[e] = (k % 4) + 4                    # +4 marks a pure Pauli RX(k pi): no sign bit
         elif t == EV_D1:
             L[lay]["a"][slot, q0] = val
-        elif t == EV_D2:
+        elif t in (EV_D2, EV_D2C):
             assert slot == len(L[lay]["terms"])
-            L[lay]["terms"].append((q0, q1, val))
+            L[lay]["terms"].append((q0, q1 if t == EV_D2 else -1, val))     # -1: partner is |0> in psi'
     return L, k_of
 
 
@@ -53,14 +57,15 @@ def frame_walk(prog, k_of, seed, trajs):
                                 int(ev["q1"][e]), int(ev["slot"][e]))
         b0 = np.uint64(q0)
         if t == EV_ROT:
-            masks[lay, 0] |= ((fz >> b0) & one) << b0
-            k = int(k_of[e])
+            if k_of[e] < 4:
+                masks[lay, 0] |= ((fz >> b0) & one) << b0
+            k = int(k_of[e]) % 4
             if k & 1:
                 fx ^= one << b0
             ph += 3 * k
         elif t == EV_D1:
             masks[lay, 1 + slot] |= ((fx >> b0) & one) << b0
-        elif t == EV_D2:
+        elif t in (EV_D2, EV_D2C):
             b1 = np.uint64(q1)
             masks[lay, 3] |= (((fx >> b0) ^ (fx >> b1)) & one) << np.uint64(slot)
         elif t == EV_NOISE:
@@ -104,7 +109,7 @@ def diag_phase(layer, const, n, m1a, m1b, m2):
                 sg = 1.0 - 2.0 * ((m >> np.uint64(q)) & one).astype(np.float64)
                 ph *= math.cos(a / 2) - 1j * math.sin(a / 2) * sg[:, None] * z[None, :]
     for k, (i, j, b) in enumerate(layer["terms"]):
-        zz = (1.0 - 2.0 * _bits(n, i)) * (1.0 - 2.0 * _bits(n, j))
+        zz = (1.0 - 2.0 * _bits(n, i)) * ((1.0 - 2.0 * _bits(n, j)) if j >= 0 else 1.0)
         sg = 1.0 - 2.0 * ((m2 >> np.uint64(k)) & one).astype(np.float64)
         ph *= math.cos(b / 2) - 1j * math.sin(b / 2) * sg[:, None] * zz[None, :]
     return ph
@@ -112,8 +117,9 @@ def diag_phase(layer, const, n, m1a, m1b, m2):
 
 def run(prog, seed=0, trajs=(0,), init_index=0, materialize=True):
     """Execute the program for the given trajectory ids; returns psi_true [T, 2^n] (or psi', frame)."""
-    n = prog.n
+    n = prog.n_main                                   # < prog.n when the read-out is factorised
     layers, k_of = build_layers(prog)
+    layers = layers[:prog.n_exec_layers]
     masks, fx, fz, ph = frame_walk(prog, k_of, seed, trajs)
     T = len(trajs)
     psi = np.zeros((T, 1 << n), dtype=np.complex128)

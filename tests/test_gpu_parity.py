@@ -312,3 +312,37 @@ def test_error_paths(ctx):
     h = ctypes.c_void_p()
     assert capi.load().dtc_program_create(0, 1, ctypes.byref(h)) == -1
     assert b"n_qubits" in capi.load().dtc_last_error()
+
+
+# ----------------------------------------------------------------------------------- read-out factorisation
+def test_rdm_kernel(ctx, disorder):
+    from dtcsim import backend
+    hs, phis = disorder[20][0][3][:13], disorder[20][1][3][:12]
+    circ = RC.transpiled(RC.qc_body("vacuum", 13, 0.9, hs, phis, 2, 6, False))
+    prog = compile_circuit(circ, RC.noise_model(0.3))
+    batch = backend.evolve(ctx, prog, 8, 0, 3)
+    r2 = batch.rdm([5, 2]).cpu().numpy()
+    r1 = batch.rdm([11]).cpu().numpy()
+    r0 = batch.rdm([]).cpu().numpy()
+    psi = batch.state.view(8, -1).cpu().numpy()
+    from test_readout_factorisation import _rdm
+    assert np.abs(r2 - _rdm(psi, prog.n, [5, 2])).max() < 1e-12
+    assert np.abs(r1 - _rdm(psi, prog.n, [11])).max() < 1e-12
+    assert np.abs(r0[:, 0, 0] - 1).max() < 1e-12
+
+
+def test_factorised_run_equals_full_run(disorder):
+    """run() with the ancilla factorised out (default) == run() on the full register == oracle counts."""
+    hs, phis = disorder[20][0][0][:12], disorder[20][1][0][:11]
+    nm = RC.noise_model(0.05)
+    fast = dtcsim.AerSimulator(noise_model=nm)
+    full = dtcsim.AerSimulator(noise_model=nm, optimize=False)
+    for t, echo, state in ((0, False, "vacuum"), (2, False, "neel"), (3, True, "vacuum")):
+        circ = RC.transpiled(RC.qc_body(state, 12, 0.97, hs, phis, t, 6, echo))
+        r1 = fast.run(circ, shots=300, seed_simulator=42).result()
+        r2 = full.run(circ, shots=300, seed_simulator=42).result()
+        assert r1.data()["register_qubits"] == (12 if t else 1) and r2.data()["register_qubits"] == (13 if t else 2)
+        assert r1.get_counts() == r2.get_counts()
+        assert abs(r1.expectation_z()[0] - r2.expectation_z()[0]) < 1e-12
+        want, _ = O.run_counts(RC.ops_of(circ), 31, 1, shots=300, noise=O.PauliNoise.depolarizing(0.05), seed=42)
+        assert r1.get_counts() == want
