@@ -340,6 +340,22 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
                 if ((r >> k) & 1) o += 1ull << T.tb[T.s2_lo + 5 + k];
             T.roff[r] = o;
         }
+        {
+            const int S1 = T.s2_lo + 5;
+            for (int b = 0; b < 7; ++b) T.tid_off[b] = 1ull << T.tb[b < S1 ? b : b + 5];
+            u64 used = 0;
+            for (int l = 0; l < DTC_TILE_BITS; ++l) used |= 1ull << T.tb[l];
+            T.seg_n = 0;
+            int src = 0, pos = 0;
+            while (pos < n) {
+                if ((used >> pos) & 1ull) { ++pos; continue; }
+                int len = 0;
+                while (pos + len < n && !((used >> (pos + len)) & 1ull)) ++len;
+                if (T.seg_n >= 8) { err = "internal: too many tile index segments"; return false; }
+                T.seg_src[T.seg_n] = src; T.seg_len[T.seg_n] = len; T.seg_dst[T.seg_n] = pos; ++T.seg_n;
+                src += len; pos += len;
+            }
+        }
         P.passes.push_back(T);
         if (complete) {
             ++j;

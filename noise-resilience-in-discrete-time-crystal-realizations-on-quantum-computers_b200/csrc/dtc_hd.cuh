@@ -69,6 +69,9 @@ struct DtcTilePass {
     double t1[DTC_TILE_BITS];      // tan for R_A on local bit l (0: none in this pass)
     double t2[DTC_TILE_BITS];      // tan for R_B
     u64 roff[DTC_NREG];            // global offset of register r in phases 1/3 (sum of S1 strides)
+    u64 tid_off[7];                // global offset contributed by thread-id bit b in phases 1/3
+    int seg_n;                     // tile counter -> global base: sum over segments of
+    int seg_src[8], seg_len[8], seg_dst[8];   //   ((tile >> src) & ((1 << len) - 1)) << dst
     // classification of D_layerD's two-body terms relative to this tile
     int nT1, nT2, nX, nC, nO;
     unsigned char T1k[DTC_MAXT], T1a[DTC_MAXT], T1b[DTC_MAXT];   // both ends in local [0, s1_lo]
@@ -193,9 +196,10 @@ DTC_HD void rot_pair(double2& x0, double2& x1, double t) {
 }
 
 // ------------------------------------------------------------------------------------ tile engine
+#define DTC_TILE_PAD (DTC_TILE + 128)     // phys(l) = l + (l >> S1), S1 >= 5
 struct TileSmem {
-    double2 tile[DTC_TILE];
-    double2 T1[256];
+    double2 tile[DTC_TILE_PAD];
+    double2 T1[256 + 8];
     double2 T2[128];
     double2 E[DTC_TILE_BITS][2];
     double2 B[DTC_MAXT][2];
@@ -204,7 +208,11 @@ struct TileSmem {
     u64 rmA, rmB;      // rotation sign masks of the trajectory
 };
 
-DTC_HD int tile_swz(int l) { return l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9)) & 7); }
+// Shared-memory layout: one padding chunk (16 B) after every 2^S1 chunks.  For l = T | R (thread bits and
+// register bits disjoint) phys(l) = phys(T) + phys(R), so every access is thread base + compile-time constant;
+// quarter-warps hit 8 distinct 16 B bank groups in all three phases (no conflicts).
+template <int S2_LO>
+DTC_HD int tile_pad(int l) { return l + (l >> (S2_LO + 5)); }
 
 // local index of (thread, register) in phases 1 and 3 (register bits = S1)
 template <int S2_LO>
@@ -220,38 +228,22 @@ DTC_HD int tile_local_p2(int tid, int r) {
     return (r << S2_LO) | ((tid & ((1 << NH) - 1)) << S1) | (tid >> NH);
 }
 
-DTC_HD u64 tile_deposit_local(int l, const int* tb) {
-    u64 o = 0;
-#pragma unroll
-    for (int b = 0; b < DTC_TILE_BITS; ++b)
-        if ((l >> b) & 1) o |= 1ull << tb[b];
-    return o;
-}
-
-// spread the tile counter over the global bit positions not covered by tb[]
-DTC_HD u64 tile_base_index(u64 tile, int n_local, const int* tb) {
-    u64 used = 0;
-    for (int b = 0; b < DTC_TILE_BITS; ++b) used |= 1ull << tb[b];
+DTC_HD u64 tile_base_index(u64 tile, const DtcTilePass& P) {
     u64 base = 0;
-    int src = 0;
-    for (int pos = 0; pos < n_local; ++pos) {
-        if ((used >> pos) & 1ull) continue;
-        if ((tile >> src) & 1ull) base |= 1ull << pos;
-        ++src;
-    }
+    for (int k = 0; k < P.seg_n; ++k)
+        base |= ((tile >> P.seg_src[k]) & ((1ull << P.seg_len[k]) - 1)) << P.seg_dst[k];
     return base;
 }
 
 // rotations on the five register bits; t[k] already carries the trajectory's sign
 DTC_HD void tile_rot5(double2 a[DTC_NREG], const double t[5]) {
+    // no "skip if t == 0" branches: x0 - i*0*x1 is exact, and straight-line code lets ptxas rename
+    // registers instead of moving every result back to a home register
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        const double tk = t[k];
-        if (tk != 0.0) {
 #pragma unroll
-            for (int i = 0; i < DTC_NREG; ++i) {
-                if (!((i >> k) & 1)) rot_pair(a[i], a[i | (1 << k)], tk);
-            }
+        for (int i = 0; i < DTC_NREG; ++i) {
+            if (!((i >> k) & 1)) rot_pair(a[i], a[i | (1 << k)], t[k]);
         }
     }
 }
@@ -306,13 +298,19 @@ DTC_HD void tile_tables_thread(int tid, TileSmem& sm, const DtcTilePass& P) {
     constexpr int S1 = S2_LO + 5;
     constexpr int T1B = S1 + 1;
     constexpr int T2B = DTC_TILE_BITS - S1;
+    if (P.layerD < 0) {                       // pass without a diagonal layer: identity tables
+        for (int idx = tid; idx < (1 << T1B); idx += DTC_THREADS) sm.T1[idx + 4 * (idx >> S1)] = make_double2(1.0, 0.0);
+        for (int idx = tid; idx < (1 << T2B); idx += DTC_THREADS) sm.T2[idx] = make_double2(1.0, 0.0);
+        if (tid == 0) sm.C = make_double2(1.0, 0.0);
+        return;
+    }
     for (int idx = tid; idx < (1 << T1B); idx += DTC_THREADS) {
         double2 p = sm.E[0][idx & 1];
 #pragma unroll
         for (int l = 1; l < T1B; ++l) p = cmul(p, sm.E[l][(idx >> l) & 1]);
         for (int c = 0; c < P.nT1; ++c)
             p = cmul(p, sm.B[P.T1k[c]][((idx >> P.T1a[c]) ^ (idx >> P.T1b[c])) & 1]);
-        sm.T1[idx ^ (((idx >> S1) & 1) << 2)] = p;
+        sm.T1[idx + 4 * (idx >> S1)] = p;     // +4 chunks when bit S1 is set: conflict-free lookups
     }
     for (int idx = tid; idx < (1 << T2B); idx += DTC_THREADS) {
         double2 p = make_double2(1.0, 0.0);
@@ -339,68 +337,56 @@ DTC_HD void tile_signed_t(const double* tbase, const int* tb, int lo, u64 rmask,
 #define DTC_SCHED_FENCE() ((void)0)
 #endif
 
-// rotations on register bits [0, nb) only
+// rotations on register bits [kbeg, kend)
 DTC_HD void tile_rot_bits(double2 a[DTC_NREG], const double t[5], int kbeg, int kend) {
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         if (k < kbeg || k >= kend) continue;
-        const double tk = t[k];
-        if (tk != 0.0) {
 #pragma unroll
-            for (int i = 0; i < DTC_NREG; ++i) {
-                if (!((i >> k) & 1)) rot_pair(a[i], a[i | (1 << k)], tk);
-            }
+        for (int i = 0; i < DTC_NREG; ++i) {
+            if (!((i >> k) & 1)) rot_pair(a[i], a[i | (1 << k)], t[k]);
         }
     }
 }
 
-// phase 2 body on the register file: R_A|S2, D, R_B|S2.
-// The diagonal multiply is fused into the pair loop of the top register bit (R_A bit 4 -> D -> R_B bit 4
-// per pair) so that only two phase-table entries are live at a time.
+// phase 2 body on the register file: R_A|S2, D, R_B|S2 -- branch-free.  Absent layers have t = 0 /
+// identity tables.  The diagonal multiply is fused into the pair loop of the top register bit
+// (R_A bit 4 -> D -> R_B bit 4 per pair) so that only two phase-table entries are live at a time.
 template <int S2_LO, bool HAS_X>
 DTC_HD void tile_phase2_compute(int tid, double2 a[DTC_NREG], const TileSmem& sm, const DtcTilePass& P,
                                 u64 rmA, u64 rmB) {
     constexpr int S1 = S2_LO + 5;
     constexpr int NH = 7 - S2_LO;
-    double tA[5] = {0, 0, 0, 0, 0}, tB[5] = {0, 0, 0, 0, 0};
-    if (P.layerA >= 0) tile_signed_t(P.t1, P.tb, S2_LO, rmA, tA);
-    if (P.layerB >= 0) tile_signed_t(P.t2, P.tb, S2_LO, rmB, tB);
+    double tA[5], tB[5];
+    tile_signed_t(P.t1, P.tb, S2_LO, rmA, tA);
+    tile_signed_t(P.t2, P.tb, S2_LO, rmB, tB);
     tile_rot_bits(a, tA, 0, 4);
-    if (P.layerD >= 0) {
-        const int idx2 = tid & ((1 << NH) - 1);
-        const double2 cthr = cmul(sm.C, sm.T2[idx2]);
-        const int low = (tid >> NH) | ((tid & 1) << S1);          // passive low bits + bit S1_LO
-        const int sw = (tid & 1) << 2;
-        if (!HAS_X) {
+    const double2 cthr = cmul(sm.C, sm.T2[tid & ((1 << NH) - 1)]);
+    // T1 index = passive low bits | register bits << S2_LO | bit S1 (thread bit 0), padded by 4*(bit S1)
+    const double2* t1 = sm.T1 + ((tid >> NH) | ((tid & 1) << S1)) + 4 * (tid & 1);
+    if (!HAS_X) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (tA[4] != 0.0) rot_pair(a[i], a[i | 16], tA[4]);
-                const double2 p0 = cmul(sm.T1[(low | (i << S2_LO)) ^ sw], cthr);
-                const double2 p1 = cmul(sm.T1[(low | ((i | 16) << S2_LO)) ^ sw], cthr);
-                a[i] = cmul(a[i], p0);
-                a[i | 16] = cmul(a[i | 16], p1);
-                if (tB[4] != 0.0) rot_pair(a[i], a[i | 16], tB[4]);
-                DTC_SCHED_FENCE();
-            }
-        } else {
-            tile_rot_bits(a, tA, 4, 5);
-#pragma unroll
-            for (int r = 0; r < DTC_NREG; ++r) {
-                const double2 ph = cmul(sm.T1[(low | (r << S2_LO)) ^ sw], cthr);
-                a[r] = cmul(a[r], ph);
-            }
-            for (int c = 0; c < P.nX; ++c) {                      // terms outside both tables (rare)
-                const double2 b0 = sm.B[P.Xk[c]][0], b1 = sm.B[P.Xk[c]][1];
-#pragma unroll
-                for (int r = 0; r < DTC_NREG; ++r) {
-                    const int l = tile_local_p2<S2_LO>(tid, r);
-                    a[r] = cmul(a[r], (((l >> P.Xa[c]) ^ (l >> P.Xb[c])) & 1) ? b1 : b0);
-                }
-            }
-            tile_rot_bits(a, tB, 4, 5);
+        for (int i = 0; i < 16; ++i) {
+            rot_pair(a[i], a[i | 16], tA[4]);
+            const double2 p0 = cmul(t1[i << S2_LO], cthr);
+            const double2 p1 = cmul(t1[(i | 16) << S2_LO], cthr);
+            a[i] = cmul(a[i], p0);
+            a[i | 16] = cmul(a[i | 16], p1);
+            rot_pair(a[i], a[i | 16], tB[4]);
+            DTC_SCHED_FENCE();
         }
     } else {
         tile_rot_bits(a, tA, 4, 5);
+#pragma unroll
+        for (int r = 0; r < DTC_NREG; ++r) a[r] = cmul(a[r], cmul(t1[r << S2_LO], cthr));
+        for (int c = 0; c < P.nX; ++c) {                          // terms outside both tables (rare)
+            const double2 b0 = sm.B[P.Xk[c]][0], b1 = sm.B[P.Xk[c]][1];
+#pragma unroll
+            for (int r = 0; r < DTC_NREG; ++r) {
+                const int l = tile_local_p2<S2_LO>(tid, r);
+                a[r] = cmul(a[r], (((l >> P.Xa[c]) ^ (l >> P.Xb[c])) & 1) ? b1 : b0);
+            }
+        }
         tile_rot_bits(a, tB, 4, 5);
     }
     tile_rot_bits(a, tB, 0, 4);
@@ -415,9 +401,12 @@ DTC_HD void tile_phase2_compute(int tid, double2 a[DTC_NREG], const TileSmem& sm
 #define DTC_STG(p, v) (*(p) = (v))
 #endif
 
-template <int S2_LO>
-DTC_HD u64 tile_thread_offset(int tid, u64 base, const int* tb) {
-    return base | tile_deposit_local(tile_local_p13<S2_LO>(tid, 0), tb);
+DTC_HD u64 tile_thread_offset(int tid, u64 base, const DtcTilePass& P) {
+    u64 o = base;
+#pragma unroll
+    for (int b = 0; b < 7; ++b)
+        if ((tid >> b) & 1) o += P.tid_off[b];
+    return o;
 }
 
 // register offsets come from the pass descriptor (constant bank), so no address registers stay live
@@ -433,23 +422,27 @@ DTC_HD void tile_gstore(double2* st, u64 off, const DtcTilePass& P, const double
 
 template <int S2_LO>
 DTC_HD void tile_sm_store13(int tid, TileSmem& sm, const double2 a[DTC_NREG]) {
+    double2* p = sm.tile + tile_pad<S2_LO>(tile_local_p13<S2_LO>(tid, 0));
 #pragma unroll
-    for (int r = 0; r < DTC_NREG; ++r) sm.tile[tile_swz(tile_local_p13<S2_LO>(tid, r))] = a[r];
+    for (int r = 0; r < DTC_NREG; ++r) p[tile_pad<S2_LO>(r << (S2_LO + 5))] = a[r];
 }
 template <int S2_LO>
 DTC_HD void tile_sm_load13(int tid, const TileSmem& sm, double2 a[DTC_NREG]) {
+    const double2* p = sm.tile + tile_pad<S2_LO>(tile_local_p13<S2_LO>(tid, 0));
 #pragma unroll
-    for (int r = 0; r < DTC_NREG; ++r) a[r] = sm.tile[tile_swz(tile_local_p13<S2_LO>(tid, r))];
+    for (int r = 0; r < DTC_NREG; ++r) a[r] = p[tile_pad<S2_LO>(r << (S2_LO + 5))];
 }
 template <int S2_LO>
 DTC_HD void tile_sm_store2(int tid, TileSmem& sm, const double2 a[DTC_NREG]) {
+    double2* p = sm.tile + tile_pad<S2_LO>(tile_local_p2<S2_LO>(tid, 0));
 #pragma unroll
-    for (int r = 0; r < DTC_NREG; ++r) sm.tile[tile_swz(tile_local_p2<S2_LO>(tid, r))] = a[r];
+    for (int r = 0; r < DTC_NREG; ++r) p[r << S2_LO] = a[r];
 }
 template <int S2_LO>
 DTC_HD void tile_sm_load2(int tid, const TileSmem& sm, double2 a[DTC_NREG]) {
+    const double2* p = sm.tile + tile_pad<S2_LO>(tile_local_p2<S2_LO>(tid, 0));
 #pragma unroll
-    for (int r = 0; r < DTC_NREG; ++r) a[r] = sm.tile[tile_swz(tile_local_p2<S2_LO>(tid, r))];
+    for (int r = 0; r < DTC_NREG; ++r) a[r] = p[r << S2_LO];
 }
 
 // rotations of layer tables tbase on the S1 register bits

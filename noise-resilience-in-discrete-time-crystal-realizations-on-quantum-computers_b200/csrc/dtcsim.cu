@@ -67,13 +67,13 @@ k_tile_pass(double2* __restrict__ state, const __grid_constant__ DtcTilePass P,
         // phase 1: coalesced global loads straight into the register file (registers span S1)
         const u64 tile = (u64)blockIdx.x & ((1ull << ntb) - 1);
         const u64 traj = (u64)blockIdx.x >> ntb;
-        const u64 base = tile_base_index(tile, P.n_local, P.tb);
-        tile_gload(state + (traj << P.n_local), tile_thread_offset<S2_LO>(tid, base, P.tb), P, a);
-        // warm L2 with the tile a CTA of the next wave will load (one lane per 64 B run)
+        const u64 base = tile_base_index(tile, P);
+        tile_gload(state + (traj << P.n_local), tile_thread_offset(tid, base, P), P, a);
+        // warm L2 with the tile a later CTA will load (one lane per 64 B run)
         const u64 b2 = (u64)blockIdx.x + (u64)pf_blocks;
         if (pf_blocks > 0 && b2 < gridDim.x && (tid & 3) == 0) {
-            const u64 base2 = tile_base_index(b2 & ((1ull << ntb) - 1), P.n_local, P.tb);
-            tile_prefetch(state + ((b2 >> ntb) << P.n_local), tile_thread_offset<S2_LO>(tid, base2, P.tb), P);
+            const u64 base2 = tile_base_index(b2 & ((1ull << ntb) - 1), P);
+            tile_prefetch(state + ((b2 >> ntb) << P.n_local), tile_thread_offset(tid, base2, P), P);
         }
         const TileMasks M = tile_load_masks(P, masks, n_traj, traj);
         if (tid == 0) {
@@ -86,9 +86,9 @@ k_tile_pass(double2* __restrict__ state, const __grid_constant__ DtcTilePass P,
             tile_setup_thread(tid, sm, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
     }
     __syncthreads();
-    if (P.layerA >= 0) tile_rot_s1<S2_LO>(a, P.t1, P.tb, sm.rmA);
+    tile_rot_s1<S2_LO>(a, P.t1, P.tb, sm.rmA);
     tile_sm_store13<S2_LO>(tid, sm, a);
-    if (P.layerD >= 0) tile_tables_thread<S2_LO>(tid, sm, P);     // after the stores: a[] is dead here
+    tile_tables_thread<S2_LO>(tid, sm, P);          // after the stores: a[] is dead here
     __syncthreads();
 
     // phase 2: registers span S2:  R_A|S2, D, R_B|S2
@@ -99,8 +99,8 @@ k_tile_pass(double2* __restrict__ state, const __grid_constant__ DtcTilePass P,
 
     // phase 3: registers span S1 again, coalesced stores
     tile_sm_load13<S2_LO>(tid, sm, a);
-    if (P.layerB >= 0) tile_rot_s1<S2_LO>(a, P.t2, P.tb, sm.rmB);
-    tile_gstore(state + (((u64)blockIdx.x >> ntb) << P.n_local), tile_thread_offset<S2_LO>(tid, sm.base, P.tb), P, a);
+    tile_rot_s1<S2_LO>(a, P.t2, P.tb, sm.rmB);
+    tile_gstore(state + (((u64)blockIdx.x >> ntb) << P.n_local), tile_thread_offset(tid, sm.base, P), P, a);
 }
 
 // ---- generic engine

@@ -19,13 +19,13 @@ static void emu_tile_pass(double2* state, const DtcTilePass& P, const DtcLayer* 
     const u64 tile = block & ((1ull << ntb) - 1);
     const u64 traj = block >> ntb;
     double2* st = state + (traj << P.n_local);
-    const u64 base = tile_base_index(tile, P.n_local, P.tb);
+    const u64 base = tile_base_index(tile, P);
     const TileMasks M = tile_load_masks(P, masks, n_traj, traj);
     u64 off[DTC_THREADS];
     // --- up to the first barrier
     for (int tid = 0; tid < DTC_THREADS; ++tid) {
         double2* a = &regs[(size_t)tid * DTC_NREG];
-        off[tid] = tile_thread_offset<S2_LO>(tid, base, P.tb);
+        off[tid] = tile_thread_offset(tid, base, P);
         tile_gload(st, off[tid], P, a);
         if (P.layerD >= 0)
             tile_setup_thread(tid, sm, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
@@ -33,9 +33,9 @@ static void emu_tile_pass(double2* state, const DtcTilePass& P, const DtcLayer* 
     // --- second segment
     for (int tid = 0; tid < DTC_THREADS; ++tid) {
         double2* a = &regs[(size_t)tid * DTC_NREG];
-        if (P.layerA >= 0) tile_rot_s1<S2_LO>(a, P.t1, P.tb, M.rmA);
+        tile_rot_s1<S2_LO>(a, P.t1, P.tb, M.rmA);
         tile_sm_store13<S2_LO>(tid, sm, a);
-        if (P.layerD >= 0) tile_tables_thread<S2_LO>(tid, sm, P);
+        tile_tables_thread<S2_LO>(tid, sm, P);
     }
     // --- phase 2
     for (int tid = 0; tid < DTC_THREADS; ++tid) {
@@ -50,7 +50,7 @@ static void emu_tile_pass(double2* state, const DtcTilePass& P, const DtcLayer* 
     for (int tid = 0; tid < DTC_THREADS; ++tid) {
         double2 a[DTC_NREG];
         tile_sm_load13<S2_LO>(tid, sm, a);
-        if (P.layerB >= 0) tile_rot_s1<S2_LO>(a, P.t2, P.tb, M.rmB);
+        tile_rot_s1<S2_LO>(a, P.t2, P.tb, M.rmB);
         tile_gstore(st, off[tid], P, a);
     }
 }
