@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdtcsim.so")
+LIB_PATH = os.environ.get("DTCSIM_LIB") or os.path.join(_HERE, "csrc", "libdtcsim.so")   # env override: tuning builds
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_i64 = ctypes.c_int64

@@ -345,6 +345,7 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
             for (int b = 0; b < 7; ++b) T.tid_off[b] = 1ull << T.tb[b < S1 ? b : b + 5];
             u64 used = 0;
             for (int l = 0; l < DTC_TILE_BITS; ++l) used |= 1ull << T.tb[l];
+            T.tile_mask = used;
             T.seg_n = 0;
             int src = 0, pos = 0;
             while (pos < n) {

@@ -70,6 +70,7 @@ struct DtcTilePass {
     double t2[DTC_TILE_BITS];      // tan for R_B
     u64 roff[DTC_NREG];            // global offset of register r in phases 1/3 (sum of S1 strides)
     u64 tid_off[7];                // global offset contributed by thread-id bit b in phases 1/3
+    u64 tile_mask;                 // global bit positions covered by the tile
     int seg_n;                     // tile counter -> global base: sum over segments of
     int seg_src[8], seg_len[8], seg_dst[8];   //   ((tile >> src) & ((1 << len) - 1)) << dst
     // classification of D_layerD's two-body terms relative to this tile
@@ -204,6 +205,7 @@ struct TileSmem {
     double2 E[DTC_TILE_BITS][2];
     double2 B[DTC_MAXT][2];
     double2 C;
+    double2 Cpart[32];  // per-lane partial products of the tile constant
     u64 base;          // global index of tile-local index 0 (kept here, not in registers, across phases)
     u64 rmA, rmB;      // rotation sign masks of the trajectory
 };
@@ -248,8 +250,20 @@ DTC_HD void tile_rot5(double2 a[DTC_NREG], const double t[5]) {
     }
 }
 
+#if defined(__CUDA_ARCH__)
+#define DTC_SYNCWARP() __syncwarp()
+#define DTC_CTZ64(x) (__ffsll((long long)(x)) - 1)
+#define DTC_POPC64(x) __popcll(x)
+#else
+#define DTC_SYNCWARP() ((void)0)
+#define DTC_CTZ64(x) __builtin_ctzll(x)
+#define DTC_POPC64(x) __builtin_popcountll(x)
+#endif
+
 // per-CTA setup of the diagonal layer: E (local one-body incl. cross terms), B (local two-body), C.
-// Executed by threads 0..23 (E), 32..95 (B), 127 (C).  g_outer: global index with all tile-local bits 0.
+// Warp 0 lanes 0..23: E; warps 1,2: B; warp 3: tile constant C, one factor per lane (outer one-body
+// factors and outer-outer bonds), multiplied together by the warp's last lane.
+// g_outer: global index with all tile-local bits 0.
 DTC_HD void tile_setup_thread(int tid, TileSmem& sm, const DtcTilePass& P, const DtcLayer& L, u64 g_outer,
                               u64 m1a, u64 m1b, u64 m2) {
     if (tid < 2 * DTC_TILE_BITS) {
@@ -269,25 +283,31 @@ DTC_HD void tile_setup_thread(int tid, TileSmem& sm, const DtcTilePass& P, const
             sm.B[k][0] = d2_factor(L, k, 0, m2);
             sm.B[k][1] = d2_factor(L, k, 1, m2);
         }
-    } else if (tid == DTC_THREADS - 1) {
-        double2 c = make_double2(L.cr, L.ci);
-        u64 used = 0;
-        for (int b = 0; b < DTC_TILE_BITS; ++b) used |= 1ull << P.tb[b];
-        u64 any = (L.d1_any[0] | L.d1_any[1]) & ~used;
-        while (any) {
-#if defined(__CUDA_ARCH__)
-            const int q = __ffsll((long long)any) - 1;
-#else
-            const int q = __builtin_ctzll(any);
-#endif
-            any &= any - 1;
-            c = cmul(c, d1_factor(L, q, (int)((g_outer >> q) & 1ull), m1a, m1b));
+    } else if (tid >= 96) {
+        const int lane = tid - 96;
+        const u64 any = (L.d1_any[0] | L.d1_any[1]) & ~P.tile_mask;
+        const int cnt = DTC_POPC64(any);
+        double2 f = make_double2(1.0, 0.0);
+        for (int it = lane; it < cnt + P.nO; it += 32) {
+            if (it < cnt) {
+                u64 m = any;
+                for (int k = 0; k < it; ++k) m &= m - 1;
+                const int q = DTC_CTZ64(m);
+                f = cmul(f, d1_factor(L, q, (int)((g_outer >> q) & 1ull), m1a, m1b));
+            } else {
+                const int o = it - cnt;
+                const int par = (int)(((g_outer >> P.Oa[o]) ^ (g_outer >> P.Ob[o])) & 1ull);
+                f = cmul(f, d2_factor(L, P.Ok[o], par, m2));
+            }
         }
-        for (int o = 0; o < P.nO; ++o) {
-            const int par = (int)(((g_outer >> P.Oa[o]) ^ (g_outer >> P.Ob[o])) & 1ull);
-            c = cmul(c, d2_factor(L, P.Ok[o], par, m2));
+        sm.Cpart[lane] = f;
+        DTC_SYNCWARP();
+        if (lane == 31) {
+            double2 c = make_double2(L.cr, L.ci);
+            const int used = (cnt + P.nO < 32) ? cnt + P.nO : 32;
+            for (int k = 0; k < used; ++k) c = cmul(c, sm.Cpart[k]);
+            sm.C = c;
         }
-        sm.C = c;
     }
 }
 
@@ -331,6 +351,9 @@ DTC_HD void tile_signed_t(const double* tbase, const int* tb, int lo, u64 rmask,
     }
 }
 
+#ifndef DTC_FENCE_EVERY
+#define DTC_FENCE_EVERY 1      // pairs between scheduling fences in the fused diagonal loop (0: none)
+#endif
 #if defined(__CUDA_ARCH__)
 #define DTC_SCHED_FENCE() asm volatile("" ::: "memory")
 #else
@@ -373,7 +396,7 @@ DTC_HD void tile_phase2_compute(int tid, double2 a[DTC_NREG], const TileSmem& sm
             a[i] = cmul(a[i], p0);
             a[i | 16] = cmul(a[i | 16], p1);
             rot_pair(a[i], a[i | 16], tB[4]);
-            DTC_SCHED_FENCE();
+            if (DTC_FENCE_EVERY > 0 && (i % (DTC_FENCE_EVERY > 0 ? DTC_FENCE_EVERY : 1)) == DTC_FENCE_EVERY - 1) DTC_SCHED_FENCE();
         }
     } else {
         tile_rot_bits(a, tA, 4, 5);

@@ -63,6 +63,7 @@ k_tile_pass(double2* __restrict__ state, const __grid_constant__ DtcTilePass P,
     const int tid = threadIdx.x;
     const int ntb = P.n_local - DTC_TILE_BITS;
     double2 a[DTC_NREG];
+    u64 rmA0;
     {
         // phase 1: coalesced global loads straight into the register file (registers span S1)
         const u64 tile = (u64)blockIdx.x & ((1ull << ntb) - 1);
@@ -81,12 +82,13 @@ k_tile_pass(double2* __restrict__ state, const __grid_constant__ DtcTilePass P,
             sm.rmA = M.rmA;
             sm.rmB = M.rmB;
         }
+        rmA0 = M.rmA;
         // diagonal-layer setup overlaps the loads in flight
         if (P.layerD >= 0)
             tile_setup_thread(tid, sm, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
     }
+    tile_rot_s1<S2_LO>(a, P.t1, P.tb, rmA0);    // needs only the loads, not the setup
     __syncthreads();
-    tile_rot_s1<S2_LO>(a, P.t1, P.tb, sm.rmA);
     tile_sm_store13<S2_LO>(tid, sm, a);
     tile_tables_thread<S2_LO>(tid, sm, P);          // after the stores: a[] is dead here
     __syncthreads();
