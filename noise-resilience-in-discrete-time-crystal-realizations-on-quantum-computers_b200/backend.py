@@ -423,6 +423,36 @@ class DTCSimulator:
         data["time_taken"] = time.time() - t0
         return ExperimentResult(name or circ.name, counts, data, shots, seed)
 
+    def sample_trajectories(self, circuit, traj_begin, traj_end, seed, noise_model=None):
+        """Classical-register values (numpy int64) of noise trajectories traj_begin..traj_end-1 of `circuit`
+        (one shot each).  The Philox counters are global trajectory ids, so disjoint ranges computed on
+        different GPUs concatenate to exactly what one GPU produces (used by dist.ShardedSampler)."""
+        torch = self.ctx.torch
+        ctx = self.ctx
+        nm = as_noise_model(self.noise_model if noise_model is None else noise_model)
+        prog = compile_circuit(as_circuit(circuit), nm, optimize=self.optimize)
+        meas = prog.measures
+        k = len(meas)
+        if k == 0 or k > MAX_PROB_QUBITS:
+            raise ValueError("sample_trajectories needs 1..12 measured qubits")
+        cbits = np.array([c for _, c in meas], dtype=np.int64)
+        handle = capi.ProgramHandle(prog, ctx.index, self.engine)
+        per = 16 << prog.n_main
+        n = traj_end - traj_begin
+        bt = max(1, min(n, (self.max_memory_bytes or int(0.7 * ctx.free_bytes())) // per))
+        state = ctx.empty(bt << prog.n_main, torch.complex128)
+        vals = np.zeros(n, dtype=np.int64)
+        for a in range(0, n, bt):
+            nt = min(bt, n - a)
+            batch = evolve(ctx, prog, nt, traj_begin + a, seed, handle=handle, state=state)
+            cols = sample_rows(ctx, batch.outcome_probs(), 1, seed, traj_begin + a).cpu().numpy()[:, 0].astype(np.int64)
+            v = np.zeros(nt, dtype=np.int64)
+            for i in range(k):
+                v |= ((cols >> i) & 1) << cbits[i]
+            vals[a:a + nt] = v
+        handle.close()
+        return vals
+
     @staticmethod
     def _clbit_probs(p_cols, to_clbits, n_clbits):
         vals = to_clbits(np.arange(len(p_cols)))

@@ -346,3 +346,18 @@ def test_factorised_run_equals_full_run(disorder):
         assert abs(r1.expectation_z()[0] - r2.expectation_z()[0]) < 1e-12
         want, _ = O.run_counts(RC.ops_of(circ), 31, 1, shots=300, noise=O.PauliNoise.depolarizing(0.05), seed=42)
         assert r1.get_counts() == want
+
+
+def test_trajectory_ranges_concatenate(disorder):
+    """Multi-GPU contract (dist.ShardedSampler): disjoint trajectory ranges reproduce the single-GPU run."""
+    hs, phis = disorder[20][0][0][:12], disorder[20][1][0][:11]
+    sim = dtcsim.AerSimulator(noise_model=RC.noise_model(0.05))
+    circ = RC.transpiled(RC.qc_body("vacuum", 12, 0.97, hs, phis, 3, 6, True))
+    whole = sim.sample_trajectories(circ, 0, 200, 9)
+    parts = np.concatenate([sim.sample_trajectories(circ, 0, 77, 9), sim.sample_trajectories(circ, 77, 200, 9)])
+    assert np.array_equal(whole, parts)
+    counts = sim.run(circ, shots=200, seed_simulator=9).result().get_counts()
+    assert counts == {k: v for k, v in (("0", int((whole == 0).sum())), ("1", int((whole == 1).sum()))) if v}
+    from dtcsim import dist as D
+    sampler = D.ShardedSampler(sim, 0, 1)
+    assert sampler.run_counts(circ, shots=200, seed_simulator=9) == counts
