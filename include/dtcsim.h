@@ -43,6 +43,10 @@ typedef enum {
 
 enum { DTC_EV_ROT = 0, DTC_EV_D1 = 1, DTC_EV_D2 = 2, DTC_EV_NOISE = 3, DTC_EV_D2C = 4 };
 enum { DTC_ENGINE_AUTO = 0, DTC_ENGINE_GENERIC = 1, DTC_ENGINE_TILE = 2 };
+/* special init_index values of dtc_program_run: continue from the buffer's contents / start from the zero vector
+ * (shards of a distributed state that do not hold the basis amplitude) */
+#define DTC_INIT_KEEP 0xFFFFFFFFFFFFFFFFull
+#define DTC_INIT_ZERO 0xFFFFFFFFFFFFFFFEull
 
 typedef struct dtc_program dtc_program;   /* opaque compiled circuit */
 

@@ -53,6 +53,7 @@ _SIGS = {
 EXPORTED = tuple(_SIGS)
 
 ENGINE_AUTO, ENGINE_GENERIC, ENGINE_TILE = 0, 1, 2
+INIT_KEEP, INIT_ZERO = 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFE
 _lib = None
 
 
@@ -97,7 +98,7 @@ class ProgramHandle:
     def __init__(self, prog, device, engine=ENGINE_AUTO, n_local=None):
         lib = load()
         self.prog = prog
-        self.n_local = prog.n_main if n_local is None else n_local
+        self.n_local = getattr(prog, "n_main", prog.n) if n_local is None else n_local
         self.device = device
         self._h = c_vp()
         check(lib.dtc_program_create(prog.n, prog.n_layers, ctypes.byref(self._h)))

@@ -589,7 +589,8 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     if (!state || !workspace || n_traj < 1) return fail(DTC_ERR_INVALID, "bad argument");
     const DtcProgramHost& h = p->h;
     if (workspace_bytes < dtc_workspace_bytes(h, n_traj)) return fail(DTC_ERR_INVALID, "workspace too small");
-    if (init_index >> h.n_local) return fail(DTC_ERR_INVALID, "init_index out of range");
+    const bool keep = init_index == DTC_INIT_KEEP, zero = init_index == DTC_INIT_ZERO;
+    if (!keep && !zero && (init_index >> h.n_local)) return fail(DTC_ERR_INVALID, "init_index out of range");
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(h.device));
     u64 *masks, *fx, *fz;
@@ -599,9 +600,12 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     const int fb = 128;
     k_frames<<<(unsigned)((n_traj + fb - 1) / fb), fb, 0, s>>>(p->d_events, (long long)h.events.size(), masks,
                                                               n_traj, traj_offset, seed, fx, fz, ph);
-    const size_t sbytes = ((size_t)n_traj << h.n_local) * sizeof(double2);
-    CUDA_TRY(cudaMemsetAsync(state, 0, sbytes, s));
-    k_init_basis<<<(unsigned)((n_traj + 127) / 128), 128, 0, s>>>((double2*)state, h.n_local, n_traj, init_index);
+    if (!keep) {
+        const size_t sbytes = ((size_t)n_traj << h.n_local) * sizeof(double2);
+        CUDA_TRY(cudaMemsetAsync(state, 0, sbytes, s));
+        if (!zero)
+            k_init_basis<<<(unsigned)((n_traj + 127) / 128), 128, 0, s>>>((double2*)state, h.n_local, n_traj, init_index);
+    }
     if (p->profiling) CUDA_TRY(cudaEventRecord(p->ev0, s));
     p->last_launches = (h.engine == DTC_ENGINE_TILE) ? (int)h.passes.size() : (int)h.gsteps.size();
     if (h.engine == DTC_ENGINE_TILE) {

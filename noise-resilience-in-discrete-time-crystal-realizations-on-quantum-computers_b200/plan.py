@@ -431,17 +431,11 @@ def _segment_dm(prims):
     return out
 
 
-def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True, optimize=False):
-    """Compile a (transpiled) circuit + noise model into a :class:`Program`.
+def lower_to_prims(circuit, noise_model=None):
+    """Stage 1 of the compiler: gates -> primitive list on compacted qubits.
 
-    optimize=True enables the read-out factorisation (see _analyse_readout): qubits that only couple to
-    the rest through a small measured suffix are kept out of the big register (prog.n_main < prog.n)
-    and the suffix runs on a tiny density matrix per trajectory (prog.small).  Counts and expectation
-    values are unchanged; the full statevector is then not available, so amplitude-level consumers
-    compile with optimize=False.
-
-    Raises ValueError for anything the device path cannot execute exactly (unsupported gate,
-    noise on a multi-qubit gate, mid-circuit measurement) -- there is no CPU fallback.
+    Returns (prims, global_phase, measured {clbit: compacted qubit}, used (original qubit of each compacted
+    one), n_clbits).  prims entries: ("R", (q,), theta) | ("D", (q,), a) | ("D", (i, j), b) | ("N", (q,), (px,py,pz)).
     """
     circ = as_circuit(circuit)
     for op in circ.ops:
@@ -463,7 +457,6 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True, opti
             return None
         return noise_model.lookup(op.name, op.qubits[0])
 
-    # ---- stage 1: gates -> primitives on compacted qubit indices
     b = _Prims()
     b.global_phase = float(circ.global_phase)
     ops = [o for o in circ.ops if o.name != "barrier"]
@@ -517,7 +510,23 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True, opti
         pr = probs_of(op)
         if pr is not None:
             b.noise(qs[0], pr)
-    prims = b.prims
+    return b.prims, b.global_phase, measured, used, circ.num_clbits
+
+
+def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True, optimize=False):
+    """Compile a (transpiled) circuit + noise model into a :class:`Program`.
+
+    optimize=True enables the read-out factorisation (see _analyse_readout): qubits that only couple to
+    the rest through a small measured suffix are kept out of the big register (prog.n_main < prog.n)
+    and the suffix runs on a tiny density matrix per trajectory (prog.small).  Counts and expectation
+    values are unchanged; the full statevector is then not available, so amplitude-level consumers
+    compile with optimize=False.
+
+    Raises ValueError for anything the device path cannot execute exactly (unsupported gate,
+    noise on a multi-qubit gate, mid-circuit measurement) -- there is no CPU fallback.
+    """
+    prims, global_phase, measured, used, n_clbits = lower_to_prims(circuit, noise_model)
+    n = len(used)
 
     # ---- stage 2: read-out analysis and internal bit order (eliminated qubits become the top bits)
     plan = _analyse_readout(prims, n, sorted(set(measured.values()))) if optimize else None
@@ -535,8 +544,8 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True, opti
     prog.active = used
     prog.order = order
     prog.bit_of = bit_of
-    prog.n_clbits = circ.num_clbits
-    prog.global_phase = b.global_phase
+    prog.n_clbits = n_clbits
+    prog.global_phase = global_phase
 
     # ---- stage 3: primitives -> layered events (main register, then the small read-out domain)
     main = _Layerer(prog, n)
