@@ -205,7 +205,6 @@ struct TileSmem {
     double2 E[DTC_TILE_BITS][2];
     double2 B[DTC_MAXT][2];
     double2 C;
-    double2 Cpart[32];  // per-lane partial products of the tile constant
     u64 base;          // global index of tile-local index 0 (kept here, not in registers, across phases)
     u64 rmA, rmB;      // rotation sign masks of the trajectory
 };
@@ -300,12 +299,12 @@ DTC_HD void tile_setup_thread(int tid, TileSmem& sm, const DtcTilePass& P, const
                 f = cmul(f, d2_factor(L, P.Ok[o], par, m2));
             }
         }
-        sm.Cpart[lane] = f;
+        sm.T2[lane] = f;                    // scratch: T2 is rebuilt after the next barrier
         DTC_SYNCWARP();
         if (lane == 31) {
             double2 c = make_double2(L.cr, L.ci);
             const int used = (cnt + P.nO < 32) ? cnt + P.nO : 32;
-            for (int k = 0; k < used; ++k) c = cmul(c, sm.Cpart[k]);
+            for (int k = 0; k < used; ++k) c = cmul(c, sm.T2[k]);
             sm.C = c;
         }
     }
@@ -475,6 +474,9 @@ DTC_HD void tile_rot_s1(double2 a[DTC_NREG], const double* tbase, const int* tb,
     tile_signed_t(tbase, tb, S2_LO + 5, rmask, t);
     tile_rot5(a, t);
 }
+
+// 228 KB of shared memory per SM, 1 KB reserved per CTA: three resident CTAs need <= 75 KB each
+static_assert(3 * (sizeof(TileSmem) + 1024) <= 228 * 1024, "three CTAs per SM must fit in shared memory");
 
 struct TileMasks {
     u64 rmA, rmB, m1a, m1b, m2;
