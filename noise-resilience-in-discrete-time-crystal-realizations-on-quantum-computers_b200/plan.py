@@ -164,51 +164,50 @@ def choose_bit_order(n, pairs):
 
 
 def _fuse_cx_rz_cx(ops, noisy):
-    """Peephole: cx(a,b) [diag 1q on b] cx(a,b) -> rzz-equivalent.  `noisy(op)` must be False for all three.
+    """Peephole: cx(a,b) [diag 1q on b] cx(a,b) -> rzz-equivalent; `noisy[i]` must be falsy for all three.
 
-    Only ops touching a or b are considered neighbours; diagonal 1q gates on the control a in
-    between commute with everything involved and are left in place.
+    Only ops touching a or b are neighbours; diagonal 1q gates on the control a in between commute with
+    everything involved and stay in place.  Linear time: per-qubit lists of op indices.
     """
-    out = []
-    i = 0
     n = len(ops)
-    consumed = set()
-    while i < n:
-        if i in consumed:
-            i += 1
+    per_q = {}
+    where = [None] * n                     # where[i] = {qubit: position of op i in per_q[qubit]}
+    for i, op in enumerate(ops):
+        w = {}
+        for q in op.qubits:
+            lst = per_q.setdefault(q, [])
+            w[q] = len(lst)
+            lst.append(i)
+        where[i] = w
+    consumed = [False] * n
+    out = []
+    for i, op in enumerate(ops):
+        if consumed[i]:
             continue
-        op = ops[i]
-        if op.name == "cx" and not noisy(op):
+        if op.name == "cx" and not noisy[i]:
             a, b = op.qubits
-            mid = None
-            close = None
-            for j in range(i + 1, n):
-                if j in consumed:
+            lb, la = per_q[b], per_q[a]
+            kb = where[i][b]
+            ok = kb + 2 <= len(lb) - 1
+            if ok:
+                m, c = lb[kb + 1], lb[kb + 2]
+                om, oc = ops[m], ops[c]
+                ok = (om.name in _DIAG_OF and om.qubits == (b,) and not noisy[m] and not consumed[m]
+                      and oc.name == "cx" and oc.qubits == (a, b) and not noisy[c] and not consumed[c])
+                if ok:
+                    # everything on the control between the two cx must be a noiseless diagonal 1q gate
+                    ka, kc = where[i][a], where[c][a]
+                    for k in range(ka + 1, kc):
+                        o2 = ops[la[k]]
+                        if not (o2.name in _DIAG_OF and o2.qubits == (a,) and not noisy[la[k]]):
+                            ok = False
+                            break
+                if ok:
+                    ang, ph = _DIAG_OF[om.name](om.params)
+                    out.append(("rzz_fused", (a, b), ang, ph))
+                    consumed[m] = consumed[c] = True
                     continue
-                o2 = ops[j]
-                if not (set(o2.qubits) & {a, b}):
-                    continue
-                if mid is None:
-                    if o2.name in _DIAG_OF and o2.qubits == (b,) and not noisy(o2):
-                        mid = j
-                        continue
-                    if o2.name in _DIAG_OF and o2.qubits == (a,) and not noisy(o2):
-                        continue            # commutes with the control of the cx pair
-                    break
-                if o2.name in _DIAG_OF and o2.qubits == (a,) and not noisy(o2):
-                    continue
-                if o2.name == "cx" and o2.qubits == (a, b) and not noisy(o2):
-                    close = j
-                break
-            if mid is not None and close is not None:
-                ang, ph = _DIAG_OF[ops[mid].name](ops[mid].params)
-                out.append(("rzz_fused", (a, b), ang, ph))
-                consumed.add(mid)
-                consumed.add(close)
-                i += 1
-                continue
         out.append(op)
-        i += 1
     return out
 
 
@@ -460,7 +459,9 @@ def lower_to_prims(circuit, noise_model=None):
     b = _Prims()
     b.global_phase = float(circ.global_phase)
     ops = [o for o in circ.ops if o.name != "barrier"]
-    ops = _fuse_cx_rz_cx(ops, lambda o: probs_of(o) is not None)
+    op_probs = [probs_of(o) for o in ops]
+    probs_by_id = {id(o): pr for o, pr in zip(ops, op_probs)}
+    ops = _fuse_cx_rz_cx(ops, [pr is not None for pr in op_probs])
     measured = {}
     finished = set()
     for op in ops:
@@ -507,7 +508,7 @@ def lower_to_prims(circuit, noise_model=None):
             b.cx(qs[0], qs[1])
             b.cx(qs[1], qs[0])
             b.cx(qs[0], qs[1])
-        pr = probs_of(op)
+        pr = probs_by_id[id(op)]
         if pr is not None:
             b.noise(qs[0], pr)
     return b.prims, b.global_phase, measured, used, circ.num_clbits
