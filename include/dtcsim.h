@@ -90,6 +90,13 @@ int dtc_program_run(dtc_program *p, void *state, int64_t n_traj, int64_t traj_of
 int dtc_program_frames(const dtc_program *p, void *workspace, int64_t n_traj,
                        uint64_t **fx, uint64_t **fz, int32_t **ph);
 
+/* Engine selection inside the tile engine.  A fused pass whose tile is [0,12) or {0,1}+[g,g+10) runs on the
+ * TMA-fed persistent kernel k_tile_stream; other passes (and all passes after dtc_set_stream_engine(0)) run on
+ * the register-fed k_tile_pass.  enable < 0 restores the default (environment DTCSIM_STREAM, else on).
+ * dtc_program_num_stream_passes(): how many passes of the schedule are eligible for k_tile_stream. */
+int dtc_set_stream_engine(int enable);
+int dtc_program_num_stream_passes(const dtc_program *p, int *n_passes);
+
 /* Kernel timing for roofline accounting: when enabled, dtc_program_run() brackets its pass loop with
  * CUDA events on the launching stream; dtc_program_pass_time() waits for the last run and returns the
  * elapsed milliseconds and the number of state-sweep launches in that run. */

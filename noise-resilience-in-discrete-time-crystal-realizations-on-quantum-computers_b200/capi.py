@@ -32,6 +32,8 @@ _SIGS = {
     "dtc_program_run": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_u64, c_u64, c_u64, c_vp, ctypes.c_size_t, c_vp]),
     "dtc_program_frames": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
                                           ctypes.POINTER(c_vp)]),
+    "dtc_set_stream_engine": (ctypes.c_int, [ctypes.c_int]),
+    "dtc_program_num_stream_passes": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "dtc_program_pass_time": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "dtc_materialize": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -72,6 +74,11 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def set_stream_engine(enable):
+    """True/False: force k_tile_stream on/off for eligible passes; None: library default (on)."""
+    check(load().dtc_set_stream_engine(-1 if enable is None else int(bool(enable))))
 
 
 def check(rc):
@@ -118,6 +125,13 @@ class ProgramHandle:
     def num_passes(self):
         n = ctypes.c_int(0)
         check(load().dtc_program_num_passes(self._h, ctypes.byref(n)))
+        return n.value
+
+    @property
+    def num_stream_passes(self):
+        """Passes of the schedule that run on the TMA-fed k_tile_stream (the rest use k_tile_pass)."""
+        n = ctypes.c_int(0)
+        check(load().dtc_program_num_stream_passes(self._h, ctypes.byref(n)))
         return n.value
 
     def workspace_bytes(self, n_traj):

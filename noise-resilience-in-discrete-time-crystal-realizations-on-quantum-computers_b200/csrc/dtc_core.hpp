@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "dtc_hd.cuh"
+#include "dtc_stream.cuh"
 
 struct DtcGenericStep {
     int kind;      // 0: rotation on qubit q of `layer`, 1: diagonal of `layer`
@@ -26,6 +27,7 @@ struct DtcProgramHost {
     std::vector<DtcEvent> events;
     std::vector<DtcLayer> layers;
     std::vector<DtcTilePass> passes;
+    std::vector<DtcStreamPass> spasses;      // parallel to passes; mode == 0: not eligible for the streaming engine
     std::vector<DtcGenericStep> gsteps;
 };
 
@@ -146,6 +148,28 @@ static inline bool dtc_build_tile(u64 S, int n_local, int tb[DTC_TILE_BITS], int
     int top = -1;
     for (int b = 0; b < n_local; ++b)
         if ((S >> b) & 1ull) top = b;
+    // preferred shapes (eligible for the TMA-fed streaming engine): [0,12) with the active set below bit 10,
+    // or {0,1} + ten consecutive bits containing the active set
+    if (n_local >= DTC_TILE_BITS && top >= 0) {
+        int g = -1;
+        if (!(S >> 10)) g = 0;
+        else if (!(S & 3ull)) {
+            g = top + 1 - 10;
+            if (g < 2) g = 2;
+            if (g + 10 > n_local || (S & ((1ull << g) - 1))) g = -1;
+        }
+        if (g == 0 || g == 2) {
+            for (int l = 0; l < DTC_TILE_BITS; ++l) tb[l] = l;
+            *s2_lo = g;
+            return true;
+        }
+        if (g > 2) {
+            tb[0] = 0; tb[1] = 1;
+            for (int l = 2; l < DTC_TILE_BITS; ++l) tb[l] = g + l - 2;
+            *s2_lo = 2;
+            return true;
+        }
+    }
     for (int klow = need; klow >= 0; --klow) {
         u64 tile = must;
         int added = 0;
@@ -208,6 +232,57 @@ static inline void dtc_classify_terms(DtcTilePass& T, const DtcLayer& L) {
             T.Ok[T.nO] = k; T.Oa[T.nO] = L.ti[k]; T.Ob[T.nO] = L.tj[k]; ++T.nO;
         }
     }
+}
+
+// ---- streaming engine eligibility ---------------------------------------------------------------
+// A pass runs on k_tile_stream when its tile is [0,12) or {0,1} + [g,g+10), its active bits avoid the
+// two passive positions of that layout, and every local two-body term fits one of the two tables.
+static inline bool dtc_make_stream_pass(const DtcTilePass& T, const DtcLayer* LD, DtcStreamPass& S) {
+    memset(&S, 0, sizeof(S));
+    bool contig = true, modeB_shape = T.tb[0] == 0 && T.tb[1] == 1;
+    for (int l = 0; l < DTC_TILE_BITS; ++l) contig = contig && T.tb[l] == l;
+    for (int l = 3; l < DTC_TILE_BITS; ++l) modeB_shape = modeB_shape && T.tb[l] == T.tb[2] + (l - 2);
+    unsigned active = 0;
+    for (int l = 0; l < DTC_TILE_BITS; ++l)
+        if (T.t1[l] != 0.0 || T.t2[l] != 0.0) active |= 1u << l;
+    int mode = 0;
+    if (contig && !(active & 0xC00u)) mode = 1;
+    else if ((contig || modeB_shape) && !(active & 0x3u)) mode = 2;
+    if (!mode) return false;
+    S.mode = mode;
+    S.contig = contig ? 1 : 0;
+    S.n_local = T.n_local;
+    S.g = T.tb[2];
+    if (!contig && S.g + 10 > T.n_local) return false;
+    S.layerA = T.layerA; S.layerD = T.layerD; S.layerB = T.layerB;
+    memcpy(S.tb, T.tb, sizeof(S.tb));
+    memcpy(S.t1, T.t1, sizeof(S.t1));
+    memcpy(S.t2, T.t2, sizeof(S.t2));
+    S.tile_mask = T.tile_mask;
+    if (T.layerD < 0 || !LD) return true;
+    const DtcLayer& L = *LD;
+    int loc[DTC_MAXQ];
+    for (int q = 0; q < DTC_MAXQ; ++q) loc[q] = -1;
+    for (int l = 0; l < DTC_TILE_BITS; ++l) loc[T.tb[l]] = l;
+    const unsigned W2 = 0xF07u;                              // local bits 0,1,2,8,9,10,11
+    for (int k = 0; k < L.n_terms; ++k) {
+        if (L.ts[k] == 0.0 && L.tc[k] == 1.0) continue;      // unused slot
+        int a = loc[L.ti[k]], b = loc[L.tj[k]];
+        if (a >= 0 && b >= 0) {
+            if (a > b) { int t = a; a = b; b = t; }
+            if (a >= 2 && b <= 8) { S.T1k[S.nT1] = k; S.T1a[S.nT1] = a; S.T1b[S.nT1] = b; ++S.nT1; }
+            else if (((W2 >> a) & 1u) && ((W2 >> b) & 1u)) { S.T2k[S.nT2] = k; S.T2a[S.nT2] = a; S.T2b[S.nT2] = b; ++S.nT2; }
+            else return false;
+        } else if (a >= 0 || b >= 0) {
+            S.Ck[S.nC] = k;
+            S.Ca[S.nC] = (a >= 0) ? a : b;
+            S.Cb[S.nC] = (a >= 0) ? L.tj[k] : L.ti[k];
+            ++S.nC;
+        } else {
+            S.Ok[S.nO] = k; S.Oa[S.nO] = L.ti[k]; S.Ob[S.nO] = L.tj[k]; ++S.nO;
+        }
+    }
+    return true;
 }
 
 // ---- pass schedule -----------------------------------------------------------------------------
@@ -279,6 +354,7 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
     const int M = P.n_exec_layers, n = P.n_local;
     const u64 local_mask = (n >= 64) ? ~0ull : ((1ull << n) - 1);
     P.passes.clear();
+    P.spasses.clear();
     for (int j = 0; j < M; ++j)
         if (P.layers[j].rot_any & ~local_mask) {
             err = "rotation on a non-local (global) qubit: exchange qubits before this layer";
@@ -358,6 +434,11 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
             }
         }
         P.passes.push_back(T);
+        {
+            DtcStreamPass S;
+            if (!dtc_make_stream_pass(T, T.layerD >= 0 ? &L : nullptr, S)) S.mode = 0;
+            P.spasses.push_back(S);
+        }
         if (complete) {
             ++j;
             done = SB;

@@ -8,6 +8,7 @@
 //   k_probs / k_expect_z warp-shuffle reductions for read-out.
 //   k_generic_*          one-thread-per-element fallbacks (n < 12, cross-checks).
 //   k_dm_*               exact density-matrix primitives (small n).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
@@ -19,6 +20,7 @@
 
 // ------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
+static int g_num_sms[16] = {0};
 static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -103,6 +105,134 @@ k_tile_pass(double2* __restrict__ state, const __grid_constant__ DtcTilePass P,
     tile_sm_load13<S2_LO>(tid, sm, a);
     tile_rot_s1<S2_LO>(a, P.t2, P.tb, sm.rmB);
     tile_gstore(state + (((u64)blockIdx.x >> ntb) << P.n_local), tile_thread_offset(tid, sm.base, P), P, a);
+}
+
+
+// ------------------------------------------------------------------------------------ k_tile_stream
+// Persistent, warp-specialised version of the fused pass: one CTA per SM, DTC_STREAM_STAGES stage
+// buffers of 64 KB.  Warp 8 (one elected lane) drives the TMA engine: bulk / tensor-map loads into a
+// free stage (mbarrier full[s]), and -- once a compute warpgroup has signalled done[s] -- the bulk /
+// tensor-map store of the finished tile.  Two compute warpgroups (128 threads, tiles k = wg, wg+2, ...)
+// run the three in-place phases of dtc_stream.cuh on the stage buffer.  Loads and stores therefore cost
+// no registers and no issue slots of the compute warps.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+
+__device__ __forceinline__ void stream_tma_load(const DtcStreamPass& P, const CUtensorMap* tmap, const double2* state,
+                                                u64 T, uint32_t dst, uint32_t bar) {
+    mbar_expect_tx(bar, DTC_TILE * 16);
+    if (P.contig) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(state + (T << DTC_TILE_BITS)), "r"(DTC_TILE * 16), "r"(bar) : "memory");
+    } else {
+        const int lb = P.g - 2;
+        asm volatile(
+            "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5,%6}], [%7];"
+            ::"r"(dst), "l"(tmap), "r"(0), "r"((int)(T & ((1ull << lb) - 1))), "r"(0), "r"(0), "r"((int)(T >> lb)), "r"(bar)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void stream_tma_store(const DtcStreamPass& P, const CUtensorMap* tmap, double2* state, u64 T,
+                                                 uint32_t src) {
+    if (P.contig) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(state + (T << DTC_TILE_BITS)), "r"(src), "r"(DTC_TILE * 16) : "memory");
+    } else {
+        const int lb = P.g - 2;
+        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1,%2,%3,%4,%5}], [%6];"
+                     ::"l"(tmap), "r"(0), "r"((int)(T & ((1ull << lb) - 1))), "r"(0), "r"(0), "r"((int)(T >> lb)), "r"(src)
+                     : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+struct StreamSmem {
+    double2 stage[DTC_STREAM_STAGES][DTC_TILE];
+    StreamTables tab[DTC_STREAM_WG];
+    unsigned long long full[DTC_STREAM_STAGES], done[DTC_STREAM_STAGES];
+};
+static_assert(sizeof(StreamSmem) + 128 <= 227 * 1024, "stage buffers + tables must fit one CTA's shared memory");
+
+template <int MODE>
+__global__ void __launch_bounds__(DTC_STREAM_THREADS, 1)
+k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DtcStreamPass P,
+              const DtcLayer* __restrict__ layers, const u64* __restrict__ masks, long long n_traj, u64 rank_bits,
+              long long n_tiles) {
+    extern __shared__ unsigned char smraw[];
+    StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smraw + ((128u - (smem_u32(smraw) & 127u)) & 127u));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long K = (n_tiles - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < DTC_STREAM_STAGES; ++s) {
+            mbar_init(smem_u32(&sm.full[s]), 1);
+            mbar_init(smem_u32(&sm.done[s]), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 4 * DTC_STREAM_WG) {
+        // ---- TMA driver
+        if ((tid & 31) != 0) return;
+        for (long long k = 0; k < K && k < DTC_STREAM_STAGES; ++k)
+            stream_tma_load(P, &tmap, state, (u64)blockIdx.x + (u64)k * gridDim.x, smem_u32(sm.stage[k]), smem_u32(&sm.full[k]));
+        int s = 0;
+        uint32_t par = 0;
+        for (long long k = 0; k < K; ++k) {
+            mbar_wait(smem_u32(&sm.done[s]), par);
+            stream_tma_store(P, &tmap, state, (u64)blockIdx.x + (u64)k * gridDim.x, smem_u32(sm.stage[s]));
+            if (k + DTC_STREAM_STAGES < K) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has read the stage
+                stream_tma_load(P, &tmap, state, (u64)blockIdx.x + (u64)(k + DTC_STREAM_STAGES) * gridDim.x,
+                                smem_u32(sm.stage[s]), smem_u32(&sm.full[s]));
+            }
+            if (++s == DTC_STREAM_STAGES) { s = 0; par ^= 1u; }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        return;
+    }
+    // ---- compute warpgroups
+    const int wg = warp >> 2, t = tid & 127;
+    StreamTables& tab = sm.tab[wg];
+    const int ntb = P.n_local - DTC_TILE_BITS;
+    for (long long k = wg; k < K; k += DTC_STREAM_WG) {
+        const int s = (int)(k % DTC_STREAM_STAGES);
+        const uint32_t u = (uint32_t)(k / DTC_STREAM_STAGES);
+        const u64 T = (u64)blockIdx.x + (u64)k * gridDim.x;
+        const u64 traj = T >> ntb;
+        const u64 base = stream_tile_base(T & ((1ull << ntb) - 1), P);
+        const StreamMasks M = stream_load_masks(P, masks, n_traj, traj);
+        // phase tables of this tile (overlaps the load in flight)
+        if (P.layerD >= 0) stream_setup1(t, tab, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
+        wg_barrier(wg);
+        stream_setup2(t, tab, P);
+        wg_barrier(wg);
+        if (u > 0) mbar_wait(smem_u32(&sm.done[s]), (u - 1) & 1u);     // never run a full phase ahead of the stage
+        mbar_wait(smem_u32(&sm.full[s]), u & 1u);
+        double2* tile = sm.stage[s];
+        stream_phase13<MODE>(t, tile, P.t1, P.tb, M.rmA);
+        if (MODE == 1) __syncwarp(); else wg_barrier(wg);              // mode A: a warp owns local bits 10,11 in all phases
+        stream_phase2(t, tile, tab, P, M.rmA, M.rmB);
+        if (MODE == 1) __syncwarp(); else wg_barrier(wg);
+        stream_phase13<MODE>(t, tile, P.t2, P.tb, M.rmB);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
+        mbar_arrive(smem_u32(&sm.done[s]));
+    }
 }
 
 // ---- generic engine
@@ -457,6 +587,45 @@ __global__ void k_shard_pack(const double2* __restrict__ state, double2* __restr
     else out[i] = state[x];
 }
 
+
+// ---- host side of k_tile_stream
+typedef CUresult (*dtc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static dtc_encode_fn tensor_map_encoder() {
+    static dtc_encode_fn fn = []() -> dtc_encode_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+        return (dtc_encode_fn)p;
+    }();
+    return fn;
+}
+
+// tensor map of the tile {0,1} + [g, g+10) over the whole batch: (8 doubles | bits [2,g) | 32 | 32 | everything above)
+static int stream_tensor_map(CUtensorMap* tm, void* state, int n_local, int g, int64_t n_traj) {
+    dtc_encode_fn enc = tensor_map_encoder();
+    if (!enc) return fail(DTC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[5] = {8, 1ull << (g - 2), 32, 32, (cuuint64_t)n_traj << (n_local - g - 10)};
+    const cuuint64_t strides[4] = {64, 16ull << g, 16ull << (g + 5), 16ull << (g + 10)};
+    const cuuint32_t box[5] = {8, 1, 32, 32, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, state, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DTC_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    return DTC_OK;
+}
+
+static int g_stream_override = -1;      // dtc_set_stream_engine(); -1: environment / default
+static bool stream_enabled() {
+    if (g_stream_override >= 0) return g_stream_override != 0;
+    static const bool on = []() {
+        const char* e = getenv("DTCSIM_STREAM");      // 0: register-fed k_tile_pass everywhere (A/B measurements)
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+
 // ------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -548,6 +717,10 @@ int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
         CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
         CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
         CUDA_TRY(cudaFuncSetAttribute(k_tile_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
+        const int ssb = (int)sizeof(StreamSmem) + 128;
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
+        CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms[device], cudaDevAttrMultiProcessorCount, device));
         attr_set[device] = true;
     }
     p->h.finalized = true;
@@ -615,7 +788,26 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
             const char* e = getenv("DTCSIM_PREFETCH_BLOCKS");      // tuning knob; default 148 CTAs ahead (measured best on B200)
             return e ? atoi(e) : 148;
         }();
-        for (const DtcTilePass& T : h.passes) {
+        const int n_sms = (h.device >= 0 && h.device < 16 && g_num_sms[h.device] > 0) ? g_num_sms[h.device] : 148;
+        for (size_t ip = 0; ip < h.passes.size(); ++ip) {
+            const DtcTilePass& T = h.passes[ip];
+            const DtcStreamPass& S = h.spasses[ip];
+            if (S.mode && stream_enabled()) {
+                // TMA-fed streaming engine: one persistent CTA per SM
+                alignas(64) CUtensorMap tm;
+                memset(&tm, 0, sizeof(tm));
+                if (!S.contig) {
+                    const int rc = stream_tensor_map(&tm, state, h.n_local, S.g, n_traj);
+                    if (rc != DTC_OK) return rc;
+                }
+                const unsigned sgrid = (unsigned)(grid < n_sms ? grid : n_sms);
+                const size_t ssb = sizeof(StreamSmem) + 128;
+                if (S.mode == 1)
+                    k_tile_stream<1><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid);
+                else
+                    k_tile_stream<2><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid);
+                continue;
+            }
             const bool hx = T.layerD >= 0 && T.nX > 0;
 #define DTC_LAUNCH(S, X)                                                                               \
     k_tile_pass<S, X><<<(unsigned)grid, DTC_THREADS, sizeof(TileSmem), s>>>((double2*)state, T, p->d_layers, masks, \
@@ -645,6 +837,19 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     }
     if (p->profiling) CUDA_TRY(cudaEventRecord(p->ev1, s));
     CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+int dtc_set_stream_engine(int enable) {
+    g_stream_override = enable < 0 ? -1 : (enable != 0);
+    return DTC_OK;
+}
+
+int dtc_program_num_stream_passes(const dtc_program* p, int* n_passes) {
+    if (!p || !n_passes || !p->h.finalized) return fail(DTC_ERR_INVALID, "program not finalized");
+    int n = 0;
+    for (const DtcStreamPass& S : p->h.spasses) n += S.mode != 0;
+    *n_passes = n;
     return DTC_OK;
 }
 

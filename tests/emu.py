@@ -13,7 +13,7 @@ CSRC = os.path.join(os.path.dirname(HERE),
 
 
 def build(force=False):
-    deps = [SRC, os.path.join(CSRC, "dtc_hd.cuh"), os.path.join(CSRC, "dtc_core.hpp")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("dtc_hd.cuh", "dtc_core.hpp", "dtc_stream.cuh")]
     if force or not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", OUT, SRC])
@@ -61,7 +61,7 @@ def run(prog, n_traj=1, traj_offset=0, seed=0, init_index=0, engine=0, n_local=N
 def schedule(prog, n_local=None, cap=4096):
     ev = prog.arrays()
     n_local = prog.n_main if n_local is None else n_local
-    rows = np.zeros((cap, 21), dtype=np.int32)
+    rows = np.zeros((cap, 22), dtype=np.int32)
     err = ctypes.create_string_buffer(512)
     n = lib().emu_schedule(
         ctypes.c_int(prog.n), ctypes.c_int(prog.n_layers), ctypes.c_int64(len(ev["type"])),

@@ -55,6 +55,34 @@ static void emu_tile_pass(double2* state, const DtcTilePass& P, const DtcLayer* 
     }
 }
 
+
+// k_tile_stream: the TMA load / store are emulated by a gather / scatter of the tile into a dense stage
+// buffer; the two warpgroup barriers of the table setup and the phase boundaries are loop boundaries.
+template <int MODE>
+static void emu_stream_pass(double2* state, const DtcStreamPass& P, const DtcLayer* layers, const u64* masks,
+                            long long n_traj, u64 rank_bits, u64 T, std::vector<double2>& stage, StreamTables& tab) {
+    const int ntb = P.n_local - DTC_TILE_BITS;
+    const u64 traj = T >> ntb, tit = T & ((1ull << ntb) - 1);
+    double2* st = state + (traj << P.n_local);
+    const u64 base = stream_tile_base(tit, P);
+    auto gidx = [&](int l) {
+        u64 o = base;
+        for (int b = 0; b < DTC_TILE_BITS; ++b)
+            if ((l >> b) & 1) o += 1ull << P.tb[b];
+        return o;
+    };
+    for (int l = 0; l < DTC_TILE; ++l) stage[l] = st[gidx(l)];
+    const StreamMasks M = stream_load_masks(P, masks, n_traj, traj);
+    if (P.layerD >= 0)
+        for (int t = 0; t < 128; ++t)
+            stream_setup1(t, tab, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
+    for (int t = 0; t < 128; ++t) stream_setup2(t, tab, P);
+    for (int t = 0; t < 128; ++t) stream_phase13<MODE>(t, stage.data(), P.t1, P.tb, M.rmA);
+    for (int t = 0; t < 128; ++t) stream_phase2(t, stage.data(), tab, P, M.rmA, M.rmB);
+    for (int t = 0; t < 128; ++t) stream_phase13<MODE>(t, stage.data(), P.t2, P.tb, M.rmB);
+    for (int l = 0; l < DTC_TILE; ++l) st[gidx(l)] = stage[l];
+}
+
 extern "C" int emu_run(int n_qubits, int n_layers, int64_t n_events, const int32_t* type, const int32_t* layer,
                        const int32_t* q0, const int32_t* q1, const int32_t* slot, const double* val,
                        const double* probs, double global_phase, int engine, int n_local, int n_exec_layers, int64_t n_traj,
@@ -73,6 +101,9 @@ extern "C" int emu_run(int n_qubits, int n_layers, int64_t n_events, const int32
     if (!dtc_stage_events(P, n_events, type, layer, q0, q1, slot, val, probs, global_phase, err)) return bail(err);
     if (!dtc_build_layers(P, err)) return bail(err);
     if (engine == 0) engine = (n_local >= DTC_TILE_BITS) ? 2 : 1;
+    const bool use_stream = engine == 3;      // 3: streaming engine where a pass is eligible, tile engine elsewhere
+    if (engine == 3) engine = 2;
+    int n_stream = 0;
     if (engine == 2) {
         if (n_local < DTC_TILE_BITS) return bail("tile engine needs n_local >= 12");
         if (!dtc_schedule_tile(P, err)) return bail(err);
@@ -93,7 +124,19 @@ extern "C" int emu_run(int n_qubits, int n_layers, int64_t n_events, const int32
         TileSmem* sm = new TileSmem();
         std::vector<double2> regs((size_t)DTC_THREADS * DTC_NREG);
         const u64 grid = (u64)n_traj << (n_local - DTC_TILE_BITS);
-        for (const DtcTilePass& T : P.passes) {
+        std::vector<double2> stage(DTC_TILE);
+        StreamTables* tab = new StreamTables();
+        for (size_t ip = 0; ip < P.passes.size(); ++ip) {
+            const DtcTilePass& T = P.passes[ip];
+            const DtcStreamPass& S = P.spasses[ip];
+            if (use_stream && S.mode) {
+                ++n_stream;
+                for (u64 b = 0; b < grid; ++b) {
+                    if (S.mode == 1) emu_stream_pass<1>(st, S, P.layers.data(), masks.data(), n_traj, rank_bits, b, stage, *tab);
+                    else emu_stream_pass<2>(st, S, P.layers.data(), masks.data(), n_traj, rank_bits, b, stage, *tab);
+                }
+                continue;
+            }
             for (u64 b = 0; b < grid; ++b) {
                 if (T.s2_lo == 0) emu_tile_pass<0>(st, T, P.layers.data(), masks.data(), n_traj, rank_bits, b, *sm, regs);
                 else if (T.s2_lo == 1) emu_tile_pass<1>(st, T, P.layers.data(), masks.data(), n_traj, rank_bits, b, *sm, regs);
@@ -101,6 +144,8 @@ extern "C" int emu_run(int n_qubits, int n_layers, int64_t n_events, const int32
             }
         }
         delete sm;
+        delete tab;
+        if (use_stream) *n_passes = n_stream;      // callers of engine 3 want to know how many passes streamed
     } else {
         for (const DtcGenericStep& g : P.gsteps) {
             if (g.kind == 0) {
@@ -130,7 +175,7 @@ extern "C" int emu_run(int n_qubits, int n_layers, int64_t n_events, const int32
 }
 
 // expose the pass schedule for inspection by tests: fills up to `cap` rows of
-// [s2_lo, layerA, layerD, layerB, nT1, nT2, nX, nC, nO, tb0..tb11]
+// [s2_lo, layerA, layerD, layerB, nT1, nT2, nX, nC, nO, tb0..tb11, stream mode (0: not eligible)]
 extern "C" int emu_schedule(int n_qubits, int n_layers, int64_t n_events, const int32_t* type, const int32_t* layer,
                             const int32_t* q0, const int32_t* q1, const int32_t* slot, const double* val,
                             const double* probs, int n_local, int n_exec_layers, int32_t* rows, int cap, char* errbuf, int errlen) {
@@ -148,10 +193,11 @@ extern "C" int emu_schedule(int n_qubits, int n_layers, int64_t n_events, const 
     int n = 0;
     for (const DtcTilePass& T : P.passes) {
         if (n >= cap) break;
-        int32_t* r = rows + (size_t)n * 21;
+        int32_t* r = rows + (size_t)n * 22;
         r[0] = T.s2_lo; r[1] = T.layerA; r[2] = T.layerD; r[3] = T.layerB;
         r[4] = T.nT1; r[5] = T.nT2; r[6] = T.nX; r[7] = T.nC; r[8] = T.nO;
         for (int l = 0; l < 12; ++l) r[9 + l] = T.tb[l];
+        r[21] = P.spasses[(size_t)n].mode;
         ++n;
     }
     return (int)P.passes.size();

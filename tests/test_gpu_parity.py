@@ -361,3 +361,47 @@ def test_trajectory_ranges_concatenate(disorder):
     from dtcsim import dist as D
     sampler = D.ShardedSampler(sim, 0, 1)
     assert sampler.run_counts(circ, shots=200, seed_simulator=9) == counts
+
+
+# ---- TMA-fed streaming engine (k_tile_stream)
+@pytest.mark.parametrize("L,t,echo,pol,state,ntraj", [
+    (12, 2, False, "x", "vacuum", 200),    # n = 12: more tiles than SMs, one contiguous tile per state
+    (13, 3, True, "y", "vacuum", 5),       # mode A + mode B (64 B runs, g = 3), fewer tiles than CTAs x stages
+    (16, 2, True, "xy", "neel", 21),       # ragged: 21 * 16 tiles over 148 CTAs
+    (20, 3, True, "x", "vacuum", 3),       # config-C2 shape: 768 tiles, >= 5 per CTA (stage ring wraps)
+])
+def test_stream_engine_equals_register_engine(ctx, disorder, L, t, echo, pol, state, ntraj):
+    """Same program through k_tile_stream and through k_tile_pass: psi' within 1e-13, frames identical."""
+    from dtcsim import backend, capi
+    hs, phis = disorder[20][0][1][:L], disorder[20][1][1][:L - 1]
+    circ = RC.transpiled(RC.qc_body(state, L, 0.97, hs, phis, t, L // 2, echo, pol))
+    prog = compile_circuit(circ, RC.noise_model(0.05), optimize=True)
+    h = capi.ProgramHandle(prog, 0)
+    assert h.num_stream_passes == h.num_passes > 0
+    try:
+        capi.set_stream_engine(False)
+        a = backend.evolve(ctx, prog, ntraj, 7, 99, handle=h)
+        sa, fa = a.state.clone(), a.frames_host()
+        capi.set_stream_engine(True)
+        b = backend.evolve(ctx, prog, ntraj, 7, 99, handle=h)
+        sb, fb = b.state, b.frames_host()
+    finally:
+        capi.set_stream_engine(None)
+    assert all(np.array_equal(x, y) for x, y in zip(fa, fb))
+    assert float((sa - sb).abs().max()) < 1e-13
+    assert abs(float((sb.abs() ** 2).sum()) / ntraj - 1.0) < 1e-9
+
+
+def test_stream_engine_vs_oracle_full_register(ctx, disorder):
+    """Ancilla kept in the register: streaming where eligible, amplitudes against the numpy oracle."""
+    from dtcsim import capi
+    L = 14
+    hs, phis = disorder[20][0][2][:L], disorder[20][1][2][:L - 1]
+    circ = RC.transpiled(RC.qc_body("vacuum", L, 0.97, hs, phis, 2, L // 2, True, "x"))
+    oc, na, _ = O.compact_ops(RC.ops_of(circ), circ.num_qubits)
+    prog = compile_circuit(circ, RC.noise_model(0.05))
+    h = capi.ProgramHandle(prog, 0)
+    assert h.num_stream_passes > 0
+    psi, _ = _evolve_true(ctx, prog, 4, 11, 5, engine=2)
+    ref = O.run_trajectories(oc, na, O.PauliNoise.depolarizing(0.05), 5, np.arange(11, 15))
+    assert np.abs(psi - ref).max() < AMP_TOL
