@@ -262,7 +262,8 @@ def run_ours(args):
     gpu_launches = launches[0]
     autocorr = (sums[:, 0] / (NT * world)).cpu().numpy()
 
-    # ---- roofline of the dominant kernel (k_tile_pass): algorithmic bytes per launch / launch duration
+    # ---- roofline of the dominant kernel (k_tile_stream, the TMA-fed fused pass; k_tile_pass where a pass is not
+    #      eligible): algorithmic bytes per launch / launch duration
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_file):
         with open(peaks_file) as fh:
@@ -272,11 +273,19 @@ def run_ours(args):
     last_batch = NT - ((NT - 1) // bt) * bt              # pass_time() refers to each handle's last run
     bytes_per_launch = 2 * 16 * (1 << nmax) * last_batch           # one read + one write of the batch of states
     roof = None
+    n_stream = int(sum(h.num_stream_passes for h in handles))
+    n_pass_all = int(sum(h.num_passes for h in handles))
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "ncu_tile_stream_traffic.json")      # from the committed ncu --set full capture
+    if os.path.exists(tf):
+        with open(tf) as fh:
+            traffic = float(json.load(fh)["dram_bytes_per_algorithmic_byte"]) * bytes_per_launch
     if pass_n:
         avg_ms = pass_ms / pass_n
         ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "kernel": "k_tile_pass", "avg_launch_ms": avg_ms, "launches_timed": pass_n,
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "kernel": "k_tile_stream" if 2 * n_stream >= n_pass_all else "k_tile_pass",
+                "stream_passes": n_stream, "passes": n_pass_all, "avg_launch_ms": avg_ms, "launches_timed": pass_n,
                 "bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
                 "register_qubits": nmax,
                 "periods_frac_n21_model": (value / world) * (2 * 16 * (1 << (L + 1))) / (peak * 1e9),

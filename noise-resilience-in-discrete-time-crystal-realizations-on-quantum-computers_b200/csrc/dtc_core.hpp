@@ -250,6 +250,7 @@ static inline bool dtc_make_stream_pass(const DtcTilePass& T, const DtcLayer* LD
     else if ((contig || modeB_shape) && !(active & 0x3u)) mode = 2;
     if (!mode) return false;
     S.mode = mode;
+    S.two = 2;
     S.contig = contig ? 1 : 0;
     S.n_local = T.n_local;
     S.g = T.tb[2];
@@ -264,15 +265,23 @@ static inline bool dtc_make_stream_pass(const DtcTilePass& T, const DtcLayer* LD
     int loc[DTC_MAXQ];
     for (int q = 0; q < DTC_MAXQ; ++q) loc[q] = -1;
     for (int l = 0; l < DTC_TILE_BITS; ++l) loc[T.tb[l]] = l;
-    const unsigned W2 = 0xF07u;                              // local bits 0,1,2,8,9,10,11
+    struct Bond { int k, a, b, fam; };
+    Bond bonds[DTC_MAXT];
+    int nb = 0;
     for (int k = 0; k < L.n_terms; ++k) {
         if (L.ts[k] == 0.0 && L.tc[k] == 1.0) continue;      // unused slot
         int a = loc[L.ti[k]], b = loc[L.tj[k]];
         if (a >= 0 && b >= 0) {
             if (a > b) { int t = a; a = b; b = t; }
-            if (a >= 2 && b <= 8) { S.T1k[S.nT1] = k; S.T1a[S.nT1] = a; S.T1b[S.nT1] = b; ++S.nT1; }
-            else if (((W2 >> a) & 1u) && ((W2 >> b) & 1u)) { S.T2k[S.nT2] = k; S.T2a[S.nT2] = a; S.T2b[S.nT2] = b; ++S.nT2; }
-            else return false;
+            int fam;
+            if (a >= 3 && b <= 7) fam = 0;
+            else if (a == 2 && b == 3) fam = 1;
+            else if (a == 7 && b == 8) fam = 2;
+            else if (b <= 2) fam = 3;
+            else if (a >= 8) fam = 4;
+            else if (a <= 2 && b >= 8) fam = 5;
+            else return false;                               // a bit of [3,7] bonded to a far bit: register-fed kernel
+            bonds[nb++] = Bond{k, a, b, fam};
         } else if (a >= 0 || b >= 0) {
             S.Ck[S.nC] = k;
             S.Ca[S.nC] = (a >= 0) ? a : b;
@@ -282,6 +291,13 @@ static inline bool dtc_make_stream_pass(const DtcTilePass& T, const DtcLayer* LD
             S.Ok[S.nO] = k; S.Oa[S.nO] = L.ti[k]; S.Ob[S.nO] = L.tj[k]; ++S.nO;
         }
     }
+    int n = 0;
+    for (int f = 0; f < 6; ++f) {
+        S.fam_off[f] = n;
+        for (int i = 0; i < nb; ++i)
+            if (bonds[i].fam == f) { S.Fk[n] = bonds[i].k; S.Fa[n] = bonds[i].a; S.Fb[n] = bonds[i].b; ++n; }
+    }
+    S.fam_off[6] = n;
     return true;
 }
 

@@ -18,32 +18,49 @@
 #pragma once
 #include "dtc_hd.cuh"
 
+#if defined(__CUDACC__)
+#define DTC_NOUNROLL _Pragma("unroll 1")
+#else
+#define DTC_NOUNROLL
+#endif
+
 #define DTC_STREAM_STAGES 3
 #define DTC_STREAM_WG 2                       // compute warpgroups (128 threads each) per CTA
-#define DTC_STREAM_THREADS (128 * DTC_STREAM_WG + 32)
+#define DTC_STREAM_THREADS (128 * DTC_STREAM_WG + 32 + 32 * DTC_STREAM_STAGES)   // + TMA driver warp + one table-builder warp per stage
 
 struct DtcStreamPass {
     int mode;                      // 1: A, 2: B
     int contig;                    // tile is 64 KB contiguous in global memory (bulk copy, no tensor map)
     int n_local, g;                // B: tile bits 2..11 = global bits g..g+9
     int layerA, layerD, layerB;
-    int n_terms_pad_;
+    int two;                       // = 2: opaque trip count that keeps shared code blocks rolled (instruction footprint)
     int tb[DTC_TILE_BITS];
     double t1[DTC_TILE_BITS], t2[DTC_TILE_BITS];
     u64 tile_mask;
-    int nT1, nT2, nC, nO;
-    unsigned char T1k[DTC_MAXT], T1a[DTC_MAXT], T1b[DTC_MAXT];   // bonds with both ends in local [2, 8]
-    unsigned char T2k[DTC_MAXT], T2a[DTC_MAXT], T2b[DTC_MAXT];   // both ends in {0,1,2,8,9,10,11}
+    // two-body terms of D_layerD, local-local ones by table family:
+    //   0: core  both ends in local [3,7]      1: (2,3)                    2: (7,8)
+    //   3: T2lo  both in {0,1,2}               4: T2hi  both in [8,11]     5: T2x  one in {0,1,2}, one in [8,11]
+    int fam_off[7];                // family f = entries [fam_off[f], fam_off[f+1]) of Fk/Fa/Fb
+    int nC, nO;
+    unsigned char Fk[DTC_MAXT], Fa[DTC_MAXT], Fb[DTC_MAXT];
     unsigned char Ck[DTC_MAXT], Ca[DTC_MAXT], Cb[DTC_MAXT];      // local a, outer qubit b
     unsigned char Ok[DTC_MAXT], Oa[DTC_MAXT], Ob[DTC_MAXT];      // outer, outer
 };
 
-// per-warpgroup phase tables
-struct StreamTables {
-    double2 T1[128];               // index = local bits 2..8
+// per-stage phase tables of the tile in that stage, written by the stage's table-builder warp.
+// Phase of tile-local index l = T1c[l[3:7]] * F[l2][l3] * G[l8][l7] * T2[l[0:2], l[8:11]]
+struct StreamSlot {
+    double2 T1c[32];               // one-body of local 3..7 and bonds inside [3,7]; index = l[3:7] (the phase-2 register)
+    double2 F[2][2], G[2][2];      // bonds (2,3): F[l2][l3];  bonds (7,8): G[l8][l7]
     double2 T2[128];               // index = local bits 0,1,2,8,9,10,11 (= thread id of phase 2), times the tile constant
+    u64 rmA, rmB;                  // rotation sign masks of the tile's trajectory
+};
+
+// scratch of one table-builder warp
+struct StreamBuild {
     double2 E[DTC_TILE_BITS][2];
     double2 B[DTC_MAXT][2];
+    double2 T1c[32], FG[8], T2lo[8], T2hi[16];
     double2 scratch[32];
     double2 C;
 };
@@ -88,9 +105,7 @@ DTC_HD void stream_signed_s1(const double* tbase, const int* tb, u64 rmask, doub
 
 // ---- phases (tile: the stage buffer, 4096 chunks of 16 B)
 template <int MODE>
-DTC_HD void stream_phase13(int t, double2* tile, const double* tbase, const int* tb, u64 rmask) {
-    double tt[5];
-    stream_signed_s1<MODE>(tbase, tb, rmask, tt);
+DTC_HD void stream_phase13_signed(int t, double2* tile, const double tt[5]) {
     double2 a[DTC_NREG];
     // MODE A: 8 address registers (k & 7) + immediates; MODE B: 2 + immediates
     double2* p[8];
@@ -104,7 +119,14 @@ DTC_HD void stream_phase13(int t, double2* tile, const double* tbase, const int*
     for (int k = 0; k < DTC_NREG; ++k) p[k & (NP - 1)][(MODE == 1) ? ((k >> 3) << 8) : ((k >> 1) << 8)] = a[k];
 }
 
-DTC_HD void stream_phase2(int t, double2* tile, const StreamTables& tab, const DtcStreamPass& P, u64 rmA, u64 rmB) {
+template <int MODE>
+DTC_HD void stream_phase13(int t, double2* tile, const double* tbase, const int* tb, u64 rmask) {
+    double tt[5];
+    stream_signed_s1<MODE>(tbase, tb, rmask, tt);
+    stream_phase13_signed<MODE>(t, tile, tt);
+}
+
+DTC_HD void stream_phase2(int t, double2* tile, const StreamSlot& tab, const DtcStreamPass& P, u64 rmA, u64 rmB) {
     double tA[5], tB[5];
     tile_signed_t(P.t1, P.tb, 3, rmA, tA);
     tile_signed_t(P.t2, P.tb, 3, rmB, tB);
@@ -112,16 +134,19 @@ DTC_HD void stream_phase2(int t, double2* tile, const StreamTables& tab, const D
     double2* p = tile + stream_chunk2(t, 0);
 #pragma unroll
     for (int r = 0; r < DTC_NREG; ++r) a[r] = p[r << 3];
+    // thread constants c[l7][l3] = T2[t] * F[l2][l3] * G[l8][l7]   (l2 = lane bit 2, l8 = lane bit 3)
+    const int lane = t & 31, l2 = (lane >> 2) & 1, l8 = (lane >> 3) & 1;
+    const double2 cf0 = cmul(tab.T2[t], tab.F[l2][0]), cf1 = cmul(tab.T2[t], tab.F[l2][1]);
+    const double2 c00 = cmul(cf0, tab.G[l8][0]), c01 = cmul(cf1, tab.G[l8][0]);
+    const double2 c10 = cmul(cf0, tab.G[l8][1]), c11 = cmul(cf1, tab.G[l8][1]);
+    // (a rolled two-iteration loop sharing the two four-level blocks was measured slower: selects + spills)
     tile_rot_bits(a, tA, 0, 4);
-    const int lane = t & 31;
-    const double2 cthr = tab.T2[t];
-    // T1 index = l2 | r << 1 | l8 << 6   (l2 = lane bit 2, l8 = lane bit 3)
-    const double2* t1 = tab.T1 + (((lane >> 2) & 1) | (((lane >> 3) & 1) << 6));
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         rot_pair(a[i], a[i | 16], tA[4]);
-        const double2 p0 = cmul(t1[i << 1], cthr);
-        const double2 p1 = cmul(t1[(i | 16) << 1], cthr);
+        // T1c is read at warp-uniform addresses (one shared-memory wavefront per load)
+        const double2 p0 = cmul(tab.T1c[i], (i & 1) ? c01 : c00);
+        const double2 p1 = cmul(tab.T1c[i | 16], (i & 1) ? c11 : c10);
         a[i] = cmul(a[i], p0);
         a[i | 16] = cmul(a[i | 16], p1);
         rot_pair(a[i], a[i | 16], tB[4]);
@@ -132,73 +157,109 @@ DTC_HD void stream_phase2(int t, double2* tile, const StreamTables& tab, const D
     for (int r = 0; r < DTC_NREG; ++r) p[r << 3] = a[r];
 }
 
-// ---- phase tables of one tile.  Step 1 (E, B, tile constant), warpgroup barrier, step 2 (T1, T2).
+// ---- phase tables of one tile, built by ONE warp in three steps separated by __syncwarp().
 // g_outer: global index of the tile's local index 0 (incl. rank bits above n_local).
-DTC_HD void stream_setup1(int t, StreamTables& tab, const DtcStreamPass& P, const DtcLayer& L, u64 g_outer,
+DTC_HD double2 stream_bond(const StreamBuild& bl, const DtcStreamPass& P, int c, int l12) {
+    return bl.B[P.Fk[c]][((l12 >> P.Fa[c]) ^ (l12 >> P.Fb[c])) & 1];
+}
+
+// step 1: one-body factors E (incl. bonds to outer qubits), bond factors B, outer factors of the tile constant
+DTC_HD void stream_build1(int lane, StreamBuild& bl, const DtcStreamPass& P, const DtcLayer& L, u64 g_outer,
                           u64 m1a, u64 m1b, u64 m2) {
-    if (t < 2 * DTC_TILE_BITS) {
-        const int l = t >> 1, bit = t & 1;
+    if (lane < 2 * DTC_TILE_BITS) {
+        const int l = lane >> 1, bit = lane & 1;
         double2 e = d1_factor(L, P.tb[l], bit, m1a, m1b);
+        DTC_NOUNROLL
         for (int c = 0; c < P.nC; ++c)
             if (P.Ca[c] == l) e = cmul(e, d2_factor(L, P.Ck[c], bit ^ (int)((g_outer >> P.Cb[c]) & 1ull), m2));
-        tab.E[l][bit] = e;
-    } else if (t >= 32 && t < 32 + DTC_MAXT) {
-        const int k = t - 32;
-        if (k < L.n_terms) {
-            tab.B[k][0] = d2_factor(L, k, 0, m2);
-            tab.B[k][1] = d2_factor(L, k, 1, m2);
+        bl.E[l][bit] = e;
+    }
+    DTC_NOUNROLL
+    for (int k = lane; k < L.n_terms; k += 32) {
+        bl.B[k][0] = d2_factor(L, k, 0, m2);
+        bl.B[k][1] = d2_factor(L, k, 1, m2);
+    }
+    const u64 any = (L.d1_any[0] | L.d1_any[1]) & ~P.tile_mask;
+    const int cnt = DTC_POPC64(any);
+    double2 f = make_double2(1.0, 0.0);
+    DTC_NOUNROLL
+    for (int it = lane; it < cnt + P.nO; it += 32) {
+        if (it < cnt) {
+            u64 m = any;
+            DTC_NOUNROLL
+            for (int k = 0; k < it; ++k) m &= m - 1;
+            const int q = DTC_CTZ64(m);
+            f = cmul(f, d1_factor(L, q, (int)((g_outer >> q) & 1ull), m1a, m1b));
+        } else {
+            const int o = it - cnt;
+            const int par = (int)(((g_outer >> P.Oa[o]) ^ (g_outer >> P.Ob[o])) & 1ull);
+            f = cmul(f, d2_factor(L, P.Ok[o], par, m2));
         }
-    } else if (t >= 96) {
-        const int lane = t - 96;
-        const u64 any = (L.d1_any[0] | L.d1_any[1]) & ~P.tile_mask;
-        const int cnt = DTC_POPC64(any);
-        double2 f = make_double2(1.0, 0.0);
-        for (int it = lane; it < cnt + P.nO; it += 32) {
-            if (it < cnt) {
-                u64 m = any;
-                for (int k = 0; k < it; ++k) m &= m - 1;
-                const int q = DTC_CTZ64(m);
-                f = cmul(f, d1_factor(L, q, (int)((g_outer >> q) & 1ull), m1a, m1b));
-            } else {
-                const int o = it - cnt;
-                const int par = (int)(((g_outer >> P.Oa[o]) ^ (g_outer >> P.Ob[o])) & 1ull);
-                f = cmul(f, d2_factor(L, P.Ok[o], par, m2));
-            }
-        }
-        tab.scratch[lane] = f;
-        DTC_SYNCWARP();
+    }
+    bl.scratch[lane] = f;
+}
+
+// step 2: core table (one entry per lane), F/G, and the two halves of T2 (T2lo over local 0..2, T2hi over local 8..11)
+DTC_HD void stream_build2(int lane, StreamBuild& bl, const DtcStreamPass& P, const DtcLayer& L) {
+    {
+        const int l12 = lane << 3;
+        double2 p = bl.E[3][lane & 1];
+#pragma unroll
+        for (int l = 4; l <= 7; ++l) p = cmul(p, bl.E[l][(lane >> (l - 3)) & 1]);
+        DTC_NOUNROLL
+        for (int c = P.fam_off[0]; c < P.fam_off[1]; ++c) p = cmul(p, stream_bond(bl, P, c, l12));
+        bl.T1c[lane] = p;
+    }
+    if (lane < 16) {
+        const int l12 = lane << 8;
+        double2 p = bl.E[8][lane & 1];
+#pragma unroll
+        for (int l = 9; l < DTC_TILE_BITS; ++l) p = cmul(p, bl.E[l][(lane >> (l - 8)) & 1]);
+        DTC_NOUNROLL
+        for (int c = P.fam_off[4]; c < P.fam_off[5]; ++c) p = cmul(p, stream_bond(bl, P, c, l12));
+        bl.T2hi[lane] = p;
+    } else if (lane < 24) {
+        const int i = lane - 16;
+        double2 p = cmul(bl.E[0][i & 1], cmul(bl.E[1][(i >> 1) & 1], bl.E[2][(i >> 2) & 1]));
+        DTC_NOUNROLL
+        for (int c = P.fam_off[3]; c < P.fam_off[4]; ++c) p = cmul(p, stream_bond(bl, P, c, i));
+        bl.T2lo[i] = p;
+    } else {
+        // FG[0..3] = F[l2][l3], FG[4..7] = G[l8][l7]: products of bond factors, index = parity of the two bits
+        const int i = lane - 24, fam = 1 + (i >> 2), par = ((i >> 1) ^ i) & 1;
+        double2 p = make_double2(1.0, 0.0);
+        DTC_NOUNROLL
+        for (int c = P.fam_off[fam]; c < P.fam_off[fam + 1]; ++c) p = cmul(p, bl.B[P.Fk[c]][par]);
+        bl.FG[i] = p;
         if (lane == 31) {                 // the last lane: the sequential CPU emulation has run all others by now
+            const u64 any = (L.d1_any[0] | L.d1_any[1]) & ~P.tile_mask;
+            const int n = DTC_POPC64(any) + P.nO;
             double2 c = make_double2(L.cr, L.ci);
-            const int used = (cnt + P.nO < 32) ? cnt + P.nO : 32;
-            for (int k = 0; k < used; ++k) c = cmul(c, tab.scratch[k]);
-            tab.C = c;
+            DTC_NOUNROLL
+            for (int k = 0; k < (n < 32 ? n : 32); ++k) c = cmul(c, bl.scratch[k]);
+            bl.C = c;
         }
     }
 }
 
-DTC_HD void stream_setup2(int t, StreamTables& tab, const DtcStreamPass& P) {
-    if (P.layerD < 0) {
-        tab.T1[t] = make_double2(1.0, 0.0);
-        tab.T2[t] = make_double2(1.0, 0.0);
-        return;
-    }
-    {   // T1: index bit j <-> local bit 2 + j; one-body factors of local bits 3..7, bonds inside [2, 8]
-        double2 p = tab.E[3][(t >> 1) & 1];
-#pragma unroll
-        for (int l = 4; l <= 7; ++l) p = cmul(p, tab.E[l][(t >> (l - 2)) & 1]);
-        for (int c = 0; c < P.nT1; ++c)
-            p = cmul(p, tab.B[P.T1k[c]][((t >> (P.T1a[c] - 2)) ^ (t >> (P.T1b[c] - 2))) & 1]);
-        tab.T1[t] = p;
-    }
-    {   // T2: index bits 0..2 <-> local 0..2, bits 3..6 <-> local 8..11
-        const int l12 = (t & 7) | ((t >> 3) << 8);          // the thread's fixed local bits as a 12-bit index
-        double2 p = tab.C;
-#pragma unroll
-        for (int l = 0; l < DTC_TILE_BITS; ++l)
-            if (l < 3 || l > 7) p = cmul(p, tab.E[l][(l12 >> l) & 1]);
-        for (int c = 0; c < P.nT2; ++c)
-            p = cmul(p, tab.B[P.T2k[c]][((l12 >> P.T2a[c]) ^ (l12 >> P.T2b[c])) & 1]);
-        tab.T2[t] = p;
+// step 3: fill the slot
+DTC_HD void stream_build3(int lane, const StreamBuild& bl, StreamSlot& slot, const DtcStreamPass& P) {
+    const double2 one = make_double2(1.0, 0.0);
+    const bool ident = P.layerD < 0;
+    slot.T1c[lane] = ident ? one : bl.T1c[lane];
+    if (lane < 8) (&slot.F[0][0])[lane] = ident ? one : bl.FG[lane];      // F and G are adjacent: FG[4..7] lands in G
+#pragma unroll 1
+    for (int m = 0; m < 4; ++m) {
+        const int idx = lane + 32 * m;
+        if (ident) {
+            slot.T2[idx] = one;
+            continue;
+        }
+        const int l12 = (idx & 7) | ((idx >> 3) << 8);
+        double2 q = cmul(bl.C, cmul(bl.T2lo[idx & 7], bl.T2hi[idx >> 3]));
+        DTC_NOUNROLL
+        for (int c = P.fam_off[5]; c < P.fam_off[6]; ++c) q = cmul(q, stream_bond(bl, P, c, l12));
+        slot.T2[idx] = q;
     }
 }
 

@@ -131,7 +131,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ void wg_barrier(int wg) {
+    if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 
 __device__ __forceinline__ void stream_tma_load(const DtcStreamPass& P, const CUtensorMap* tmap, const double2* state,
                                                 u64 T, uint32_t dst, uint32_t bar) {
@@ -161,13 +164,38 @@ __device__ __forceinline__ void stream_tma_store(const DtcStreamPass& P, const C
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+// Optional role timing (build with -DDTC_STREAM_TIMING; tuning only): cycles per role and state, summed over CTAs.
+#ifdef DTC_STREAM_TIMING
+__device__ unsigned long long g_stream_prof[16];
+#define PROF_DECL unsigned long long pf_t = clock64(), pf_acc[4] = {0, 0, 0, 0}
+#define PROF_LAP(i) do { const unsigned long long n_ = clock64(); pf_acc[i] += n_ - pf_t; pf_t = n_; } while (0)
+#define PROF_FLUSH(base, cond) do { if (cond) for (int i_ = 0; i_ < 4; ++i_) atomicAdd(&g_stream_prof[(base) + i_], pf_acc[i_]); } while (0)
+#else
+#define PROF_DECL
+#define PROF_LAP(i)
+#define PROF_FLUSH(base, cond)
+#endif
+
+// Phases 1 and 3 are the same code with different tan values; one out-of-line copy keeps the instruction
+// footprint of the compute warps small (straight-line code, fetched once per tile per warp).
+template <int MODE>
+__device__ __noinline__ void stream_phase13_call(int t, double2* tile, double t0, double t1, double t2, double t3, double t4) {
+    const double tt[5] = {t0, t1, t2, t3, t4};
+    stream_phase13_signed<MODE>(t, tile, tt);
+}
+
 struct StreamSmem {
     double2 stage[DTC_STREAM_STAGES][DTC_TILE];
-    StreamTables tab[DTC_STREAM_WG];
+    StreamSlot slot[DTC_STREAM_STAGES];
+    StreamBuild build[DTC_STREAM_STAGES];
+    DtcLayer layer;                                   // D layer of this pass (fixed for the whole launch)
     unsigned long long full[DTC_STREAM_STAGES], done[DTC_STREAM_STAGES];
 };
 static_assert(sizeof(StreamSmem) + 128 <= 227 * 1024, "stage buffers + tables must fit one CTA's shared memory");
 
+// Warp roles: warps 0..7 two compute warpgroups; warp 8 TMA driver (one lane); warps 9.. one table builder per stage.
+// full[s] completes when the tile's bytes have landed AND its tables are written (2 arrivals + tx bytes);
+// done[s] completes when all 128 threads of the warpgroup have finished the tile in stage s.
 template <int MODE>
 __global__ void __launch_bounds__(DTC_STREAM_THREADS, 1)
 k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DtcStreamPass P,
@@ -180,10 +208,15 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < DTC_STREAM_STAGES; ++s) {
-            mbar_init(smem_u32(&sm.full[s]), 1);
+            mbar_init(smem_u32(&sm.full[s]), 2);
             mbar_init(smem_u32(&sm.done[s]), 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (P.layerD >= 0) {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(layers + P.layerD);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sm.layer);
+        for (int i = tid; i < (int)(sizeof(DtcLayer) / 8); i += DTC_STREAM_THREADS) dst[i] = src[i];
     }
     __syncthreads();
     if (warp == 4 * DTC_STREAM_WG) {
@@ -193,46 +226,91 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
             stream_tma_load(P, &tmap, state, (u64)blockIdx.x + (u64)k * gridDim.x, smem_u32(sm.stage[k]), smem_u32(&sm.full[k]));
         int s = 0;
         uint32_t par = 0;
+        PROF_DECL;
         for (long long k = 0; k < K; ++k) {
             mbar_wait(smem_u32(&sm.done[s]), par);
+            PROF_LAP(0);
             stream_tma_store(P, &tmap, state, (u64)blockIdx.x + (u64)k * gridDim.x, smem_u32(sm.stage[s]));
             if (k + DTC_STREAM_STAGES < K) {
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has read the stage
+                PROF_LAP(1);
                 stream_tma_load(P, &tmap, state, (u64)blockIdx.x + (u64)(k + DTC_STREAM_STAGES) * gridDim.x,
                                 smem_u32(sm.stage[s]), smem_u32(&sm.full[s]));
             }
             if (++s == DTC_STREAM_STAGES) { s = 0; par ^= 1u; }
+            PROF_LAP(2);
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        PROF_LAP(3);
+        PROF_FLUSH(0, true);
+        return;
+    }
+    const int ntb = P.n_local - DTC_TILE_BITS;
+    if (warp > 4 * DTC_STREAM_WG) {
+        // ---- table builder of stage s: phase tables + rotation sign masks of tiles k = s, s + stages, ...
+        const int lane = tid & 31, s = warp - (4 * DTC_STREAM_WG + 1);
+        StreamBuild& bl = sm.build[s];
+        StreamSlot& slot = sm.slot[s];
+        if (s >= K) return;
+        StreamMasks M = stream_load_masks(P, masks, n_traj, ((u64)blockIdx.x + (u64)s * gridDim.x) >> ntb);
+        uint32_t par = 1;                                  // parity of done[s] for the PREVIOUS use of the slot
+        PROF_DECL;
+        for (long long k = s; k < K; k += DTC_STREAM_STAGES) {
+            const u64 T = (u64)blockIdx.x + (u64)k * gridDim.x;
+            // next tile's masks: issued now, consumed in the next iteration
+            const u64 Tn = (k + DTC_STREAM_STAGES < K) ? T + (u64)DTC_STREAM_STAGES * gridDim.x : T;
+            const StreamMasks Mn = stream_load_masks(P, masks, n_traj, Tn >> ntb);
+            const u64 base = stream_tile_base(T & ((1ull << ntb) - 1), P);
+            if (P.layerD >= 0) {
+                stream_build1(lane, bl, P, sm.layer, base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
+                __syncwarp();
+                stream_build2(lane, bl, P, sm.layer);
+                __syncwarp();
+            }
+            PROF_LAP(0);
+            if (k >= DTC_STREAM_STAGES) mbar_wait(smem_u32(&sm.done[s]), par);      // slot s is free again
+            PROF_LAP(1);
+            stream_build3(lane, bl, slot, P);
+            if (lane == 0) { slot.rmA = M.rmA; slot.rmB = M.rmB; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.full[s]));
+            M = Mn;
+            par ^= 1u;
+            PROF_LAP(2);
+        }
+        PROF_FLUSH(4, lane == 0 && s == 0);
         return;
     }
     // ---- compute warpgroups
     const int wg = warp >> 2, t = tid & 127;
-    StreamTables& tab = sm.tab[wg];
-    const int ntb = P.n_local - DTC_TILE_BITS;
+    PROF_DECL;
     for (long long k = wg; k < K; k += DTC_STREAM_WG) {
         const int s = (int)(k % DTC_STREAM_STAGES);
         const uint32_t u = (uint32_t)(k / DTC_STREAM_STAGES);
-        const u64 T = (u64)blockIdx.x + (u64)k * gridDim.x;
-        const u64 traj = T >> ntb;
-        const u64 base = stream_tile_base(T & ((1ull << ntb) - 1), P);
-        const StreamMasks M = stream_load_masks(P, masks, n_traj, traj);
-        // phase tables of this tile (overlaps the load in flight)
-        if (P.layerD >= 0) stream_setup1(t, tab, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
-        wg_barrier(wg);
-        stream_setup2(t, tab, P);
-        wg_barrier(wg);
         if (u > 0) mbar_wait(smem_u32(&sm.done[s]), (u - 1) & 1u);     // never run a full phase ahead of the stage
         mbar_wait(smem_u32(&sm.full[s]), u & 1u);
+        wg_barrier(wg);          // keep the warpgroup's warps on the same instructions (one fetch stream per warpgroup)
+        PROF_LAP(0);
         double2* tile = sm.stage[s];
-        stream_phase13<MODE>(t, tile, P.t1, P.tb, M.rmA);
-        if (MODE == 1) __syncwarp(); else wg_barrier(wg);              // mode A: a warp owns local bits 10,11 in all phases
-        stream_phase2(t, tile, tab, P, M.rmA, M.rmB);
-        if (MODE == 1) __syncwarp(); else wg_barrier(wg);
-        stream_phase13<MODE>(t, tile, P.t2, P.tb, M.rmB);
+        const StreamSlot& slot = sm.slot[s];
+        const u64 rmA = slot.rmA, rmB = slot.rmB;
+        double tt[5];
+        stream_signed_s1<MODE>(P.t1, P.tb, rmA, tt);
+        stream_phase13_call<MODE>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+        wg_barrier(wg);      // mode A would only need __syncwarp() (a warp owns local bits 10,11 in all phases); the
+                             // warpgroup barrier keeps its four warps on one instruction-fetch stream
+        PROF_LAP(1);
+        stream_phase2(t, tile, slot, P, rmA, rmB);
+        wg_barrier(wg);
+        PROF_LAP(2);
+        stream_signed_s1<MODE>(P.t2, P.tb, rmB, tt);
+        stream_phase13_call<MODE>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
         mbar_arrive(smem_u32(&sm.done[s]));
+        PROF_LAP(3);
     }
+    PROF_FLUSH(8, t == 0 && wg == 0);
+    PROF_FLUSH(12, t == 0 && wg == 1);
 }
 
 // ---- generic engine
@@ -839,6 +917,18 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     CUDA_TRY(cudaGetLastError());
     return DTC_OK;
 }
+
+#ifdef DTC_STREAM_TIMING
+/* tuning builds only: out[16] = cycles summed over CTAs -- TMA driver {wait done, wait store read, issue, drain},
+ * table builder {build1+2, wait done, build3, -}, compute warpgroup 0 and 1 {wait full, phase 1, phase 2, phase 3}; resets. */
+int dtc_debug_stream_timing(unsigned long long* out) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out, g_stream_prof, sizeof(unsigned long long) * 16));
+    unsigned long long z[16] = {0};
+    CUDA_TRY(cudaMemcpyToSymbol(g_stream_prof, z, sizeof(z)));
+    return DTC_OK;
+}
+#endif
 
 int dtc_set_stream_engine(int enable) {
     g_stream_override = enable < 0 ? -1 : (enable != 0);

@@ -57,10 +57,10 @@ static void emu_tile_pass(double2* state, const DtcTilePass& P, const DtcLayer* 
 
 
 // k_tile_stream: the TMA load / store are emulated by a gather / scatter of the tile into a dense stage
-// buffer; the two warpgroup barriers of the table setup and the phase boundaries are loop boundaries.
+// buffer; the __syncwarp()s of the table-builder warp and the phase boundaries are loop boundaries.
 template <int MODE>
 static void emu_stream_pass(double2* state, const DtcStreamPass& P, const DtcLayer* layers, const u64* masks,
-                            long long n_traj, u64 rank_bits, u64 T, std::vector<double2>& stage, StreamTables& tab) {
+                            long long n_traj, u64 rank_bits, u64 T, std::vector<double2>& stage, StreamSlot& tab, StreamBuild& bl) {
     const int ntb = P.n_local - DTC_TILE_BITS;
     const u64 traj = T >> ntb, tit = T & ((1ull << ntb) - 1);
     double2* st = state + (traj << P.n_local);
@@ -73,10 +73,13 @@ static void emu_stream_pass(double2* state, const DtcStreamPass& P, const DtcLay
     };
     for (int l = 0; l < DTC_TILE; ++l) stage[l] = st[gidx(l)];
     const StreamMasks M = stream_load_masks(P, masks, n_traj, traj);
-    if (P.layerD >= 0)
-        for (int t = 0; t < 128; ++t)
-            stream_setup1(t, tab, P, layers[P.layerD], base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
-    for (int t = 0; t < 128; ++t) stream_setup2(t, tab, P);
+    // table-builder warp: three steps separated by __syncwarp()
+    if (P.layerD >= 0) {
+        const DtcLayer& L = layers[P.layerD];
+        for (int lane = 0; lane < 32; ++lane) stream_build1(lane, bl, P, L, base | (rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
+        for (int lane = 0; lane < 32; ++lane) stream_build2(lane, bl, P, L);
+    }
+    for (int lane = 0; lane < 32; ++lane) stream_build3(lane, bl, tab, P);
     for (int t = 0; t < 128; ++t) stream_phase13<MODE>(t, stage.data(), P.t1, P.tb, M.rmA);
     for (int t = 0; t < 128; ++t) stream_phase2(t, stage.data(), tab, P, M.rmA, M.rmB);
     for (int t = 0; t < 128; ++t) stream_phase13<MODE>(t, stage.data(), P.t2, P.tb, M.rmB);
@@ -125,15 +128,16 @@ extern "C" int emu_run(int n_qubits, int n_layers, int64_t n_events, const int32
         std::vector<double2> regs((size_t)DTC_THREADS * DTC_NREG);
         const u64 grid = (u64)n_traj << (n_local - DTC_TILE_BITS);
         std::vector<double2> stage(DTC_TILE);
-        StreamTables* tab = new StreamTables();
+        StreamSlot* tab = new StreamSlot();
+        StreamBuild* bl = new StreamBuild();
         for (size_t ip = 0; ip < P.passes.size(); ++ip) {
             const DtcTilePass& T = P.passes[ip];
             const DtcStreamPass& S = P.spasses[ip];
             if (use_stream && S.mode) {
                 ++n_stream;
                 for (u64 b = 0; b < grid; ++b) {
-                    if (S.mode == 1) emu_stream_pass<1>(st, S, P.layers.data(), masks.data(), n_traj, rank_bits, b, stage, *tab);
-                    else emu_stream_pass<2>(st, S, P.layers.data(), masks.data(), n_traj, rank_bits, b, stage, *tab);
+                    if (S.mode == 1) emu_stream_pass<1>(st, S, P.layers.data(), masks.data(), n_traj, rank_bits, b, stage, *tab, *bl);
+                    else emu_stream_pass<2>(st, S, P.layers.data(), masks.data(), n_traj, rank_bits, b, stage, *tab, *bl);
                 }
                 continue;
             }
@@ -145,6 +149,7 @@ extern "C" int emu_run(int n_qubits, int n_layers, int64_t n_events, const int32
         }
         delete sm;
         delete tab;
+        delete bl;
         if (use_stream) *n_passes = n_stream;      // callers of engine 3 want to know how many passes streamed
     } else {
         for (const DtcGenericStep& g : P.gsteps) {
