@@ -103,6 +103,18 @@ int dtc_program_num_stream_passes(const dtc_program *p, int *n_passes);
 int dtc_program_set_profiling(dtc_program *p, int enable);
 int dtc_program_pass_time(dtc_program *p, float *ms, int *n_launches);
 
+/* Read-out of a factorised circuit (the Hadamard-test ancilla kept out of the register; replaces the measure
+ * sampling input of AerSimulator.run(), fast.py:211).  set_readout() (once, after finalize): the indices of the
+ * "small" events in the event list, the internal bit indices of the register qubits whose reduced density
+ * matrix is read back (<= 2), of the eliminated qubits, and of the measured qubits (1..3, all inside those).
+ * readout(): rdm = device output of dtc_rdm on reg_bits for the same n_traj; workspace = the one dtc_program_run
+ * used (sign masks, frames); probs[n_traj][2^m] (device, double), bit i of the column = i-th measured bit. */
+int dtc_program_set_readout(dtc_program *p, int64_t n_small, const int64_t *small_events, int n_reg,
+                            const int32_t *reg_bits, int n_elim, const int32_t *elim_bits, int m,
+                            const int32_t *measure_bits);
+int dtc_program_readout(const dtc_program *p, const void *rdm, void *workspace, int64_t n_traj, double *probs,
+                        void *stream);
+
 /* ---- state utilities ---------------------------------------------------------------------- */
 /* In-place psi' -> psi_true for each trajectory (used for amplitude-level parity / save_statevector). */
 int dtc_materialize(void *state, int n_local, int64_t n_traj, const uint64_t *fx, const uint64_t *fz,

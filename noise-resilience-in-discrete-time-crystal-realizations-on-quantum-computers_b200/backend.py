@@ -20,7 +20,7 @@ import time
 
 import numpy as np
 
-from . import capi, readout
+from . import capi
 from .ir import as_circuit
 from .noise import as_noise_model
 from .plan import compile_circuit
@@ -115,11 +115,11 @@ class TrajectoryBatch:
         torch = self.ctx.torch
         if prog.small is None:
             return self.probs([q for q, _ in prog.measures])
-        rdm = (self.rdm(prog.small["reg_bits"]) if rdm is None else rdm).cpu().numpy()
-        masks = self.masks_host(prog.small["first_layer"])
-        fx, _, _ = self.frames_host()
-        pr = readout.simulate_small(prog, rdm, masks, fx, first_mask_layer=prog.small["first_layer"])
-        return torch.from_numpy(np.ascontiguousarray(pr)).to(self.ctx.device)
+        if rdm is None:
+            rdm = self.rdm(prog.small["reg_bits"])
+        out = self.ctx.empty(self.n_traj << len(prog.measures), torch.float64)
+        self.handle.readout(rdm.data_ptr(), self.ws.data_ptr(), self.n_traj, out.data_ptr(), self.ctx.stream)
+        return out.view(self.n_traj, 1 << len(prog.measures))
 
     def expect_z(self, apply_frame=True):
         torch = self.ctx.torch

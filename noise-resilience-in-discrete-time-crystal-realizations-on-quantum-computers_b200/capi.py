@@ -32,6 +32,9 @@ _SIGS = {
     "dtc_program_run": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_u64, c_u64, c_u64, c_vp, ctypes.c_size_t, c_vp]),
     "dtc_program_frames": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
                                           ctypes.POINTER(c_vp)]),
+    "dtc_program_set_readout": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, c_i32p, ctypes.c_int,
+                                               c_i32p, ctypes.c_int, c_i32p]),
+    "dtc_program_readout": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "dtc_set_stream_engine": (ctypes.c_int, [ctypes.c_int]),
     "dtc_program_num_stream_passes": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
@@ -117,6 +120,15 @@ class ProgramHandle:
                                              float(prog.global_phase)))
             check(lib.dtc_program_set_exec_layers(self._h, int(prog.n_exec_layers)))
             check(lib.dtc_program_finalize(self._h, int(device), int(engine), int(self.n_local)))
+            small = getattr(prog, "small", None)
+            if small is not None:
+                idx = np.ascontiguousarray(small["events"], dtype=np.int64)
+                rb, rbp = i32(small["reg_bits"] if small["reg_bits"] else [0])
+                eb, ebp = i32(small["elim_bits"])
+                mb, mbp = i32([b for b, _c in prog.measures])
+                check(lib.dtc_program_set_readout(self._h, len(idx), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                                  len(small["reg_bits"]), rbp, len(small["elim_bits"]), ebp,
+                                                  len(prog.measures), mbp))
         except Exception:
             self.close()
             raise
@@ -143,6 +155,9 @@ class ProgramHandle:
         check(load().dtc_program_run(self._h, state_ptr, int(n_traj), int(traj_offset),
                                      int(seed) & 0xFFFFFFFFFFFFFFFF, int(init_index), int(rank_bits),
                                      ws_ptr, ws_bytes, stream))
+
+    def readout(self, rdm_ptr, ws_ptr, n_traj, probs_ptr, stream):
+        check(load().dtc_program_readout(self._h, rdm_ptr, ws_ptr, int(n_traj), probs_ptr, stream))
 
     def set_profiling(self, enable=True):
         check(load().dtc_program_set_profiling(self._h, int(bool(enable))))

@@ -17,6 +17,7 @@
 
 #include "../../include/dtcsim.h"
 #include "dtc_core.hpp"
+#include "dtc_readout.cuh"
 
 // ------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -32,10 +33,32 @@ static int fail(int code, const std::string& msg) {
             return fail(DTC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
     } while (0)
 
+// Table memory of a program comes from the device's stream-ordered pool (kept warm: release threshold = max), because
+// cudaFree costs tens of milliseconds on a device whose address space holds multi-GiB state buffers and run()
+// creates and destroys one program per circuit.
+static cudaError_t table_alloc(void** ptr, size_t bytes, int device) {
+    static bool tuned[16] = {false};
+    if (device >= 0 && device < 16 && !tuned[device]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        tuned[device] = true;
+    }
+    return cudaMallocAsync(ptr, bytes, 0);
+}
+static void table_free(void* ptr) {
+    if (ptr) cudaFreeAsync(ptr, 0);
+}
+
 struct dtc_program {
     DtcProgramHost h;
     DtcEvent* d_events = nullptr;
     DtcLayer* d_layers = nullptr;
+    DtcSmallPlan small;
+    long long* d_small_idx = nullptr;
+    long long n_small = -1;              // -1: no read-out plan set
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0;
@@ -579,6 +602,18 @@ __global__ void k_sample_states(const double2* __restrict__ state, int n_local, 
     out[t] = idx;
 }
 
+// ---- read-out of a factorised circuit: the small events on a <= 3-qubit density matrix, one thread per trajectory
+__global__ void k_readout_small(const __grid_constant__ DtcSmallPlan S, const DtcEvent* __restrict__ ev,
+                                const long long* __restrict__ idx, long long n_small, const double2* __restrict__ rdm,
+                                const u64* __restrict__ masks, const u64* __restrict__ fx, long long n_traj,
+                                double* __restrict__ probs) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_traj) return;
+    double pr[DTC_SMALL_DIM];
+    small_readout_traj(S, ev, idx, n_small, rdm + (t << (2 * S.n_reg)), masks + t, n_traj, fx[t], pr);
+    for (int b = 0; b < (1 << S.m); ++b) probs[(t << S.m) + b] = pr[b];
+}
+
 // ---- density matrix (2n-bit vector, index = row + 2^n col)
 __global__ void k_rot_cs(double2* __restrict__ v, int nbits, int bit, double c, double s) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -731,8 +766,13 @@ int dtc_program_create(int n_qubits, int n_layers, dtc_program** out) {
 
 int dtc_program_destroy(dtc_program* p) {
     if (!p) return DTC_OK;
-    if (p->d_events) cudaFree(p->d_events);
-    if (p->d_layers) cudaFree(p->d_layers);
+    if (p->h.device >= 0) {
+        cudaSetDevice(p->h.device);
+        if (p->d_events) cudaDeviceSynchronize();      // kernels of this program may still run on the caller's stream
+    }
+    table_free(p->d_events);
+    table_free(p->d_layers);
+    table_free(p->d_small_idx);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     delete p;
@@ -782,8 +822,8 @@ int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
     }
     CUDA_TRY(cudaSetDevice(device));
     const size_t eb = p->h.events.size() * sizeof(DtcEvent), lb = p->h.layers.size() * sizeof(DtcLayer);
-    CUDA_TRY(cudaMalloc(&p->d_events, eb ? eb : 16));
-    CUDA_TRY(cudaMalloc(&p->d_layers, lb));
+    CUDA_TRY(table_alloc((void**)&p->d_events, eb ? eb : 16, device));
+    CUDA_TRY(table_alloc((void**)&p->d_layers, lb, device));
     if (eb) CUDA_TRY(cudaMemcpy(p->d_events, p->h.events.data(), eb, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(p->d_layers, p->h.layers.data(), lb, cudaMemcpyHostToDevice));
     static bool attr_set[16] = {false};
@@ -929,6 +969,47 @@ int dtc_debug_stream_timing(unsigned long long* out) {
     return DTC_OK;
 }
 #endif
+
+int dtc_program_set_readout(dtc_program* p, int64_t n_small, const int64_t* small_events, int n_reg, const int32_t* reg_bits,
+                            int n_elim, const int32_t* elim_bits, int m, const int32_t* measure_bits) {
+    if (!p || !p->h.finalized) return fail(DTC_ERR_INVALID, "program not finalized");
+    if (n_small < 0 || (n_small > 0 && !small_events) || n_reg < 0 || n_reg > 2 || n_elim < 1 || n_reg + n_elim > DTC_SMALL_MAXQ ||
+        m < 1 || m > DTC_SMALL_MAXQ || (n_reg > 0 && !reg_bits) || !elim_bits || !measure_bits)
+        return fail(DTC_ERR_INVALID, "read-out plan: at most 3 qubits (<= 2 register bits), 1..3 measured bits");
+    DtcSmallPlan S;
+    memset(&S, 0, sizeof(S));
+    S.nq = n_reg + n_elim; S.n_reg = n_reg; S.m = m;
+    for (int i = 0; i < n_reg; ++i) S.bits[i] = reg_bits[i];
+    for (int i = 0; i < n_elim; ++i) S.bits[n_reg + i] = elim_bits[i];
+    for (int i = 0; i < m; ++i) {
+        S.meas_bit[i] = measure_bits[i];
+        S.meas_pos[i] = small_pos(S, measure_bits[i]);
+        if (S.meas_pos[i] < 0) return fail(DTC_ERR_INVALID, "read-out plan: measured bit outside the small register");
+    }
+    for (int64_t e = 0; e < n_small; ++e)
+        if (small_events[e] < 0 || small_events[e] >= (int64_t)p->h.events.size())
+            return fail(DTC_ERR_INVALID, "read-out plan: event index out of range");
+    CUDA_TRY(cudaSetDevice(p->h.device));
+    table_free(p->d_small_idx);
+    p->d_small_idx = nullptr;
+    CUDA_TRY(table_alloc((void**)&p->d_small_idx, sizeof(long long) * (size_t)(n_small ? n_small : 1), p->h.device));
+    if (n_small) CUDA_TRY(cudaMemcpy(p->d_small_idx, small_events, sizeof(long long) * (size_t)n_small, cudaMemcpyHostToDevice));
+    p->small = S;
+    p->n_small = n_small;
+    return DTC_OK;
+}
+
+int dtc_program_readout(const dtc_program* p, const void* rdm, void* workspace, int64_t n_traj, double* probs, void* stream) {
+    if (!p || p->n_small < 0) return fail(DTC_ERR_INVALID, "no read-out plan set (dtc_program_set_readout)");
+    if (!rdm || !workspace || !probs || n_traj < 1) return fail(DTC_ERR_INVALID, "bad argument");
+    u64 *masks, *fx, *fz;
+    int* ph;
+    ws_pointers(p->h, workspace, n_traj, &masks, &fx, &fz, &ph);
+    k_readout_small<<<(unsigned)((n_traj + 63) / 64), 64, 0, (cudaStream_t)stream>>>(p->small, p->d_events, p->d_small_idx, p->n_small,
+                                                                                    (const double2*)rdm, masks, fx, n_traj, probs);
+    CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
 
 int dtc_set_stream_engine(int enable) {
     g_stream_override = enable < 0 ? -1 : (enable != 0);

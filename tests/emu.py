@@ -13,7 +13,7 @@ CSRC = os.path.join(os.path.dirname(HERE),
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("dtc_hd.cuh", "dtc_core.hpp", "dtc_stream.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("dtc_hd.cuh", "dtc_core.hpp", "dtc_stream.cuh", "dtc_readout.cuh")]
     if force or not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", OUT, SRC])
@@ -72,3 +72,33 @@ def schedule(prog, n_local=None, cap=4096):
     if n < 0:
         raise ValueError(err.value.decode())
     return rows[:min(n, cap)], n
+
+
+def readout_small(prog, rdm, masks, fx):
+    """csrc/dtc_readout.cuh on the CPU: rdm [T,2^k,2^k], masks [n_layers,4,T] uint64 (all layers), fx [T] -> probs [T,2^m]."""
+    ev = prog.arrays()
+    sm = prog.small
+    T = rdm.shape[0]
+    m = len(prog.measures)
+    idx = np.ascontiguousarray(sm["events"], dtype=np.int64)
+    rb = np.ascontiguousarray(sm["reg_bits"] if sm["reg_bits"] else [0], dtype=np.int32)
+    eb = np.ascontiguousarray(sm["elim_bits"], dtype=np.int32)
+    mb = np.ascontiguousarray([b for b, _c in prog.measures], dtype=np.int32)
+    rdm = np.ascontiguousarray(rdm, dtype=np.complex128)
+    masks = np.ascontiguousarray(masks, dtype=np.uint64)
+    assert masks.shape == (prog.n_layers, 4, T)
+    fx = np.ascontiguousarray(fx, dtype=np.uint64)
+    out = np.zeros((T, 1 << m))
+    err = ctypes.create_string_buffer(512)
+    rc = lib().emu_readout_small(
+        ctypes.c_int(prog.n), ctypes.c_int(prog.n_layers), ctypes.c_int64(len(ev["type"])),
+        _p(ev["type"], ctypes.c_int32), _p(ev["layer"], ctypes.c_int32), _p(ev["q0"], ctypes.c_int32),
+        _p(ev["q1"], ctypes.c_int32), _p(ev["slot"], ctypes.c_int32), _p(ev["val"], ctypes.c_double),
+        _p(ev["probs"], ctypes.c_double), ctypes.c_int64(len(idx)), _p(idx, ctypes.c_int64),
+        ctypes.c_int(len(sm["reg_bits"])), _p(rb, ctypes.c_int32), ctypes.c_int(len(eb)), _p(eb, ctypes.c_int32),
+        ctypes.c_int(m), _p(mb, ctypes.c_int32), rdm.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+        _p(masks, ctypes.c_uint64), _p(fx, ctypes.c_uint64), ctypes.c_int64(T),
+        out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), err, ctypes.c_int(512))
+    if rc != 0:
+        raise ValueError(err.value.decode())
+    return out

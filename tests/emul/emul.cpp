@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../noise-resilience-in-discrete-time-crystal-realizations-on-quantum-computers_b200/csrc/dtc_core.hpp"
+#include "../../noise-resilience-in-discrete-time-crystal-realizations-on-quantum-computers_b200/csrc/dtc_readout.cuh"
 
 template <int S2_LO>
 static void emu_tile_pass(double2* state, const DtcTilePass& P, const DtcLayer* layers, const u64* masks,
@@ -206,4 +207,36 @@ extern "C" int emu_schedule(int n_qubits, int n_layers, int64_t n_events, const 
         ++n;
     }
     return (int)P.passes.size();
+}
+
+// k_readout_small: the per-trajectory read-out function of csrc/dtc_readout.cuh on the CPU.
+// masks: [n_layers*4][n_traj] as written by frame_walk; rdm: [n_traj][2^n_reg][2^n_reg]; probs: [n_traj][2^m].
+extern "C" int emu_readout_small(int n_qubits, int n_layers, int64_t n_events, const int32_t* type, const int32_t* layer,
+                                 const int32_t* q0, const int32_t* q1, const int32_t* slot, const double* val,
+                                 const double* probs_in, int64_t n_small, const int64_t* small_events, int n_reg,
+                                 const int32_t* reg_bits, int n_elim, const int32_t* elim_bits, int m,
+                                 const int32_t* measure_bits, const double* rdm, const u64* masks, const u64* fx,
+                                 int64_t n_traj, double* probs_out, char* errbuf, int errlen) {
+    DtcProgramHost P;
+    P.n_qubits = n_qubits;
+    P.n_layers = n_layers;
+    P.n_exec_layers = n_layers;
+    P.n_local = n_qubits;
+    std::string err;
+    if (!dtc_stage_events(P, n_events, type, layer, q0, q1, slot, val, probs_in, 0.0, err) || !dtc_build_layers(P, err)) {
+        snprintf(errbuf, errlen, "%s", err.c_str());
+        return -1;
+    }
+    DtcSmallPlan S;
+    memset(&S, 0, sizeof(S));
+    S.nq = n_reg + n_elim; S.n_reg = n_reg; S.m = m;
+    for (int i = 0; i < n_reg; ++i) S.bits[i] = reg_bits[i];
+    for (int i = 0; i < n_elim; ++i) S.bits[n_reg + i] = elim_bits[i];
+    for (int i = 0; i < m; ++i) { S.meas_bit[i] = measure_bits[i]; S.meas_pos[i] = small_pos(S, measure_bits[i]); }
+    std::vector<long long> idx(small_events, small_events + n_small);
+    const double2* r = reinterpret_cast<const double2*>(rdm);
+    for (int64_t t = 0; t < n_traj; ++t)
+        small_readout_traj(S, P.events.data(), idx.data(), n_small, r + (t << (2 * n_reg)), masks + t, n_traj, fx[t],
+                           probs_out + (t << m));
+    return 0;
 }

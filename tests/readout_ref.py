@@ -13,7 +13,7 @@ import math
 
 import numpy as np
 
-from .plan import EV_D1, EV_D2, EV_D2C, EV_NOISE, EV_ROT
+from dtcsim.plan import EV_D1, EV_D2, EV_D2C, EV_NOISE, EV_ROT
 
 
 def _full_1q(U, p, nq):

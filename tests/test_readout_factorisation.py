@@ -1,4 +1,5 @@
-"""Read-out factorisation (plan.compile_circuit(optimize=True) + readout.simulate_small) on the CPU:
+"""Read-out factorisation (plan.compile_circuit(optimize=True) + the per-trajectory read-out of
+csrc/dtc_readout.cuh, executed on the CPU by tests/emul, and its numpy restatement tests/readout_ref.py):
 device part emulated (tests/emul), reduced density matrix taken with numpy, compared with the oracle's
 per-trajectory outcome probabilities of the *full* (L+1)-qubit circuit."""
 import numpy as np
@@ -8,7 +9,8 @@ import dtcsim
 import emu
 import program_interp as PI
 import refcircuits as RC
-from dtcsim import compile_circuit, readout
+import readout_ref as readout
+from dtcsim import compile_circuit
 from oracle import oracle as O
 
 
@@ -37,7 +39,10 @@ def _probs_factorised(prog, seed, trajs, engine=0):
     masks, rfx, rfz, rph = PI.frame_walk(prog, k_of, seed, trajs)
     assert np.array_equal(fx, rfx)
     rdm = _rdm(st, prog.n_main, list(prog.small["reg_bits"]))
-    return readout.simulate_small(prog, rdm, masks, fx), npass
+    ref = readout.simulate_small(prog, rdm, masks, fx)
+    dev = emu.readout_small(prog, rdm, masks, fx)          # the function the GPU kernel k_readout_small runs
+    assert np.abs(dev - ref).max() < 1e-13
+    return dev, npass
 
 
 def _probs_oracle(circ, onoise, seed, trajs):
