@@ -223,7 +223,10 @@ template <int MODE>
 __global__ void __launch_bounds__(DTC_STREAM_THREADS, 1)
 k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DtcStreamPass P,
               const DtcLayer* __restrict__ layers, const u64* __restrict__ masks, long long n_traj, u64 rank_bits,
-              long long n_tiles) {
+              long long n_tiles, u64 init_index) {
+    // init_index != DTC_INIT_KEEP: the input is not read -- every trajectory starts in the basis state init_index
+    // (DTC_INIT_ZERO: the zero vector).  Tiles without the basis amplitude are written as zeros without compute.
+    const bool gen = init_index != DTC_INIT_KEEP;
     extern __shared__ unsigned char smraw[];
     StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smraw + ((128u - (smem_u32(smraw) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -245,8 +248,10 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
     if (warp == 4 * DTC_STREAM_WG) {
         // ---- TMA driver
         if ((tid & 31) != 0) return;
-        for (long long k = 0; k < K && k < DTC_STREAM_STAGES; ++k)
-            stream_tma_load(P, &tmap, state, (u64)blockIdx.x + (u64)k * gridDim.x, smem_u32(sm.stage[k]), smem_u32(&sm.full[k]));
+        for (long long k = 0; k < K && k < DTC_STREAM_STAGES; ++k) {
+            if (gen) mbar_arrive(smem_u32(&sm.full[k]));
+            else stream_tma_load(P, &tmap, state, (u64)blockIdx.x + (u64)k * gridDim.x, smem_u32(sm.stage[k]), smem_u32(&sm.full[k]));
+        }
         int s = 0;
         uint32_t par = 0;
         PROF_DECL;
@@ -257,8 +262,9 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
             if (k + DTC_STREAM_STAGES < K) {
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has read the stage
                 PROF_LAP(1);
-                stream_tma_load(P, &tmap, state, (u64)blockIdx.x + (u64)(k + DTC_STREAM_STAGES) * gridDim.x,
-                                smem_u32(sm.stage[s]), smem_u32(&sm.full[s]));
+                if (gen) mbar_arrive(smem_u32(&sm.full[s]));
+                else stream_tma_load(P, &tmap, state, (u64)blockIdx.x + (u64)(k + DTC_STREAM_STAGES) * gridDim.x,
+                                     smem_u32(sm.stage[s]), smem_u32(&sm.full[s]));
             }
             if (++s == DTC_STREAM_STAGES) { s = 0; par ^= 1u; }
             PROF_LAP(2);
@@ -317,6 +323,25 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
         double2* tile = sm.stage[s];
         const StreamSlot& slot = sm.slot[s];
         const u64 rmA = slot.rmA, rmB = slot.rmB;
+        if (gen) {
+            const u64 T = (u64)blockIdx.x + (u64)k * gridDim.x;
+            const u64 base = stream_tile_base(T & ((1ull << ntb) - 1), P);
+#pragma unroll
+            for (int r = 0; r < DTC_NREG; ++r) tile[t + 128 * r] = make_double2(0.0, 0.0);
+            const bool has = init_index != DTC_INIT_ZERO && ((init_index ^ base) & ~P.tile_mask) == 0;
+            if (!has) {                                    // all-zero tile: nothing to compute
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(smem_u32(&sm.done[s]));
+                continue;
+            }
+            wg_barrier(wg);
+            if (t == 0) {
+                int l = 0;
+                for (int b = 0; b < DTC_TILE_BITS; ++b) l |= (int)((init_index >> P.tb[b]) & 1ull) << b;
+                tile[l] = make_double2(1.0, 0.0);
+            }
+            wg_barrier(wg);
+        }
         double tt[5];
         stream_signed_s1<MODE>(P.t1, P.tb, rmA, tt);
         stream_phase13_call<MODE>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
@@ -891,7 +916,9 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     const int fb = 128;
     k_frames<<<(unsigned)((n_traj + fb - 1) / fb), fb, 0, s>>>(p->d_events, (long long)h.events.size(), masks,
                                                               n_traj, traj_offset, seed, fx, fz, ph);
-    if (!keep) {
+    // the first pass can generate the initial state itself (no memset, no read) when it runs on k_tile_stream
+    const bool gen_first = !keep && h.engine == DTC_ENGINE_TILE && !h.spasses.empty() && h.spasses[0].mode && stream_enabled();
+    if (!keep && !gen_first) {
         const size_t sbytes = ((size_t)n_traj << h.n_local) * sizeof(double2);
         CUDA_TRY(cudaMemsetAsync(state, 0, sbytes, s));
         if (!zero)
@@ -920,10 +947,11 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
                 }
                 const unsigned sgrid = (unsigned)(grid < n_sms ? grid : n_sms);
                 const size_t ssb = sizeof(StreamSmem) + 128;
+                const u64 init = (ip == 0 && gen_first) ? (u64)init_index : (u64)DTC_INIT_KEEP;
                 if (S.mode == 1)
-                    k_tile_stream<1><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid);
+                    k_tile_stream<1><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init);
                 else
-                    k_tile_stream<2><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid);
+                    k_tile_stream<2><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init);
                 continue;
             }
             const bool hx = T.layerD >= 0 && T.nX > 0;

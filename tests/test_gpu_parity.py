@@ -379,11 +379,14 @@ def test_stream_engine_equals_register_engine(ctx, disorder, L, t, echo, pol, st
     h = capi.ProgramHandle(prog, 0)
     assert h.num_stream_passes == h.num_passes > 0
     try:
+        # init_index != 0 also checks the first pass generating the basis state itself (no memset, no read)
+        init = ((0x2A5 << (L - 10)) | 3) if L >= 13 else 0
         capi.set_stream_engine(False)
-        a = backend.evolve(ctx, prog, ntraj, 7, 99, handle=h)
+        a = backend.evolve(ctx, prog, ntraj, 7, 99, handle=h, init_index=init)
         sa, fa = a.state.clone(), a.frames_host()
         capi.set_stream_engine(True)
-        b = backend.evolve(ctx, prog, ntraj, 7, 99, handle=h)
+        garbage = ctx.empty(ntraj << prog.n_main, a.state.dtype).fill_(float("nan"))   # the input buffer is never read
+        b = backend.evolve(ctx, prog, ntraj, 7, 99, handle=h, init_index=init, state=garbage)
         sb, fb = b.state, b.frames_host()
     finally:
         capi.set_stream_engine(None)
