@@ -213,11 +213,11 @@ def run_ours(args):
         for i, (prog, h) in enumerate(zip(progs, handles)):
             for a in range(0, NT, bt):
                 nt = min(bt, NT - a)
-                batch = backend.evolve(ctx, prog, nt, a, seed + i, handle=h, state=state)
-                # read-out: reduce the register to the density matrix of site q now (the state buffer is
-                # reused by the next circuit); the tiny ancilla simulation runs on the host afterwards
-                pending.append((i, batch, batch.rdm(prog.small["reg_bits"]) if prog.small else None))
-                launches[0] += 2 + h.num_passes + 1
+                batch = backend.evolve(ctx, prog, nt, a, seed + i, handle=h, state=state, fused_rdm=True)
+                # read-out: the density matrix of site q comes out of the last pass (fused) or of a dtc_rdm reduction
+                # taken now (the state buffer is reused by the next circuit); k_readout_small finishes it below
+                pending.append((i, batch, batch.readout_rdm() if prog.small else None))
+                launches[0] += 1 + h.num_passes + (1 if batch.fused_rdm is not None else 2)
         for i, batch, rdm in pending:
             pr = batch.outcome_probs(rdm)
             ez = pr[:, 0] - pr[:, 1]
@@ -240,7 +240,7 @@ def run_ours(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches[0] = 0
-    pass_ms, pass_n = 0.0, 0
+    pass_ms, pass_n, half_passes = 0.0, 0, 0
     e0.record()
     for k in range(args.steps):
         step(1234 + k)
@@ -252,6 +252,7 @@ def run_ours(args):
             ms, n = h.pass_time()
             pass_ms += ms
             pass_n += n
+            half_passes += sum(h.last_run_flags())        # passes that only write (generated start) or only read (fused read-out)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
     if dist is not None:
@@ -279,14 +280,18 @@ def run_ours(args):
     tf = os.path.join(ROOT, "profiles", "ncu_tile_stream_traffic.json")      # from the committed ncu --set full capture
     if os.path.exists(tf):
         with open(tf) as fh:
-            traffic = float(json.load(fh)["dram_bytes_per_algorithmic_byte"]) * bytes_per_launch
+            traffic = float(json.load(fh)["dram_bytes_per_algorithmic_byte"]) * bytes_per_launch   # per full-traffic launch
     if pass_n:
         avg_ms = pass_ms / pass_n
-        ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+        # algorithmic bytes of the timed launches: a full pass reads and writes the batch once; the first pass of a
+        # circuit only writes it (generated start) and a fused last pass only reads it
+        alg_bytes = bytes_per_launch * (pass_n - 0.5 * half_passes)
+        ach = alg_bytes / (pass_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "kernel": "k_tile_stream" if 2 * n_stream >= n_pass_all else "k_tile_pass",
                 "stream_passes": n_stream, "passes": n_pass_all, "avg_launch_ms": avg_ms, "launches_timed": pass_n,
-                "bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_launch, "half_traffic_launches": half_passes,
+                "algorithmic_bytes_timed": alg_bytes, "peak_source": peak_src,
                 "register_qubits": nmax,
                 "periods_frac_n21_model": (value / world) * (2 * 16 * (1 << (L + 1))) / (peak * 1e9),
                 "periods_frac_actual_register": (value / world) * (2 * 16 * (1 << nmax)) / (peak * 1e9)}

@@ -101,6 +101,10 @@ int dtc_program_num_stream_passes(const dtc_program *p, int *n_passes);
  * CUDA events on the launching stream; dtc_program_pass_time() waits for the last run and returns the
  * elapsed milliseconds and the number of state-sweep launches in that run. */
 int dtc_program_set_profiling(dtc_program *p, int enable);
+/* Traffic accounting of the last dtc_program_run: *gen_first = 1 if its first pass generated the initial state
+ * (wrote the batch, read nothing), *fused_rdm = 1 if its last pass reduced the read-out density matrix instead
+ * of storing (read the batch, wrote nothing). */
+int dtc_program_last_run_flags(const dtc_program *p, int *gen_first, int *fused_rdm);
 int dtc_program_pass_time(dtc_program *p, float *ms, int *n_launches);
 
 /* Read-out of a factorised circuit (the Hadamard-test ancilla kept out of the register; replaces the measure
@@ -114,6 +118,13 @@ int dtc_program_set_readout(dtc_program *p, int64_t n_small, const int64_t *smal
                             const int32_t *measure_bits);
 int dtc_program_readout(const dtc_program *p, const void *rdm, void *workspace, int64_t n_traj, double *probs,
                         void *stream);
+/* Fused read-out: when enabled and the program's last pass runs on k_tile_stream with the (single) read-out qubit
+ * inside its tile, that pass accumulates the qubit's reduced density matrix into the workspace instead of storing
+ * the state (one read + one write of the batch saved per circuit; the state buffer then holds psi' BEFORE the last
+ * pass and must not be used).  *active_or_null tells whether the next dtc_program_run will fuse;
+ * dtc_program_fused_rdm() returns the device pointer [n_traj][2][2] complex128 of the last run (NULL if not fused). */
+int dtc_program_set_fused_rdm(dtc_program *p, int enable, int *active_or_null);
+int dtc_program_fused_rdm(const dtc_program *p, void *workspace, int64_t n_traj, void **rdm);
 
 /* ---- state utilities ---------------------------------------------------------------------- */
 /* In-place psi' -> psi_true for each trajectory (used for amplitude-level parity / save_statevector). */

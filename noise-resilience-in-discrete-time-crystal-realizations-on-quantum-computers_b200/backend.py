@@ -79,6 +79,7 @@ class TrajectoryBatch:
         self.n_traj, self.traj_offset = n_traj, traj_offset
         self.n = handle.n_local
         self.fx, self.fz, self.ph = handle.frames(ws.data_ptr(), n_traj)
+        self.fused_rdm = None           # set by evolve(fused_rdm=True): [n_traj, 2, 2] view into the workspace
 
     def probs(self, qubits, apply_frame=True):
         """[n_traj, 2^k] outcome probabilities (torch float64 on device)."""
@@ -100,6 +101,13 @@ class TrajectoryBatch:
                                        self.ctx.stream))
         return out.view(self.n_traj, 1 << k, 1 << k)
 
+    def readout_rdm(self):
+        """Reduced density matrix the read-out of a factorised circuit starts from: the fused one of the last pass
+        if evolve() ran with fused_rdm=True, else a dtc_rdm reduction of the state."""
+        if self.fused_rdm is not None:
+            return self.fused_rdm
+        return self.rdm(self.handle.prog.small["reg_bits"])
+
     def masks_host(self, first_layer=0):
         """Sign masks [n_layers - first_layer, 4, n_traj] (uint64) written by the device frame walk."""
         torch = self.ctx.torch
@@ -116,7 +124,7 @@ class TrajectoryBatch:
         if prog.small is None:
             return self.probs([q for q, _ in prog.measures])
         if rdm is None:
-            rdm = self.rdm(prog.small["reg_bits"])
+            rdm = self.readout_rdm()
         out = self.ctx.empty(self.n_traj << len(prog.measures), torch.float64)
         self.handle.readout(rdm.data_ptr(), self.ws.data_ptr(), self.n_traj, out.data_ptr(), self.ctx.stream)
         return out.view(self.n_traj, 1 << len(prog.measures))
@@ -158,8 +166,11 @@ class TrajectoryBatch:
 
 
 def evolve(ctx, prog, n_traj, traj_offset=0, seed=0, engine=capi.ENGINE_AUTO, handle=None, state=None,
-           init_index=0):
-    """Run the compiled program for a batch of trajectories; returns a TrajectoryBatch."""
+           init_index=0, fused_rdm=False):
+    """Run the compiled program for a batch of trajectories; returns a TrajectoryBatch.
+
+    fused_rdm=True (read-out only: the caller will not look at the state): where the library can, the last pass
+    reduces the read-out qubit's density matrix instead of storing the state (batch.fused_rdm)."""
     torch = ctx.torch
     own = handle is None
     if own:
@@ -170,8 +181,13 @@ def evolve(ctx, prog, n_traj, traj_offset=0, seed=0, engine=capi.ENGINE_AUTO, ha
         state = ctx.empty(need, torch.complex128)
     wsb = handle.workspace_bytes(n_traj)
     ws = ctx.empty(wsb, torch.uint8)
+    fused = handle.set_fused_rdm(bool(fused_rdm) and getattr(prog, "small", None) is not None)
     handle.run(state.data_ptr(), n_traj, traj_offset, seed, ws.data_ptr(), wsb, ctx.stream, init_index=init_index)
-    return TrajectoryBatch(ctx, handle, state[:need], ws, n_traj, traj_offset)
+    batch = TrajectoryBatch(ctx, handle, state[:need], ws, n_traj, traj_offset)
+    if fused:
+        off = handle.fused_rdm_ptr(ws.data_ptr(), n_traj) - ws.data_ptr()
+        batch.fused_rdm = ws[off:off + 64 * n_traj].view(torch.complex128).view(n_traj, 2, 2)
+    return batch
 
 
 def sample_rows(ctx, probs, n_samples, seed, traj_offset):
@@ -393,7 +409,7 @@ class DTCSimulator:
             psum = None
             for a in range(0, shots, bt):
                 nt = min(bt, shots - a)
-                batch = evolve(ctx, prog0, nt, a, seed, handle=handle, state=state)
+                batch = evolve(ctx, prog0, nt, a, seed, handle=handle, state=state, fused_rdm=k <= MAX_PROB_QUBITS)
                 if k <= MAX_PROB_QUBITS:
                     probs = batch.outcome_probs()
                     cols = sample_rows(ctx, probs, 1, seed, a).cpu().numpy()[:, 0]

@@ -35,8 +35,11 @@ _SIGS = {
     "dtc_program_set_readout": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, c_i32p, ctypes.c_int,
                                                c_i32p, ctypes.c_int, c_i32p]),
     "dtc_program_readout": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "dtc_program_set_fused_rdm": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "dtc_program_fused_rdm": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_vp)]),
     "dtc_set_stream_engine": (ctypes.c_int, [ctypes.c_int]),
     "dtc_program_num_stream_passes": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int)]),
+    "dtc_program_last_run_flags": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "dtc_program_pass_time": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "dtc_materialize": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -156,6 +159,18 @@ class ProgramHandle:
                                      int(seed) & 0xFFFFFFFFFFFFFFFF, int(init_index), int(rank_bits),
                                      ws_ptr, ws_bytes, stream))
 
+    def set_fused_rdm(self, enable=True):
+        """Let the last pass reduce the read-out qubit's density matrix instead of storing the state (factorised
+        circuits whose last pass runs on k_tile_stream).  Returns True if the next run() will do so."""
+        active = ctypes.c_int(0)
+        check(load().dtc_program_set_fused_rdm(self._h, int(bool(enable)), ctypes.byref(active)))
+        return bool(active.value)
+
+    def fused_rdm_ptr(self, ws_ptr, n_traj):
+        ptr = c_vp()
+        check(load().dtc_program_fused_rdm(self._h, ws_ptr, int(n_traj), ctypes.byref(ptr)))
+        return ptr.value
+
     def readout(self, rdm_ptr, ws_ptr, n_traj, probs_ptr, stream):
         check(load().dtc_program_readout(self._h, rdm_ptr, ws_ptr, int(n_traj), probs_ptr, stream))
 
@@ -167,6 +182,12 @@ class ProgramHandle:
         ms, n = ctypes.c_float(0), ctypes.c_int(0)
         check(load().dtc_program_pass_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def last_run_flags(self):
+        """(first pass generated the state, last pass fused the read-out) of the last run()."""
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        check(load().dtc_program_last_run_flags(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return bool(a.value), bool(b.value)
 
     def frames(self, ws_ptr, n_traj):
         fx, fz, ph = c_vp(), c_vp(), c_vp()

@@ -479,5 +479,14 @@ static inline void dtc_schedule_generic(DtcProgramHost& P) {
 static inline size_t dtc_workspace_bytes(const DtcProgramHost& P, int64_t n_traj) {
     size_t b = (size_t)(P.n_layers * 4 + 2) * (size_t)n_traj * sizeof(u64);
     b += (size_t)n_traj * sizeof(int);
+    b = (b + 255) & ~(size_t)255;
+    b += (size_t)n_traj * 4 * sizeof(double2);       // fused read-out: reduced density matrix of one qubit per trajectory
+    return (b + 255) & ~(size_t)255;
+}
+
+// offset of the fused-read-out density matrices inside the workspace
+static inline size_t dtc_workspace_rdm_offset(const DtcProgramHost& P, int64_t n_traj) {
+    size_t b = (size_t)(P.n_layers * 4 + 2) * (size_t)n_traj * sizeof(u64);
+    b += (size_t)n_traj * sizeof(int);
     return (b + 255) & ~(size_t)255;
 }

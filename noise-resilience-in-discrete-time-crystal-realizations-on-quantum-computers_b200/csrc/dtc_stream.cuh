@@ -263,6 +263,22 @@ DTC_HD void stream_build3(int lane, const StreamBuild& bl, StreamSlot& slot, con
     }
 }
 
+// ---- fused read-out (last pass of a factorised circuit): after phase 3 the tile is in the stage buffer; each thread
+// takes 16 pairs (l, l | 1 << lb) of the local bit lb and accumulates rho00, rho11, rho01 of psi'.  The stage is not stored.
+DTC_HD void stream_rdm_pairs(int t, const double2* tile, int lb, double acc[4]) {
+    const int low = (1 << lb) - 1;
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+        const int pi = t + 128 * j;                                  // pair index 0..2047, consecutive lanes adjacent
+        const int l0 = ((pi & ~low) << 1) | (pi & low);
+        const double2 a = tile[l0], b = tile[l0 | (1 << lb)];
+        acc[0] += a.x * a.x + a.y * a.y;
+        acc[1] += b.x * b.x + b.y * b.y;
+        acc[2] += a.x * b.x + a.y * b.y;                             // a conj(b)
+        acc[3] += a.y * b.x - a.x * b.y;
+    }
+}
+
 struct StreamMasks {
     u64 rmA, rmB, m1a, m1b, m2;
 };

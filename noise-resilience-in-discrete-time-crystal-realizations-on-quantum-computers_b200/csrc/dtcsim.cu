@@ -59,9 +59,12 @@ struct dtc_program {
     DtcSmallPlan small;
     long long* d_small_idx = nullptr;
     long long n_small = -1;              // -1: no read-out plan set
+    bool fuse_rdm = false;               // dtc_program_set_fused_rdm
+    int fused_local_bit = -1;            // tile-local position of the read-out qubit in the last pass (-1: not fusable)
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0;
+    bool last_gen_first = false, last_fused = false;     // what the last dtc_program_run did (traffic accounting)
 };
 
 // ------------------------------------------------------------------------------------ kernels
@@ -223,7 +226,9 @@ template <int MODE>
 __global__ void __launch_bounds__(DTC_STREAM_THREADS, 1)
 k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DtcStreamPass P,
               const DtcLayer* __restrict__ layers, const u64* __restrict__ masks, long long n_traj, u64 rank_bits,
-              long long n_tiles, u64 init_index) {
+              long long n_tiles, u64 init_index, double2* __restrict__ rdm_out, int rdm_local_bit) {
+    // rdm_out != nullptr (last pass of a factorised circuit): the tile is not stored; the reduced density matrix of the
+    // tile-local bit rdm_local_bit of psi' is accumulated into rdm_out[trajectory][2][2] instead.
     // init_index != DTC_INIT_KEEP: the input is not read -- every trajectory starts in the basis state init_index
     // (DTC_INIT_ZERO: the zero vector).  Tiles without the basis amplitude are written as zeros without compute.
     const bool gen = init_index != DTC_INIT_KEEP;
@@ -258,9 +263,9 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
         for (long long k = 0; k < K; ++k) {
             mbar_wait(smem_u32(&sm.done[s]), par);
             PROF_LAP(0);
-            stream_tma_store(P, &tmap, state, (u64)blockIdx.x + (u64)k * gridDim.x, smem_u32(sm.stage[s]));
+            if (!rdm_out) stream_tma_store(P, &tmap, state, (u64)blockIdx.x + (u64)k * gridDim.x, smem_u32(sm.stage[s]));
             if (k + DTC_STREAM_STAGES < K) {
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has read the stage
+                if (!rdm_out) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has read the stage
                 PROF_LAP(1);
                 if (gen) mbar_arrive(smem_u32(&sm.full[s]));
                 else stream_tma_load(P, &tmap, state, (u64)blockIdx.x + (u64)(k + DTC_STREAM_STAGES) * gridDim.x,
@@ -353,6 +358,24 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
         PROF_LAP(2);
         stream_signed_s1<MODE>(P.t2, P.tb, rmB, tt);
         stream_phase13_call<MODE>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+        if (rdm_out) {
+            wg_barrier(wg);
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            stream_rdm_pairs(t, tile, rdm_local_bit, acc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+            if ((t & 31) == 0) {
+                const u64 T = (u64)blockIdx.x + (u64)k * gridDim.x;
+                double* dst = reinterpret_cast<double*>(rdm_out + ((T >> ntb) << 2));
+                atomicAdd(dst + 0, acc[0]);                 // rho[0][0]
+                atomicAdd(dst + 2, acc[2]);                 // rho[0][1] = sum a conj(b)
+                atomicAdd(dst + 3, acc[3]);
+                atomicAdd(dst + 4, acc[2]);                 // rho[1][0] = conj
+                atomicAdd(dst + 5, -acc[3]);
+                atomicAdd(dst + 6, acc[1]);                 // rho[1][1]
+            }
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
         mbar_arrive(smem_u32(&sm.done[s]));
         PROF_LAP(3);
@@ -916,6 +939,7 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     const int fb = 128;
     k_frames<<<(unsigned)((n_traj + fb - 1) / fb), fb, 0, s>>>(p->d_events, (long long)h.events.size(), masks,
                                                               n_traj, traj_offset, seed, fx, fz, ph);
+    const bool fused = p->fuse_rdm && p->fused_local_bit >= 0 && stream_enabled();
     // the first pass can generate the initial state itself (no memset, no read) when it runs on k_tile_stream
     const bool gen_first = !keep && h.engine == DTC_ENGINE_TILE && !h.spasses.empty() && h.spasses[0].mode && stream_enabled();
     if (!keep && !gen_first) {
@@ -924,6 +948,8 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
         if (!zero)
             k_init_basis<<<(unsigned)((n_traj + 127) / 128), 128, 0, s>>>((double2*)state, h.n_local, n_traj, init_index);
     }
+    p->last_gen_first = gen_first;
+    p->last_fused = fused && h.engine == DTC_ENGINE_TILE;
     if (p->profiling) CUDA_TRY(cudaEventRecord(p->ev0, s));
     p->last_launches = (h.engine == DTC_ENGINE_TILE) ? (int)h.passes.size() : (int)h.gsteps.size();
     if (h.engine == DTC_ENGINE_TILE) {
@@ -948,10 +974,17 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
                 const unsigned sgrid = (unsigned)(grid < n_sms ? grid : n_sms);
                 const size_t ssb = sizeof(StreamSmem) + 128;
                 const u64 init = (ip == 0 && gen_first) ? (u64)init_index : (u64)DTC_INIT_KEEP;
+                double2* rdm_out = nullptr;
+                if (fused && ip + 1 == h.passes.size()) {
+                    rdm_out = (double2*)((char*)workspace + dtc_workspace_rdm_offset(h, n_traj));
+                    CUDA_TRY(cudaMemsetAsync(rdm_out, 0, sizeof(double2) * 4 * (size_t)n_traj, s));
+                }
                 if (S.mode == 1)
-                    k_tile_stream<1><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init);
+                    k_tile_stream<1><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
+                                                                           rdm_out, p->fused_local_bit);
                 else
-                    k_tile_stream<2><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init);
+                    k_tile_stream<2><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
+                                                                           rdm_out, p->fused_local_bit);
                 continue;
             }
             const bool hx = T.layerD >= 0 && T.nX > 0;
@@ -1027,6 +1060,27 @@ int dtc_program_set_readout(dtc_program* p, int64_t n_small, const int64_t* smal
     return DTC_OK;
 }
 
+int dtc_program_set_fused_rdm(dtc_program* p, int enable, int* active) {
+    if (!p || !p->h.finalized) return fail(DTC_ERR_INVALID, "program not finalized");
+    p->fuse_rdm = false;
+    p->fused_local_bit = -1;
+    if (enable && p->n_small >= 0 && p->small.n_reg == 1 && p->h.engine == DTC_ENGINE_TILE && !p->h.spasses.empty()) {
+        const DtcStreamPass& S = p->h.spasses.back();
+        if (S.mode)
+            for (int l = 0; l < DTC_TILE_BITS; ++l)
+                if (S.tb[l] == p->small.bits[0]) p->fused_local_bit = l;
+        p->fuse_rdm = p->fused_local_bit >= 0;
+    }
+    if (active) *active = p->fuse_rdm && stream_enabled();
+    return DTC_OK;
+}
+
+int dtc_program_fused_rdm(const dtc_program* p, void* workspace, int64_t n_traj, void** rdm) {
+    if (!p || !workspace || !rdm) return fail(DTC_ERR_INVALID, "bad argument");
+    *rdm = (p->fuse_rdm && stream_enabled()) ? (void*)((char*)workspace + dtc_workspace_rdm_offset(p->h, n_traj)) : nullptr;
+    return DTC_OK;
+}
+
 int dtc_program_readout(const dtc_program* p, const void* rdm, void* workspace, int64_t n_traj, double* probs, void* stream) {
     if (!p || p->n_small < 0) return fail(DTC_ERR_INVALID, "no read-out plan set (dtc_program_set_readout)");
     if (!rdm || !workspace || !probs || n_traj < 1) return fail(DTC_ERR_INVALID, "bad argument");
@@ -1049,6 +1103,13 @@ int dtc_program_num_stream_passes(const dtc_program* p, int* n_passes) {
     int n = 0;
     for (const DtcStreamPass& S : p->h.spasses) n += S.mode != 0;
     *n_passes = n;
+    return DTC_OK;
+}
+
+int dtc_program_last_run_flags(const dtc_program* p, int* gen_first, int* fused_rdm) {
+    if (!p || !gen_first || !fused_rdm) return fail(DTC_ERR_INVALID, "bad argument");
+    *gen_first = p->last_gen_first ? 1 : 0;
+    *fused_rdm = p->last_fused ? 1 : 0;
     return DTC_OK;
 }
 

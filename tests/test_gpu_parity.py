@@ -408,3 +408,25 @@ def test_stream_engine_vs_oracle_full_register(ctx, disorder):
     psi, _ = _evolve_true(ctx, prog, 4, 11, 5, engine=2)
     ref = O.run_trajectories(oc, na, O.PauliNoise.depolarizing(0.05), 5, np.arange(11, 15))
     assert np.abs(psi - ref).max() < AMP_TOL
+
+
+@pytest.mark.parametrize("L,t,echo,ntraj", [(12, 2, True, 40), (16, 3, False, 9), (20, 2, True, 3)])
+def test_fused_readout_rdm_equals_rdm_kernel(ctx, disorder, L, t, echo, ntraj):
+    """Last pass reducing the read-out qubit's density matrix (state not stored) == dtc_rdm on the stored state,
+    and the outcome probabilities built from either agree."""
+    from dtcsim import backend, capi
+    hs, phis = disorder[20][0][3][:L], disorder[20][1][3][:L - 1]
+    circ = RC.transpiled(RC.qc_body("vacuum", L, 0.97, hs, phis, t, L // 2, echo, "x"))
+    prog = compile_circuit(circ, RC.noise_model(0.05), optimize=True)
+    h = capi.ProgramHandle(prog, 0)
+    a = backend.evolve(ctx, prog, ntraj, 3, 17, handle=h)
+    assert a.fused_rdm is None
+    rdm_ref = a.rdm(prog.small["reg_bits"]).clone()
+    pr_ref = a.outcome_probs().clone()
+    b = backend.evolve(ctx, prog, ntraj, 3, 17, handle=h, fused_rdm=True)
+    if h.num_stream_passes == h.num_passes:
+        assert b.fused_rdm is not None          # every pass streams, the read-out qubit sits in the last tile
+    if b.fused_rdm is not None:
+        assert float((b.fused_rdm - rdm_ref).abs().max()) < 1e-12
+    assert float((b.outcome_probs() - pr_ref).abs().max()) < 1e-12
+    assert abs(float(pr_ref.sum()) / ntraj - 1.0) < 1e-10
