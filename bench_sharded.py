@@ -81,6 +81,7 @@ def main():
     sharded.ShardedStatevector(L, rank, world, eng, all_reduce=allred).run(
         build_circuit(dtcsim, L, 0.97, hs, phis, 1, True))
     eng.passes = 0
+    eng.fast_exchanges = 0
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     res = sv.run(circ)
@@ -94,7 +95,8 @@ def main():
                config={"workload": f"C5: L={L} statevector sharded on top {g} qubits, {args.periods} periods forward + inverse, complex128",
                        "n_local": n_local, "state_bytes_total": 16 << L},
                seconds=dt, norm=res["norm"], echo_max_dev=float(np.abs(ez - 1).max()),
-               segments=sv.stats["segments"], exchanges=sv.stats["exchanges"], state_sweeps=eng.passes,
+               segments=sv.stats["segments"], exchanges=sv.stats["exchanges"], exchanges_without_pack=eng.fast_exchanges,
+               state_sweeps=eng.passes,
                exchange_bytes_per_rank=sv.stats["exchange_bytes_per_rank"],
                nvlink_gbs_per_rank_lower_bound=sv.stats["exchange_bytes_per_rank"] / dt / 1e9,
                hbm_algorithmic_gbs_per_rank=eng.passes * 2 * (16 << n_local) / dt / 1e9)

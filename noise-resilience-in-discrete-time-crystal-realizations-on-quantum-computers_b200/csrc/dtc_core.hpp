@@ -383,6 +383,13 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
         const DtcLayer& L = P.layers[j];
         const u64 rem = L.rot_any & ~done;
         const u64 next = (j + 1 < M) ? P.layers[j + 1].rot_any : 0ull;
+        // a layer with nothing left to do (no rotation outstanding, identity diagonal) needs no sweep of its own:
+        // its successor's rotations ride with that layer's diagonal instead (segments of a sharded run start so)
+        if (!rem && j + 1 < M && L.n_terms == 0 && !L.d1_any[0] && !L.d1_any[1] && L.cr == 1.0 && L.ci == 0.0) {
+            ++j;
+            done = 0;
+            continue;
+        }
         // groups that still have work in this layer; the one kept for last gets D_j + look-ahead
         int pick = -1, n_cand = 0, best_keep = -1;
         for (size_t k = 0; k < groups.size(); ++k) {
