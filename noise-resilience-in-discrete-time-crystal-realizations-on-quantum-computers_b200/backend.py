@@ -342,9 +342,26 @@ class DTCSimulator:
             seed = int.from_bytes(os.urandom(6), "little")
         nm = as_noise_model(self.noise_model if noise_model is None else noise_model)
         method = self.method if method is None else method
-        exps = []
-        for i, c in enumerate(circ_list):
-            exps.append(self._run_one(as_circuit(c), shots, int(seed) + i, nm, method, getattr(c, "name", None)))
+        # A list of circuits is pipelined: circuit i+1 is compiled and enqueued while the GPU still works
+        # on circuit i, whose results are then fetched on a side stream.  Counts are identical to one-by-one calls.
+        exps = [None] * len(circ_list)
+        pending = None
+        handles = []
+        try:
+            for i, c in enumerate(circ_list):
+                r = self._run_one(as_circuit(c), shots, int(seed) + i, nm, method, getattr(c, "name", None), handles)
+                if pending is not None:
+                    exps[pending[0]] = pending[1]()
+                    pending = None
+                if callable(r):
+                    pending = (i, r)
+                else:
+                    exps[i] = r
+            if pending is not None:
+                exps[pending[0]] = pending[1]()
+        finally:
+            for h in handles:
+                h.close()
         return Job(Result(exps, circ_list, single, self.name, time.time() - t0))
 
     def _choose_method(self, method, n, shots, nm):
@@ -356,7 +373,9 @@ class DTCSimulator:
             raise ValueError(f"unsupported simulation method {method!r}")
         return method
 
-    def _run_one(self, circ, shots, seed, nm, method, name):
+    def _run_one(self, circ, shots, seed, nm, method, name, handles):
+        """Returns the ExperimentResult, or (noisy trajectory runs) a callable that fetches it once the enqueued
+        GPU work is done; program handles to close after that go to `handles`."""
         t0 = time.time()
         torch = self.ctx.torch
         ctx = self.ctx
@@ -400,33 +419,66 @@ class DTCSimulator:
             vals = to_clbits(cols)
         else:
             handle = capi.ProgramHandle(prog0, ctx.index, self.engine)
+            handles.append(handle)
             nm_ = prog0.n_main
             per = 16 << nm_
             budget = self.max_memory_bytes or int(0.7 * ctx.free_bytes())
             bt = max(1, min(shots, budget // per))
-            state = ctx.empty(bt << nm_, torch.complex128)
-            vals = np.zeros(shots, dtype=np.int64)
-            psum = None
+            state = self._state_buffer(bt << nm_)
+            queued = []                                   # per batch: (offset, n, device columns / indices, device prob sums)
             for a in range(0, shots, bt):
                 nt = min(bt, shots - a)
                 batch = evolve(ctx, prog0, nt, a, seed, handle=handle, state=state, fused_rdm=k <= MAX_PROB_QUBITS)
                 if k <= MAX_PROB_QUBITS:
                     probs = batch.outcome_probs()
-                    cols = sample_rows(ctx, probs, 1, seed, a).cpu().numpy()[:, 0]
-                    ps = probs.sum(dim=0).cpu().numpy()
-                    psum = ps if psum is None else psum + ps
-                    vals[a:a + nt] = to_clbits(cols)
+                    queued.append((a, nt, sample_rows(ctx, probs, 1, seed, a), probs.sum(dim=0), batch))
                 else:
-                    idx = batch.sample_states(seed).cpu().numpy()
-                    cols = np.zeros(nt, dtype=np.int64)
-                    for i, q in enumerate(mq):
-                        cols |= ((idx >> q) & 1) << i
-                    vals[a:a + nt] = to_clbits(cols)
+                    queued.append((a, nt, batch.sample_states(seed), None, batch))
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(ctx.index))
             data["num_passes"] = handle.num_passes
             data["trajectories"] = shots
-            if psum is not None:
-                data["probabilities"] = self._clbit_probs(psum / shots, to_clbits, prog0.n_clbits)
-            handle.close()
+
+            def finish():
+                side = self._side_stream()
+                side.wait_event(done)
+                vals = np.zeros(shots, dtype=np.int64)
+                psum = None
+                with torch.cuda.stream(side):
+                    for a, nt, cols_dev, ps_dev, _batch in queued:
+                        if ps_dev is not None:
+                            cols = cols_dev.cpu().numpy()[:, 0]
+                            ps = ps_dev.cpu().numpy()
+                            psum = ps if psum is None else psum + ps
+                        else:
+                            idx = cols_dev.cpu().numpy()
+                            cols = np.zeros(nt, dtype=np.int64)
+                            for i, q in enumerate(mq):
+                                cols |= ((idx >> q) & 1) << i
+                        vals[a:a + nt] = to_clbits(cols)
+                if psum is not None:
+                    data["probabilities"] = self._clbit_probs(psum / shots, to_clbits, prog0.n_clbits)
+                return self._experiment(vals, data, prog0, name or circ.name, shots, seed, t0)
+
+            return finish
+        return self._experiment(vals, data, prog0, name or circ.name, shots, seed, t0)
+
+    def _state_buffer(self, n_amps):
+        """One state buffer per simulator object, grown on demand (stream-ordered reuse across pipelined circuits)."""
+        torch = self.ctx.torch
+        buf = getattr(self, "_state", None)
+        if buf is None or buf.numel() < n_amps:
+            self._state = None
+            buf = self._state = self.ctx.empty(n_amps, torch.complex128)
+        return buf
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = self.ctx.torch.cuda.Stream(device=self.ctx.index)
+        return self._side
+
+    @staticmethod
+    def _experiment(vals, data, prog0, name, shots, seed, t0):
         counts = {}
         uniq, cnt = np.unique(vals, return_counts=True)
         for v, c in zip(uniq, cnt):
@@ -437,7 +489,7 @@ class DTCSimulator:
                                 for c in range(prog0.n_clbits)]
         data["counts"] = counts
         data["time_taken"] = time.time() - t0
-        return ExperimentResult(name or circ.name, counts, data, shots, seed)
+        return ExperimentResult(name, counts, data, shots, seed)
 
     def sample_trajectories(self, circuit, traj_begin, traj_end, seed, noise_model=None):
         """Classical-register values (numpy int64) of noise trajectories traj_begin..traj_end-1 of `circuit`

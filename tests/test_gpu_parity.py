@@ -430,3 +430,15 @@ def test_fused_readout_rdm_equals_rdm_kernel(ctx, disorder, L, t, echo, ntraj):
         assert float((b.fused_rdm - rdm_ref).abs().max()) < 1e-12
     assert float((b.outcome_probs() - pr_ref).abs().max()) < 1e-12
     assert abs(float(pr_ref.sum()) / ntraj - 1.0) < 1e-10
+
+
+def test_run_list_is_pipelined_and_equals_single_runs(disorder):
+    """run([c0, c1, c2]) (circuit i+1 enqueued before circuit i is read back) == three run() calls with seeds s, s+1, s+2."""
+    hs, phis = disorder[20][0][0][:13], disorder[20][1][0][:12]
+    circs = [RC.transpiled(RC.qc_body("vacuum", 13, 0.97, hs, phis, t, 6, echo)) for t, echo in ((1, False), (3, True), (2, False))]
+    sim = dtcsim.AerSimulator(noise_model=RC.noise_model(0.05))
+    res = sim.run(circs, shots=300, seed_simulator=40).result()
+    for i, c in enumerate(circs):
+        one = sim.run(c, shots=300, seed_simulator=40 + i).result()
+        assert res.get_counts(c) == one.get_counts(c) == res.get_counts()[i]
+        assert abs(res.expectation_z(i)[0] - one.expectation_z()[0]) < 1e-12
