@@ -1,13 +1,17 @@
 // dtcsim.cu -- sm_100a kernels + the C ABI declared in include/dtcsim.h.
 //
-// Kernel inventory (all complex128, HBM-bound; no tensor cores on this path -- see DESIGN.md):
-//   k_tile_pass<S2_LO>   fused  R_A|S -> D -> R_B|S  over 2^12-amplitude tiles: coalesced 16 B loads,
-//                        5-qubit register butterflies, two swizzled shared-memory transposes,
-//                        diagonal ZZ/Z phase as a product of two shared-memory tables.   (hot kernel)
+// Kernel inventory (all complex128; no tensor cores on this path -- see DESIGN.md):
+//   k_tile_stream<MODE>  fused  R_A|G -> D -> R_B|G  over 2^12-amplitude tiles, persistent and warp-specialised:
+//                        TMA bulk / tensor-map loads and stores through a 3-stage shared-memory ring (mbarriers),
+//                        table-builder warps, two compute warpgroups working in place (dtc_stream.cuh).  (hot kernel)
+//   k_tile_pass<S2_LO>   the same pass with register-fed loads/stores, for tiles / bond patterns k_tile_stream does
+//                        not take (general circuits).
 //   k_frames             Philox4x32-10 Pauli-frame walk, one thread per trajectory.
-//   k_probs / k_expect_z warp-shuffle reductions for read-out.
+//   k_probs / k_rdm / k_expect_z   warp-shuffle reductions for read-out; k_readout_small finishes the read-out of
+//                        factorised circuits on a <= 3-qubit density matrix per trajectory (dtc_readout.cuh).
 //   k_generic_*          one-thread-per-element fallbacks (n < 12, cross-checks).
 //   k_dm_*               exact density-matrix primitives (small n).
+//   k_shard_pack         gather / scatter for exchanges of a sharded state whose outgoing qubits are not the top bits.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
