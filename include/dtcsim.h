@@ -152,6 +152,11 @@ int dtc_sample_rows(const double *probs, int64_t n_rows, int n_cols, int n_sampl
  * (dtc_qasm.py measure-all).  scratch: n_traj * 2^(n_local-12 or 0) doubles. */
 int dtc_sample_states(const void *state, int n_local, int64_t n_traj, uint64_t seed, int64_t traj_offset,
                       const uint64_t *fx_or_null, double *scratch, uint64_t *out, void *stream);
+/* n_samples basis-state samples per trajectory (sample s uses Philox index s): out[n_traj][n_samples].  Shots of an
+ * ideal circuit that measures more than 12 qubits (dtc_qasm.py measure-all at L = 20). */
+int dtc_sample_states_multi(const void *state, int n_local, int64_t n_traj, int n_samples, uint64_t seed,
+                            int64_t traj_offset, const uint64_t *fx_or_null, double *scratch, uint64_t *out,
+                            void *stream);
 
 /* ---- density-matrix primitives (exact noisy evolution for small n; Aer method density_matrix).
  *      rho is a 2n-qubit vector: index = row + 2^n * col.  n <= 13. ------------------------- */

@@ -136,15 +136,16 @@ class TrajectoryBatch:
                                             self.fx if apply_frame else None, out.data_ptr(), self.ctx.stream))
         return out.view(self.n_traj, self.n)
 
-    def sample_states(self, seed):
+    def sample_states(self, seed, n_samples=1):
+        """Basis-state samples from |psi|^2 (frame applied): [n_traj] (n_samples == 1) or [n_traj, n_samples] int64."""
         torch = self.ctx.torch
         nchunk = 1 << max(self.n - 12, 0)
         scratch = self.ctx.empty(self.n_traj * nchunk, torch.float64)
-        out = self.ctx.empty(self.n_traj, torch.int64)
-        capi.check(capi.load().dtc_sample_states(self.state.data_ptr(), self.n, self.n_traj,
-                                                 int(seed) & 0xFFFFFFFFFFFFFFFF, self.traj_offset, self.fx,
-                                                 scratch.data_ptr(), out.data_ptr(), self.ctx.stream))
-        return out
+        out = self.ctx.empty(self.n_traj * n_samples, torch.int64)
+        capi.check(capi.load().dtc_sample_states_multi(self.state.data_ptr(), self.n, self.n_traj, int(n_samples),
+                                                       int(seed) & 0xFFFFFFFFFFFFFFFF, self.traj_offset, self.fx,
+                                                       scratch.data_ptr(), out.data_ptr(), self.ctx.stream))
+        return out if n_samples == 1 else out.view(self.n_traj, n_samples)
 
     def materialize(self):
         """Apply the frames in place: the buffer then holds the true statevectors."""
@@ -409,13 +410,21 @@ class DTCSimulator:
             data["probabilities"] = self._clbit_probs(p_host, to_clbits, prog0.n_clbits)
             vals = to_clbits(cols)
         elif nm is None:
-            if k > MAX_PROB_QUBITS:
-                raise ValueError(f"ideal circuits measuring more than {MAX_PROB_QUBITS} qubits are not supported yet")
             batch = evolve(ctx, prog0, 1, 0, seed, self.engine)
-            probs = batch.outcome_probs()
-            cols = sample_rows(ctx, probs, shots, seed, 0).cpu().numpy()[0]
-            data["probabilities"] = self._clbit_probs(probs.cpu().numpy()[0], to_clbits, prog0.n_clbits)
             data["num_passes"] = batch.handle.num_passes
+            if k > MAX_PROB_QUBITS:
+                # wide measurement (dtc_qasm.py measure-all at L = 20): shots = basis-state samples of the one state,
+                # exact <Z> of every measured qubit from one dtc_expect_z pass (dtc_qasm.py:145)
+                idx = batch.sample_states(seed, shots).cpu().numpy().reshape(-1)
+                cols = np.zeros(shots, dtype=np.int64)
+                for i, q in enumerate(mq):
+                    cols |= ((idx >> q) & 1) << i
+                ez = batch.expect_z().cpu().numpy()[0]
+                data["expval_z_by_clbit"] = {int(c): float(ez[q]) for q, c in meas}
+            else:
+                probs = batch.outcome_probs()
+                cols = sample_rows(ctx, probs, shots, seed, 0).cpu().numpy()[0]
+                data["probabilities"] = self._clbit_probs(probs.cpu().numpy()[0], to_clbits, prog0.n_clbits)
             vals = to_clbits(cols)
         else:
             handle = capi.ProgramHandle(prog0, ctx.index, self.engine)
@@ -426,6 +435,7 @@ class DTCSimulator:
             bt = max(1, min(shots, budget // per))
             state = self._state_buffer(bt << nm_)
             queued = []                                   # per batch: (offset, n, device columns / indices, device prob sums)
+            ez_sum = None                                 # wide measurements: sum over trajectories of <Z_q> (device)
             for a in range(0, shots, bt):
                 nt = min(bt, shots - a)
                 batch = evolve(ctx, prog0, nt, a, seed, handle=handle, state=state, fused_rdm=k <= MAX_PROB_QUBITS)
@@ -434,6 +444,8 @@ class DTCSimulator:
                     queued.append((a, nt, sample_rows(ctx, probs, 1, seed, a), probs.sum(dim=0), batch))
                 else:
                     queued.append((a, nt, batch.sample_states(seed), None, batch))
+                    ezs = batch.expect_z().sum(dim=0)
+                    ez_sum = ezs if ez_sum is None else ez_sum + ezs
             done = torch.cuda.Event()
             done.record(torch.cuda.current_stream(ctx.index))
             data["num_passes"] = handle.num_passes
@@ -458,6 +470,10 @@ class DTCSimulator:
                         vals[a:a + nt] = to_clbits(cols)
                 if psum is not None:
                     data["probabilities"] = self._clbit_probs(psum / shots, to_clbits, prog0.n_clbits)
+                if ez_sum is not None:
+                    with torch.cuda.stream(side):
+                        ez = ez_sum.cpu().numpy() / shots
+                    data["expval_z_by_clbit"] = {int(c): float(ez[q]) for q, c in meas}
                 return self._experiment(vals, data, prog0, name or circ.name, shots, seed, t0)
 
             return finish
@@ -487,6 +503,9 @@ class DTCSimulator:
             pr = data["probabilities"]
             data["expval_z"] = [sum(p * (1 - 2 * ((v >> c) & 1)) for v, p in pr.items())
                                 for c in range(prog0.n_clbits)]
+        elif "expval_z_by_clbit" in data:                 # unmeasured clbits read 0: <Z> = +1
+            by = data.pop("expval_z_by_clbit")
+            data["expval_z"] = [by.get(c, 1.0) for c in range(prog0.n_clbits)]
         data["counts"] = counts
         data["time_taken"] = time.time() - t0
         return ExperimentResult(name, counts, data, shots, seed)

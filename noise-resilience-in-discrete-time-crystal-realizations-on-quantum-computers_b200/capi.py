@@ -48,6 +48,7 @@ _SIGS = {
     "dtc_expect_z": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp]),
     "dtc_sample_rows": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_u64, c_i64, c_vp, c_vp]),
     "dtc_sample_states": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_u64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "dtc_sample_states_multi": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_u64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "dtc_dm_init": (ctypes.c_int, [c_vp, ctypes.c_int, c_u64, c_vp]),
     "dtc_dm_rot": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_vp]),
     "dtc_dm_diag": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_i32p, c_f64p, ctypes.c_int, c_i32p, c_i32p,

@@ -630,15 +630,18 @@ __global__ void k_chunk_norms(const double2* __restrict__ state, int n_local, in
 }
 
 __global__ void k_sample_states(const double2* __restrict__ state, int n_local, int chunk_bits,
-                                const double* __restrict__ sums, long long n_traj, u64 seed,
+                                const double* __restrict__ sums, long long n_traj, int n_samples, u64 seed,
                                 long long traj_offset, const u64* __restrict__ fx, u64* __restrict__ out) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_traj) return;
+    // thread per (trajectory, sample): sample s of a trajectory uses philox index s (stream 1)
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_traj * n_samples) return;
+    const long long t = i / n_samples;
+    const uint32_t smp = (uint32_t)(i % n_samples);
     const u64 nchunks = 1ull << (n_local - chunk_bits);
     const double* s = sums + (u64)t * nchunks;
     double total = 0.0;
     for (u64 c = 0; c < nchunks; ++c) total += s[c];
-    const double target = philox_uniform(seed, 0u, 1u, (u64)(traj_offset + t)) * total;
+    const double target = philox_uniform(seed, smp, 1u, (u64)(traj_offset + t)) * total;
     double cum = 0.0;
     u64 c = 0;
     for (; c + 1 < nchunks; ++c) {
@@ -654,7 +657,7 @@ __global__ void k_sample_states(const double2* __restrict__ state, int n_local, 
     }
     u64 idx = (c << chunk_bits) | pick;
     if (fx) idx ^= fx[t];
-    out[t] = idx;
+    out[i] = idx;
 }
 
 // ---- read-out of a factorised circuit: the small events on a <= 3-qubit density matrix, one thread per trajectory
@@ -1213,17 +1216,23 @@ int dtc_sample_rows(const double* probs, int64_t n_rows, int n_cols, int n_sampl
     return DTC_OK;
 }
 
-int dtc_sample_states(const void* state, int n_local, int64_t n_traj, uint64_t seed, int64_t traj_offset,
-                      const uint64_t* fx, double* scratch, uint64_t* out, void* stream) {
-    if (!state || !scratch || !out) return fail(DTC_ERR_INVALID, "bad argument");
+int dtc_sample_states_multi(const void* state, int n_local, int64_t n_traj, int n_samples, uint64_t seed, int64_t traj_offset,
+                            const uint64_t* fx, double* scratch, uint64_t* out, void* stream) {
+    if (!state || !scratch || !out || n_traj < 1 || n_samples < 1) return fail(DTC_ERR_INVALID, "bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     const int cb = n_local < 12 ? n_local : 12;
     const long long nblk = n_traj << (n_local - cb);
+    const long long n = n_traj * n_samples;
     k_chunk_norms<<<(unsigned)nblk, 128, 0, s>>>((const double2*)state, n_local, cb, scratch);
-    k_sample_states<<<(unsigned)((n_traj + 63) / 64), 64, 0, s>>>((const double2*)state, n_local, cb, scratch, n_traj, seed,
-                                                                 traj_offset, (const u64*)fx, (u64*)out);
+    k_sample_states<<<(unsigned)((n + 63) / 64), 64, 0, s>>>((const double2*)state, n_local, cb, scratch, n_traj, n_samples, seed,
+                                                            traj_offset, (const u64*)fx, (u64*)out);
     CUDA_TRY(cudaGetLastError());
     return DTC_OK;
+}
+
+int dtc_sample_states(const void* state, int n_local, int64_t n_traj, uint64_t seed, int64_t traj_offset,
+                      const uint64_t* fx, double* scratch, uint64_t* out, void* stream) {
+    return dtc_sample_states_multi(state, n_local, n_traj, 1, seed, traj_offset, fx, scratch, out, stream);
 }
 
 // ---- density matrix

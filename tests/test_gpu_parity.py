@@ -442,3 +442,34 @@ def test_run_list_is_pipelined_and_equals_single_runs(disorder):
         one = sim.run(c, shots=300, seed_simulator=40 + i).result()
         assert res.get_counts(c) == one.get_counts(c) == res.get_counts()[i]
         assert abs(res.expectation_z(i)[0] - one.expectation_z()[0]) < 1e-12
+
+
+def test_wide_measurement_ideal_and_noisy(disorder):
+    """dtc_qasm.py shape at L = 14 (> 12 measured qubits): shots are basis-state samples; exact per-qubit <Z> comes from
+    one dtc_expect_z pass.  Ideal: against the oracle statevector; noisy: against the oracle's trajectories (same Philox ids)."""
+    L = 14
+    hs, phis = disorder[20][0][0][:L], disorder[20][1][0][:L - 1]
+    ops, n, nc = C.dtc_qasm_gates("1", L, 0.94, hs, phis, 2)
+    circ = dtcsim.QuantumCircuit(L, L)
+    for nm_, qs, ps, cs in ops:
+        circ._add(nm_, qs, ps, cs)
+    psi = O.run_statevector(ops, L)
+    idx = np.arange(1 << L)
+    exact = np.array([np.sum(np.abs(psi) ** 2 * (1 - 2 * ((idx >> q) & 1))) for q in range(L)])
+    shots = 4096
+    res = dtcsim.AerSimulator().run(circ, shots=shots, seed_simulator=5).result()
+    counts = res.get_counts()
+    assert sum(counts.values()) == shots and all(len(k) == L for k in counts)
+    assert np.abs(np.array(res.expectation_z()) - exact).max() < 1e-10
+    ez = np.array(dtcsim.backend.compute_z_expectation(counts, L))
+    assert np.abs(ez - exact).max() < 4.5 / np.sqrt(shots)
+    # noisy: 96 trajectories, every qubit measured
+    nmod = dtcsim.NoiseModel()
+    nmod.add_all_qubit_quantum_error(dtcsim.depolarizing_error(0.2, 1), ["rx", "x"])
+    ntraj = 96
+    resn = dtcsim.AerSimulator(noise_model=nmod).run(circ, shots=ntraj, seed_simulator=8).result()
+    oc, na, _ = O.compact_ops(ops, L)
+    psin = O.run_trajectories(oc, na, O.PauliNoise.depolarizing(0.2, names=("rx", "x")), 8, np.arange(ntraj))
+    want = np.array([np.mean(np.sum(np.abs(psin) ** 2 * (1 - 2 * ((idx >> q) & 1)), axis=1)) for q in range(L)])
+    assert np.abs(np.array(resn.expectation_z()) - want).max() < 1e-10
+    assert sum(resn.get_counts().values()) == ntraj
