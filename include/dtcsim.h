@@ -71,6 +71,10 @@ int dtc_program_set_events(dtc_program *p, int64_t n_events, const int32_t *type
  * from the frame walk -- the host uses them for the small read-out simulation (plan.py, optimize=True).
  * DTC_EV_D2C is a D2 term whose partner q1 is still |0> in psi': sign from (q0,q1), phase one-body on q0. */
 int dtc_program_set_exec_layers(dtc_program *p, int n_exec_layers);
+/* Optional, before finalize: the internal bit index of the single read-out qubit of a factorised circuit.  The pass
+ * schedule is then chosen (among equally long ones) so that its last pass works on a tile holding that qubit, which
+ * lets that pass fuse the read-out reduction (dtc_program_set_fused_rdm). */
+int dtc_program_set_readout_hint(dtc_program *p, int bit);
 /* Build layer tables and the pass schedule and upload them to `device`.
  * engine: DTC_ENGINE_AUTO picks the fused tile engine when n_local >= 12. */
 int dtc_program_finalize(dtc_program *p, int device, int engine, int n_local);

@@ -26,6 +26,7 @@ _SIGS = {
     "dtc_program_set_events": (ctypes.c_int, [c_vp, c_i64, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_f64p, c_f64p,
                                               ctypes.c_double]),
     "dtc_program_set_exec_layers": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "dtc_program_set_readout_hint": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "dtc_program_finalize": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "dtc_program_num_passes": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_workspace_bytes": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(ctypes.c_size_t)]),
@@ -123,6 +124,9 @@ class ProgramHandle:
             check(lib.dtc_program_set_events(self._h, len(ev["type"]), *[k[1] for k in keep],
                                              float(prog.global_phase)))
             check(lib.dtc_program_set_exec_layers(self._h, int(prog.n_exec_layers)))
+            small = getattr(prog, "small", None)
+            if small is not None and len(small["reg_bits"]) == 1:
+                check(lib.dtc_program_set_readout_hint(self._h, int(small["reg_bits"][0])))
             check(lib.dtc_program_finalize(self._h, int(device), int(engine), int(self.n_local)))
             small = getattr(prog, "small", None)
             if small is not None:

@@ -21,6 +21,7 @@ struct DtcGenericStep {
 
 struct DtcProgramHost {
     int n_qubits = 0, n_layers = 0, n_exec_layers = 0, n_local = 0, device = -1, engine = 0;
+    int readout_bit = -1;          // hint (dtc_program_set_readout_hint): schedule the last pass on a tile holding this bit
     double global_phase = 0.0;
     bool finalized = false;
     int64_t n_sites = 0;
@@ -366,7 +367,9 @@ static inline std::vector<DtcGroup> dtc_make_groups(const DtcProgramHost& P) {
     return groups;
 }
 
-static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
+// first_pick >= 0: group preferred for the first "diagonal only + look-ahead" pass (the passes then alternate between the
+// groups, so this choice decides which group's tile the LAST pass works on -- see dtc_schedule_tile_for_readout).
+static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err, int first_pick = -1, int* n_groups = nullptr) {
     const int M = P.n_exec_layers, n = P.n_local;
     const u64 local_mask = (n >= 64) ? ~0ull : ((1ull << n) - 1);
     P.passes.clear();
@@ -377,6 +380,8 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
             return false;
         }
     const std::vector<DtcGroup> groups = dtc_make_groups(P);
+    if (n_groups) *n_groups = (int)groups.size();
+    bool first_choice = true;
     int j = 0;
     u64 done = 0;
     while (j < M) {
@@ -403,6 +408,10 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
             complete = true;
             for (size_t k = 0; k < groups.size(); ++k)
                 if (pick < 0 || dtc_popc(next & groups[k].members) > dtc_popc(next & groups[pick].members)) pick = (int)k;
+            if (first_choice && first_pick >= 0 && first_pick < (int)groups.size() &&
+                dtc_popc(next & groups[first_pick].members) == dtc_popc(next & groups[pick].members))
+                pick = first_pick;               // an equally good look-ahead group, chosen by the caller
+            first_choice = false;
         } else if (n_cand == 1) {
             complete = true;
             pick = best_keep;
@@ -470,6 +479,26 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err) {
         }
     }
     return true;
+}
+
+// Schedule such that the last pass works on a tile containing `bit` (the read-out qubit of a factorised circuit) when some
+// choice of the first look-ahead group achieves that without adding passes: that pass can then reduce the qubit's
+// density matrix itself instead of storing the state (k_tile_stream, fused read-out).
+static inline bool dtc_schedule_tile_for_readout(DtcProgramHost& P, int bit, std::string& err) {
+    int ng = 0;
+    if (!dtc_schedule_tile(P, err, -1, &ng)) return false;
+    auto last_has = [&]() {
+        if (P.passes.empty()) return false;
+        const DtcTilePass& T = P.passes.back();
+        return ((T.tile_mask >> bit) & 1ull) && P.spasses.back().mode != 0;
+    };
+    if (bit < 0 || bit >= P.n_local || last_has()) return true;
+    const size_t base_passes = P.passes.size();
+    for (int g = 0; g < ng; ++g) {
+        if (!dtc_schedule_tile(P, err, g)) return false;
+        if (P.passes.size() <= base_passes && last_has()) return true;
+    }
+    return dtc_schedule_tile(P, err);             // no better choice: the default schedule
 }
 
 static inline void dtc_schedule_generic(DtcProgramHost& P) {

@@ -855,6 +855,12 @@ int dtc_program_set_exec_layers(dtc_program* p, int n_exec_layers) {
     return DTC_OK;
 }
 
+int dtc_program_set_readout_hint(dtc_program* p, int bit) {
+    if (!p || p->h.finalized) return fail(DTC_ERR_INVALID, "program is NULL or finalized");
+    p->h.readout_bit = bit;
+    return DTC_OK;
+}
+
 int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
     if (!p) return fail(DTC_ERR_INVALID, "program is NULL");
     if (p->h.finalized) return fail(DTC_ERR_INVALID, "program already finalized");
@@ -869,7 +875,7 @@ int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
         return fail(DTC_ERR_INVALID, "tile engine needs n_local >= 12");
     p->h.engine = engine;
     if (engine == DTC_ENGINE_TILE) {
-        if (!dtc_schedule_tile(p->h, err)) return fail(DTC_ERR_INVALID, err);
+        if (!dtc_schedule_tile_for_readout(p->h, p->h.readout_bit, err)) return fail(DTC_ERR_INVALID, err);
     } else if (engine == DTC_ENGINE_GENERIC) {
         for (int j = 0; j < p->h.n_exec_layers; ++j)
             if (n_local < 64 && (p->h.layers[j].rot_any >> n_local))
