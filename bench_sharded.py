@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--periods", type=int, default=10)
     ap.add_argument("--noise", type=float, default=0.0)
     ap.add_argument("--check-oracle", action="store_true", help="small L only: compare <Z> with the CPU oracle")
+    ap.add_argument("--components", action="store_true", help="extra run with a synchronise after every component: seconds each")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -101,6 +102,11 @@ def main():
                nvlink_gbs_per_rank_lower_bound=sv.stats["exchange_bytes_per_rank"] / dt / 1e9,
                hbm_algorithmic_gbs_per_rank=eng.passes * 2 * (16 << n_local) / dt / 1e9)
     ok = abs(res["norm"] - 1) < 1e-9 and np.abs(ez - 1).max() < 1e-9
+    if args.components:
+        eng.timing = {}
+        sharded.ShardedStatevector(L, rank, world, eng, all_reduce=allred).run(circ)
+        out["component_seconds_rank0"] = {k: round(v, 4) for k, v in eng.timing.items()}
+        eng.timing = None
     # ---- one noisy forward trajectory
     if args.noise > 0:
         nm = dtcsim.NoiseModel()

@@ -236,17 +236,31 @@ class CudaShardEngine:
         self.b = self.ctx.empty(1 << n_local, torch.complex128)
         self.passes = 0
         self.fast_exchanges = 0
+        self.timing = None          # set to {} to collect wall-clock seconds per component (synchronises after each)
+
+    def _timed(self, key, t0):
+        if self.timing is not None:
+            import time
+            self.torch.cuda.synchronize(self.ctx.index)
+            self.timing[key] = self.timing.get(key, 0.0) + time.perf_counter() - t0
 
     def run_segment(self, prog, first):
+        import time
         capi = self.capi
+        t0 = time.perf_counter()
         h = capi.ProgramHandle(prog, self.ctx.index, capi.ENGINE_AUTO, self.n_local)
+        self._timed("segment_setup", t0)
+        t0 = time.perf_counter()
         wsb = h.workspace_bytes(1)
         ws = self.ctx.empty(wsb, self.torch.uint8)
         init = capi.INIT_KEEP if not first else (0 if self.rank == 0 else capi.INIT_ZERO)
         h.run(self.a.data_ptr(), 1, 0, 0, ws.data_ptr(), wsb, self.ctx.stream, init_index=init, rank_bits=self.rank)
         self.passes += h.num_passes
         self.torch.cuda.current_stream(self.ctx.index).synchronize()     # ws / handle are freed on return
+        self._timed("segment_sweeps", t0)
+        t0 = time.perf_counter()
         h.close()
+        self._timed("segment_teardown", t0)
 
     def exchange(self, lq):
         import torch.distributed as dist
@@ -256,9 +270,12 @@ class CudaShardEngine:
         if list(lq) == list(range(self.n_local - g, self.n_local)):
             # the outgoing qubits are the top local bits: chunk d of the state IS what rank d receives and the incoming
             # chunks land where they belong, so pack and unpack are identities -- one all-to-all, no extra sweeps
+            import time
+            t0 = time.perf_counter()
             dist.all_to_all_single(self.b.view(f64), self.a.view(f64), group=self.group)
             self.a, self.b = self.b, self.a
             self.fast_exchanges += 1
+            self._timed("all_to_all", t0)
             return
         _, lp = capi.i32(lq)
         capi.check(lib.dtc_shard_pack(self.a.data_ptr(), self.b.data_ptr(), self.n_local, g, lp, self.ctx.stream))
