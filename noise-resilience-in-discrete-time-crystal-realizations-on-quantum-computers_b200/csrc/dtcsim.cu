@@ -773,6 +773,16 @@ static dtc_encode_fn tensor_map_encoder() {
     return fn;
 }
 
+static CUtensorMapL2promotion stream_l2_promotion() {
+    static const CUtensorMapL2promotion v = []() {
+        const char* e = getenv("DTCSIM_L2_PROMOTION");      // tuning: 0 none, 64, 128, 256 bytes
+        const int b = e ? atoi(e) : 0;
+        return b == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : b == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+             : b == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    }();
+    return v;
+}
+
 // tensor map of the tile {0,1} + [g, g+10) over the whole batch: (8 doubles | bits [2,g) | 32 | 32 | everything above)
 static int stream_tensor_map(CUtensorMap* tm, void* state, int n_local, int g, int64_t n_traj) {
     dtc_encode_fn enc = tensor_map_encoder();
@@ -782,7 +792,7 @@ static int stream_tensor_map(CUtensorMap* tm, void* state, int n_local, int g, i
     const cuuint32_t box[5] = {8, 1, 32, 32, 1};
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
     const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, state, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_SWIZZLE_NONE, stream_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DTC_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
     return DTC_OK;
 }
