@@ -100,7 +100,7 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -108,6 +108,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 smax.append(float(f[2]))
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
@@ -115,7 +116,7 @@ class ClockSampler:
                     reasons.add(name)
         busy = [x for x in sm if x > 0]
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w": float(np.median(power)) if power else None}
 
 
 # ------------------------------------------------------------------------------------------ reference arm / cpu baseline
