@@ -99,6 +99,10 @@ int dtc_program_frames(const dtc_program *p, void *workspace, int64_t n_traj,
  * the register-fed k_tile_pass.  enable < 0 restores the default (environment DTCSIM_STREAM, else on).
  * dtc_program_num_stream_passes(): how many passes of the schedule are eligible for k_tile_stream. */
 int dtc_set_stream_engine(int enable);
+/* Qubit groups that start at or above this internal bit (default 15: 64 B runs of such a group's tiles would each lie in a
+ * different 2 MiB page) are given five qubits and tiles of 32 runs of 2 KB.  Affects programs finalized afterwards;
+ * tests lower it to exercise that path on small registers. */
+int dtc_set_high_stride_bit(int bit);
 int dtc_program_num_stream_passes(const dtc_program *p, int *n_passes);
 
 /* Kernel timing for roofline accounting: when enabled, dtc_program_run() brackets its pass loop with

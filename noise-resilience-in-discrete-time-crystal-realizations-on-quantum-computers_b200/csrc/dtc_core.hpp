@@ -34,6 +34,12 @@ struct DtcProgramHost {
 
 static inline int dtc_popc(u64 x) { return __builtin_popcountll(x); }
 
+// A group of ten qubits starting at bit g is swept in tiles of 1024 runs of 64 B that span 2^(g-7) pages of 2 MiB; from
+// g = 15 on that is more than the 128-entry TLB of an SM holds and the sweep becomes translation-bound (measured: 2.3 TB/s at
+// g = 20 against 5.0 TB/s at g = 10).  Groups that start at or above this bit get five qubits and 2 KB runs instead.
+#define DTC_HIGH_STRIDE_BIT (g_dtc_high_stride_bit)
+static int g_dtc_high_stride_bit = 15;      // dtc_set_high_stride_bit(): tests lower it to reach this path at small n
+
 // ---- raw event arrays -> staged DtcEvent list
 static inline bool dtc_stage_events(DtcProgramHost& P, int64_t n, const int32_t* type, const int32_t* layer,
                                     const int32_t* q0, const int32_t* q1, const int32_t* slot, const double* val,
@@ -151,6 +157,21 @@ static inline bool dtc_build_tile(u64 S, int n_local, int tb[DTC_TILE_BITS], int
         if ((S >> b) & 1ull) top = b;
     // preferred shapes (eligible for the TMA-fed streaming engine): [0,12) with the active set below bit 10,
     // or {0,1} + ten consecutive bits containing the active set
+    // high-stride groups (lowest qubit >= DTC_HIGH_STRIDE_BIT, at most five qubits within five consecutive bits): seven
+    // passive low bits + five consecutive bits -- 32 runs of 2 KB, so a tile touches at most 32 pages (mode C of the
+    // streaming engine); ten active bits there would put each of 1024 runs of 64 B into a page of its own
+    if (n_local >= DTC_TILE_BITS && top >= 0) {
+        int low = 0;
+        while (!((S >> low) & 1ull)) ++low;
+        if (low >= DTC_HIGH_STRIDE_BIT && top - low < 5 && n_local >= 12) {
+            int g = low;
+            if (g + 5 > n_local) g = n_local - 5;
+            for (int l = 0; l < 7; ++l) tb[l] = l;
+            for (int l = 7; l < DTC_TILE_BITS; ++l) tb[l] = g + l - 7;
+            *s2_lo = 2;
+            return true;
+        }
+    }
     if (n_local >= DTC_TILE_BITS && top >= 0) {
         int g = -1;
         if (!(S >> 10)) g = 0;
@@ -246,16 +267,20 @@ static inline bool dtc_make_stream_pass(const DtcTilePass& T, const DtcLayer* LD
     unsigned active = 0;
     for (int l = 0; l < DTC_TILE_BITS; ++l)
         if (T.t1[l] != 0.0 || T.t2[l] != 0.0) active |= 1u << l;
+    bool modeC_shape = true;
+    for (int l = 0; l < 7; ++l) modeC_shape = modeC_shape && T.tb[l] == l;
+    for (int l = 8; l < DTC_TILE_BITS; ++l) modeC_shape = modeC_shape && T.tb[l] == T.tb[7] + (l - 7);
     int mode = 0;
-    if (contig && !(active & 0xC00u)) mode = 1;
+    if (modeC_shape && !contig && !(active & 0x7Fu)) mode = 3;
+    else if (contig && !(active & 0xC00u)) mode = 1;
     else if ((contig || modeB_shape) && !(active & 0x3u)) mode = 2;
     if (!mode) return false;
     S.mode = mode;
     S.two = 2;
     S.contig = contig ? 1 : 0;
     S.n_local = T.n_local;
-    S.g = T.tb[2];
-    if (!contig && S.g + 10 > T.n_local) return false;
+    S.g = mode == 3 ? T.tb[7] : T.tb[2];
+    if (!contig && S.g + (mode == 3 ? 5 : 10) > T.n_local) return false;
     S.layerA = T.layerA; S.layerD = T.layerD; S.layerB = T.layerB;
     memcpy(S.tb, T.tb, sizeof(S.tb));
     memcpy(S.t1, T.t1, sizeof(S.t1));
@@ -275,7 +300,14 @@ static inline bool dtc_make_stream_pass(const DtcTilePass& T, const DtcLayer* LD
         if (a >= 0 && b >= 0) {
             if (a > b) { int t = a; a = b; b = t; }
             int fam;
-            if (a >= 3 && b <= 7) fam = 0;
+            if (mode == 3) {
+                if (a >= 7) fam = 0;                         // core: both in [7,11]
+                else if (b <= 2) fam = 3;
+                else if (a >= 3 && b <= 6) fam = 4;
+                else if (a <= 2 && b <= 6) fam = 5;
+                else return false;                           // passive-active bond: register-fed kernel
+            }
+            else if (a >= 3 && b <= 7) fam = 0;
             else if (a == 2 && b == 3) fam = 1;
             else if (a == 7 && b == 8) fam = 2;
             else if (b <= 2) fam = 3;
@@ -339,10 +371,19 @@ static inline std::vector<DtcGroup> dtc_make_groups(const DtcProgramHost& P) {
     }
     std::vector<u64> chunks;
     u64 cur = 0;
+    int cap = 10, first = -1;
     for (int q = 0; q < n; ++q) {
         if (count[q] == 0 || count[q] * 2 <= maxc) continue;
+        if (!cur) {
+            first = q;
+            cap = (q >= DTC_HIGH_STRIDE_BIT && n >= DTC_TILE_BITS) ? 5 : 10;
+        } else if (cap == 5 && q - first >= 5) {            // five consecutive bits at most
+            chunks.push_back(cur);
+            cur = 0;
+            first = q;
+        }
         cur |= 1ull << q;
-        if (dtc_popc(cur) == 10) { chunks.push_back(cur); cur = 0; }
+        if (dtc_popc(cur) == cap) { chunks.push_back(cur); cur = 0; }
     }
     if (cur) chunks.push_back(cur);
     u64 rare = 0;

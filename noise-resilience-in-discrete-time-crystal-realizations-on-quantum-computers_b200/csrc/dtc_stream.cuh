@@ -10,7 +10,9 @@
 // Tile-local index l (12 bits) = 16 B chunk index in the stage buffer (dense, no swizzle).  Two layouts:
 //   mode A  tile = local qubits 0..11 (64 KB contiguous);  rotatable bits 0..9,  passive 10,11
 //   mode B  tile = qubits {0,1} + [g, g+10) (1024 runs of 64 B);  rotatable bits 2..11, passive 0,1
-// Register sets:  S2 = bits 3..7 in both modes;  S1 = {0,1,2,8,9} (A) / {2,8,9,10,11} (B).
+//   mode C  tile = qubits 0..6 + [g, g+5) (32 runs of 2 KB);  rotatable bits 7..11, passive 0..6.  For groups whose
+//           64 B runs would each lie in a different 2 MiB page (g >= 15: translation-bound); one register set, one phase.
+// Register sets:  S2 = bits 3..7 in modes A, B;  S1 = {0,1,2,8,9} (A) / {2,8,9,10,11} (B);  mode C: bits 7..11 only.
 // Bank conflicts: a 16 B access is conflict free when the 8 lanes of a quarter warp hit 8 different
 // values of l[0:2].  Phase 2 maps those lanes to l[0:2] directly.  Phases 1/3 hold low bits in
 // registers, so lane c reads its registers in the order l_low = k ^ c: the tan-form RX butterfly is
@@ -29,7 +31,7 @@
 #define DTC_STREAM_THREADS (128 * DTC_STREAM_WG + 32 + 32 * DTC_STREAM_STAGES)   // + TMA driver warp + one table-builder warp per stage
 
 struct DtcStreamPass {
-    int mode;                      // 1: A, 2: B
+    int mode;                      // 1: A, 2: B, 3: C
     int contig;                    // tile is 64 KB contiguous in global memory (bulk copy, no tensor map)
     int n_local, g;                // B: tile bits 2..11 = global bits g..g+9
     int layerA, layerD, layerB;
@@ -40,6 +42,7 @@ struct DtcStreamPass {
     // two-body terms of D_layerD, local-local ones by table family:
     //   0: core  both ends in local [3,7]      1: (2,3)                    2: (7,8)
     //   3: T2lo  both in {0,1,2}               4: T2hi  both in [8,11]     5: T2x  one in {0,1,2}, one in [8,11]
+    // (mode C: core = [7,11], T2hi = [3,6], families 1 and 2 empty)
     int fam_off[7];                // family f = entries [fam_off[f], fam_off[f+1]) of Fk/Fa/Fb
     int nC, nO;
     unsigned char Fk[DTC_MAXT], Fa[DTC_MAXT], Fb[DTC_MAXT];
@@ -68,9 +71,17 @@ struct StreamBuild {
 // ---- tile geometry
 DTC_HD u64 stream_tile_base(u64 tile_in_traj, const DtcStreamPass& P) {
     if (P.contig) return tile_in_traj << DTC_TILE_BITS;
+    if (P.mode == 3) {
+        const int lb = P.g - 7;
+        return ((tile_in_traj & ((1ull << lb) - 1)) << 7) | ((tile_in_traj >> lb) << (P.g + 5));
+    }
     const int lb = P.g - 2;
     return ((tile_in_traj & ((1ull << lb) - 1)) << 2) | ((tile_in_traj >> lb) << (P.g + 10));
 }
+
+// first local bit of the core table (register set of the diagonal phase) and of the high half of T2
+DTC_HD int stream_core_base(int mode) { return mode == 3 ? 7 : 3; }
+DTC_HD int stream_hi_base(int mode) { return mode == 3 ? 3 : 8; }
 
 // chunk index of register k in phases 1/3
 template <int MODE>
@@ -157,6 +168,30 @@ DTC_HD void stream_phase2(int t, double2* tile, const StreamSlot& tab, const Dtc
     for (int r = 0; r < DTC_NREG; ++r) p[r << 3] = a[r];
 }
 
+// mode C: the only phase.  Thread t <-> passive local bits 0..6, registers <-> local bits 7..11; phase = T1c[r] * T2[t].
+DTC_HD void stream_phaseC(int t, double2* tile, const StreamSlot& tab, const DtcStreamPass& P, u64 rmA, u64 rmB) {
+    double tA[5], tB[5];
+    tile_signed_t(P.t1, P.tb, 7, rmA, tA);
+    tile_signed_t(P.t2, P.tb, 7, rmB, tB);
+    double2 a[DTC_NREG];
+    double2* p = tile + t;
+#pragma unroll
+    for (int r = 0; r < DTC_NREG; ++r) a[r] = p[r << 7];
+    tile_rot_bits(a, tA, 0, 4);
+    const double2 c = tab.T2[t];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        rot_pair(a[i], a[i | 16], tA[4]);
+        a[i] = cmul(a[i], cmul(tab.T1c[i], c));
+        a[i | 16] = cmul(a[i | 16], cmul(tab.T1c[i | 16], c));
+        rot_pair(a[i], a[i | 16], tB[4]);
+        DTC_SCHED_FENCE();
+    }
+    tile_rot_bits(a, tB, 0, 4);
+#pragma unroll
+    for (int r = 0; r < DTC_NREG; ++r) p[r << 7] = a[r];
+}
+
 // ---- phase tables of one tile, built by ONE warp in three steps separated by __syncwarp().
 // g_outer: global index of the tile's local index 0 (incl. rank bits above n_local).
 DTC_HD double2 stream_bond(const StreamBuild& bl, const DtcStreamPass& P, int c, int l12) {
@@ -201,20 +236,21 @@ DTC_HD void stream_build1(int lane, StreamBuild& bl, const DtcStreamPass& P, con
 
 // step 2: core table (one entry per lane), F/G, and the two halves of T2 (T2lo over local 0..2, T2hi over local 8..11)
 DTC_HD void stream_build2(int lane, StreamBuild& bl, const DtcStreamPass& P, const DtcLayer& L) {
+    const int cb = stream_core_base(P.mode), hb = stream_hi_base(P.mode);
     {
-        const int l12 = lane << 3;
-        double2 p = bl.E[3][lane & 1];
+        const int l12 = lane << cb;
+        double2 p = bl.E[cb][lane & 1];
 #pragma unroll
-        for (int l = 4; l <= 7; ++l) p = cmul(p, bl.E[l][(lane >> (l - 3)) & 1]);
+        for (int j = 1; j < 5; ++j) p = cmul(p, bl.E[cb + j][(lane >> j) & 1]);
         DTC_NOUNROLL
         for (int c = P.fam_off[0]; c < P.fam_off[1]; ++c) p = cmul(p, stream_bond(bl, P, c, l12));
         bl.T1c[lane] = p;
     }
     if (lane < 16) {
-        const int l12 = lane << 8;
-        double2 p = bl.E[8][lane & 1];
+        const int l12 = lane << hb;
+        double2 p = bl.E[hb][lane & 1];
 #pragma unroll
-        for (int l = 9; l < DTC_TILE_BITS; ++l) p = cmul(p, bl.E[l][(lane >> (l - 8)) & 1]);
+        for (int j = 1; j < 4; ++j) p = cmul(p, bl.E[hb + j][(lane >> j) & 1]);
         DTC_NOUNROLL
         for (int c = P.fam_off[4]; c < P.fam_off[5]; ++c) p = cmul(p, stream_bond(bl, P, c, l12));
         bl.T2hi[lane] = p;
@@ -255,7 +291,7 @@ DTC_HD void stream_build3(int lane, const StreamBuild& bl, StreamSlot& slot, con
             slot.T2[idx] = one;
             continue;
         }
-        const int l12 = (idx & 7) | ((idx >> 3) << 8);
+        const int l12 = (idx & 7) | ((idx >> 3) << stream_hi_base(P.mode));
         double2 q = cmul(bl.C, cmul(bl.T2lo[idx & 7], bl.T2hi[idx >> 3]));
         DTC_NOUNROLL
         for (int c = P.fam_off[5]; c < P.fam_off[6]; ++c) q = cmul(q, stream_bond(bl, P, c, l12));

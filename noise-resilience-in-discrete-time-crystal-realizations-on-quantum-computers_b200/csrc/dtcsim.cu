@@ -172,6 +172,12 @@ __device__ __forceinline__ void stream_tma_load(const DtcStreamPass& P, const CU
     if (P.contig) {
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(dst), "l"(state + (T << DTC_TILE_BITS)), "r"(DTC_TILE * 16), "r"(bar) : "memory");
+    } else if (P.mode == 3) {
+        const int lb = P.g - 7;        // tensor: (256 doubles | bits [7,g) | 32 rows | everything above)
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5}], [%6];"
+            ::"r"(dst), "l"(tmap), "r"(0), "r"((int)(T & ((1ull << lb) - 1))), "r"(0), "r"((int)(T >> lb)), "r"(bar)
+            : "memory");
     } else {
         const int lb = P.g - 2;
         asm volatile(
@@ -185,6 +191,11 @@ __device__ __forceinline__ void stream_tma_store(const DtcStreamPass& P, const C
     if (P.contig) {
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                      ::"l"(state + (T << DTC_TILE_BITS)), "r"(src), "r"(DTC_TILE * 16) : "memory");
+    } else if (P.mode == 3) {
+        const int lb = P.g - 7;
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1,%2,%3,%4}], [%5];"
+                     ::"l"(tmap), "r"(0), "r"((int)(T & ((1ull << lb) - 1))), "r"(0), "r"((int)(T >> lb)), "r"(src)
+                     : "memory");
     } else {
         const int lb = P.g - 2;
         asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1,%2,%3,%4,%5}], [%6];"
@@ -355,16 +366,23 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
             }
             wg_barrier(wg);
         }
-        double tt[5];
-        stream_signed_s1<MODE>(P.t1, P.tb, rmA, tt);
-        stream_phase13_call<MODE>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
-        if (MODE == 1) __syncwarp(); else wg_barrier(wg);
-        PROF_LAP(1);
-        stream_phase2(t, tile, slot, P, rmA, rmB);
-        if (MODE == 1) __syncwarp(); else wg_barrier(wg);
-        PROF_LAP(2);
-        stream_signed_s1<MODE>(P.t2, P.tb, rmB, tt);
-        stream_phase13_call<MODE>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+        if (MODE == 3) {
+            // one register set, one phase: thread <-> the seven passive low bits, registers <-> the five active bits
+            stream_phaseC(t, tile, slot, P, rmA, rmB);
+            PROF_LAP(2);
+        } else {
+            constexpr int M13 = MODE == 3 ? 1 : MODE;
+            double tt[5];
+            stream_signed_s1<M13>(P.t1, P.tb, rmA, tt);
+            stream_phase13_call<M13>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+            if (MODE == 1) __syncwarp(); else wg_barrier(wg);
+            PROF_LAP(1);
+            stream_phase2(t, tile, slot, P, rmA, rmB);
+            if (MODE == 1) __syncwarp(); else wg_barrier(wg);
+            PROF_LAP(2);
+            stream_signed_s1<M13>(P.t2, P.tb, rmB, tt);
+            stream_phase13_call<M13>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+        }
         if (rdm_out) {
             wg_barrier(wg);
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -784,15 +802,26 @@ static CUtensorMapL2promotion stream_l2_promotion() {
 }
 
 // tensor map of the tile {0,1} + [g, g+10) over the whole batch: (8 doubles | bits [2,g) | 32 | 32 | everything above)
-static int stream_tensor_map(CUtensorMap* tm, void* state, int n_local, int g, int64_t n_traj) {
+static int stream_tensor_map(CUtensorMap* tm, void* state, int n_local, int g, int64_t n_traj, int mode) {
     dtc_encode_fn enc = tensor_map_encoder();
     if (!enc) return fail(DTC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t dims[5] = {8, 1ull << (g - 2), 32, 32, (cuuint64_t)n_traj << (n_local - g - 10)};
-    const cuuint64_t strides[4] = {64, 16ull << g, 16ull << (g + 5), 16ull << (g + 10)};
-    const cuuint32_t box[5] = {8, 1, 32, 32, 1};
-    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, state, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, stream_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r;
+    if (mode == 3) {
+        // tile {0..6} + [g, g+5): (256 doubles | bits [7,g) | 32 rows | everything above)
+        const cuuint64_t dims[4] = {256, 1ull << (g - 7), 32, (cuuint64_t)n_traj << (n_local - g - 5)};
+        const cuuint64_t strides[3] = {2048, 16ull << g, 16ull << (g + 5)};
+        const cuuint32_t box[4] = {256, 1, 32, 1};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, state, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, stream_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t dims[5] = {8, 1ull << (g - 2), 32, 32, (cuuint64_t)n_traj << (n_local - g - 10)};
+        const cuuint64_t strides[4] = {64, 16ull << g, 16ull << (g + 5), 16ull << (g + 10)};
+        const cuuint32_t box[5] = {8, 1, 32, 32, 1};
+        const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, state, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, stream_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) return fail(DTC_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
     return DTC_OK;
 }
@@ -912,6 +941,7 @@ int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
         const int ssb = (int)sizeof(StreamSmem) + 128;
         CUDA_TRY(cudaFuncSetAttribute(k_tile_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
         CUDA_TRY(cudaFuncSetAttribute(k_tile_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
         CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms[device], cudaDevAttrMultiProcessorCount, device));
         attr_set[device] = true;
     }
@@ -994,7 +1024,7 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
                 alignas(64) CUtensorMap tm;
                 memset(&tm, 0, sizeof(tm));
                 if (!S.contig) {
-                    const int rc = stream_tensor_map(&tm, state, h.n_local, S.g, n_traj);
+                    const int rc = stream_tensor_map(&tm, state, h.n_local, S.g, n_traj, S.mode);
                     if (rc != DTC_OK) return rc;
                 }
                 const unsigned sgrid = (unsigned)(grid < n_sms ? grid : n_sms);
@@ -1008,8 +1038,11 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
                 if (S.mode == 1)
                     k_tile_stream<1><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
                                                                            rdm_out, p->fused_local_bit);
-                else
+                else if (S.mode == 2)
                     k_tile_stream<2><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
+                                                                           rdm_out, p->fused_local_bit);
+                else
+                    k_tile_stream<3><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
                                                                            rdm_out, p->fused_local_bit);
                 continue;
             }
@@ -1116,6 +1149,12 @@ int dtc_program_readout(const dtc_program* p, const void* rdm, void* workspace, 
     k_readout_small<<<(unsigned)((n_traj + 63) / 64), 64, 0, (cudaStream_t)stream>>>(p->small, p->d_events, p->d_small_idx, p->n_small,
                                                                                     (const double2*)rdm, masks, fx, n_traj, probs);
     CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+int dtc_set_high_stride_bit(int bit) {
+    if (bit < 7 || bit > 62) return fail(DTC_ERR_INVALID, "high-stride bit must be in [7, 62]");
+    g_dtc_high_stride_bit = bit;
     return DTC_OK;
 }
 

@@ -102,3 +102,7 @@ def readout_small(prog, rdm, masks, fx):
     if rc != 0:
         raise ValueError(err.value.decode())
     return out
+
+
+def set_high_stride_bit(bit=15):
+    lib().emu_set_high_stride_bit(ctypes.c_int(bit))

@@ -81,9 +81,15 @@ static void emu_stream_pass(double2* state, const DtcStreamPass& P, const DtcLay
         for (int lane = 0; lane < 32; ++lane) stream_build2(lane, bl, P, L);
     }
     for (int lane = 0; lane < 32; ++lane) stream_build3(lane, bl, tab, P);
-    for (int t = 0; t < 128; ++t) stream_phase13<MODE>(t, stage.data(), P.t1, P.tb, M.rmA);
-    for (int t = 0; t < 128; ++t) stream_phase2(t, stage.data(), tab, P, M.rmA, M.rmB);
-    for (int t = 0; t < 128; ++t) stream_phase13<MODE>(t, stage.data(), P.t2, P.tb, M.rmB);
+    tab.rmA = M.rmA; tab.rmB = M.rmB;
+    if (MODE == 3) {
+        for (int t = 0; t < 128; ++t) stream_phaseC(t, stage.data(), tab, P, M.rmA, M.rmB);
+    } else {
+        constexpr int M13 = MODE == 3 ? 1 : MODE;
+        for (int t = 0; t < 128; ++t) stream_phase13<M13>(t, stage.data(), P.t1, P.tb, M.rmA);
+        for (int t = 0; t < 128; ++t) stream_phase2(t, stage.data(), tab, P, M.rmA, M.rmB);
+        for (int t = 0; t < 128; ++t) stream_phase13<M13>(t, stage.data(), P.t2, P.tb, M.rmB);
+    }
     for (int l = 0; l < DTC_TILE; ++l) st[gidx(l)] = stage[l];
 }
 
@@ -138,7 +144,8 @@ extern "C" int emu_run(int n_qubits, int n_layers, int64_t n_events, const int32
                 ++n_stream;
                 for (u64 b = 0; b < grid; ++b) {
                     if (S.mode == 1) emu_stream_pass<1>(st, S, P.layers.data(), masks.data(), n_traj, rank_bits, b, stage, *tab, *bl);
-                    else emu_stream_pass<2>(st, S, P.layers.data(), masks.data(), n_traj, rank_bits, b, stage, *tab, *bl);
+                    else if (S.mode == 2) emu_stream_pass<2>(st, S, P.layers.data(), masks.data(), n_traj, rank_bits, b, stage, *tab, *bl);
+                    else emu_stream_pass<3>(st, S, P.layers.data(), masks.data(), n_traj, rank_bits, b, stage, *tab, *bl);
                 }
                 continue;
             }
@@ -240,3 +247,5 @@ extern "C" int emu_readout_small(int n_qubits, int n_layers, int64_t n_events, c
                            probs_out + (t << m));
     return 0;
 }
+
+extern "C" void emu_set_high_stride_bit(int bit) { g_dtc_high_stride_bit = bit; }

@@ -191,3 +191,37 @@ def test_stream_engine_sharded_rank_bits():
         st = PI.materialize_frame(st, n_local, fx, fz, ph)
         ref = O.run_statevector(ops, n, init=rank << n_local)
         assert np.abs(st[0] - ref[rank << n_local:(rank + 1) << n_local]).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,noisy", [(17, True), (18, False)])
+def test_stream_engine_mode_c_high_stride_groups(n, noisy):
+    """Groups starting at the high-stride bit (lowered to 10 here) get five qubits and tiles of 2 KB runs (mode C)."""
+    rng = np.random.default_rng(40 + n)
+    c = dtcsim.QuantumCircuit(n, 0)
+    for layer in range(3):
+        for q in range(n):
+            c.rx(rng.uniform(-3, 3), q)
+        for q in range(n - 1):
+            c.rzz(rng.uniform(-3, 3), q, q + 1)
+        for q in range(n):
+            c.rz(rng.uniform(-3, 3), q)
+    nm = None
+    if noisy:
+        nm = dtcsim.NoiseModel()
+        nm.add_all_qubit_quantum_error(dtcsim.depolarizing_error(0.3, 1), ["rx"])
+    prog = compile_circuit(c, nm, reorder=False)
+    emu.set_high_stride_bit(10)
+    try:
+        rows, npass = emu.schedule(prog)
+        assert 3 in set(rows[:npass, 21]), rows[:npass, 21]          # mode C passes present
+        assert (rows[:npass, 21] > 0).all()
+        s2, fx2, fz2, ph2, _ = emu.run(prog, n_traj=2, seed=3, engine=2)
+        s3, fx3, fz3, ph3, n_stream = emu.run(prog, n_traj=2, seed=3, engine=3)
+    finally:
+        emu.set_high_stride_bit(15)
+    assert n_stream == npass
+    assert np.abs(s2 - s3).max() < 1e-13
+    ops = RC.ops_of(c)
+    if not noisy:
+        psi = PI.materialize_frame(s3, prog.n, fx3, fz3, ph3)
+        assert np.abs(psi[0] - O.run_statevector(ops, n)).max() < 1e-11

@@ -473,3 +473,39 @@ def test_wide_measurement_ideal_and_noisy(disorder):
     want = np.array([np.mean(np.sum(np.abs(psin) ** 2 * (1 - 2 * ((idx >> q) & 1)), axis=1)) for q in range(L)])
     assert np.abs(np.array(resn.expectation_z()) - want).max() < 1e-10
     assert sum(resn.get_counts().values()) == ntraj
+
+
+@pytest.mark.parametrize("n,ntraj", [(17, 5), (19, 2)])
+def test_stream_engine_mode_c_high_stride_groups(ctx, n, ntraj):
+    """Groups starting at the high-stride bit (lowered to 10 here; 15 in production) get five qubits and tiles of 32 runs of
+    2 KB (4-D tensor map, one in-place phase): against the register-fed kernel and the oracle."""
+    from dtcsim import backend, capi
+    rng = np.random.default_rng(50 + n)
+    c = dtcsim.QuantumCircuit(n, 0)
+    for layer in range(3):
+        for q in range(n):
+            c.rx(rng.uniform(-3, 3), q)
+        for q in range(n - 1):
+            c.rzz(rng.uniform(-3, 3), q, q + 1)
+        for q in range(n):
+            c.rz(rng.uniform(-3, 3), q)
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_quantum_error(dtcsim.depolarizing_error(0.3, 1), ["rx"])
+    prog = compile_circuit(c, nm, reorder=False)
+    capi.set_high_stride_bit(10)
+    try:
+        h = capi.ProgramHandle(prog, 0)
+        assert h.num_stream_passes == h.num_passes
+        capi.set_stream_engine(False)
+        a = backend.evolve(ctx, prog, ntraj, 2, 9, handle=h)
+        sa = a.state.clone()
+        capi.set_stream_engine(True)
+        b = backend.evolve(ctx, prog, ntraj, 2, 9, handle=h)
+        assert float((sa - b.state).abs().max()) < 1e-13
+        psi = PI.to_circuit_order(b.materialize().cpu().numpy(), prog)
+    finally:
+        capi.set_stream_engine(None)
+        capi.set_high_stride_bit(15)
+    oc, na, _ = O.compact_ops(RC.ops_of(c), n)
+    ref = O.run_trajectories(oc, na, O.PauliNoise.depolarizing(0.3, names=("rx",)), 9, np.arange(2, 2 + ntraj))
+    assert np.abs(psi - ref).max() < AMP_TOL
