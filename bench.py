@@ -126,6 +126,7 @@ def cpu_sample(hs, phis, sample_points, seed=1234):
     from oracle import c_oracle as CO
     from oracle import dtc_circuits as C
     from oracle import oracle as O
+    CO.set_threads()                                  # all host cores, whatever OMP_NUM_THREADS the launcher exported
     noise = O.PauliNoise.depolarizing(P_NOISE)
     buf = np.empty(1 << (L + 1), dtype=np.complex128)
     jobs = []

@@ -33,6 +33,15 @@ def threads():
     return int(lib().orc_threads())
 
 
+def set_threads(n=None):
+    """Use n OpenMP threads (default: every host core this process may run on).  torchrun exports OMP_NUM_THREADS=1 to
+    its ranks; the CPU baseline of bench.py runs on rank 0 alone and should use the whole host."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_threads(ctypes.c_int(int(n)))
+    return threads()
+
+
 def encode(ops):
     """Compacted op tuples -> flat arrays for orc_run."""
     ops = [O._norm_op(o) for o in ops]
