@@ -225,3 +225,28 @@ def test_stream_engine_mode_c_high_stride_groups(n, noisy):
     if not noisy:
         psi = PI.materialize_frame(s3, prog.n, fx3, fz3, ph3)
         assert np.abs(psi[0] - O.run_statevector(ops, n)).max() < 1e-11
+
+
+def test_schedule_large_register_uses_2kb_run_tiles_for_high_groups():
+    """n_local = 31 (the sharded L = 34 run): groups [0,10) and [10,20) keep ten qubits (contiguous / 64 B-run tiles), the
+    qubits from bit 20 on are swept five at a time in tiles of 32 runs of 2 KB; every pass is eligible for k_tile_stream."""
+    rng = np.random.default_rng(7)
+    n = 31
+    c = dtcsim.QuantumCircuit(n, 0)
+    for layer in range(2):
+        for q in range(n):
+            c.rx(rng.uniform(-3, 3), q)
+        for q in range(n - 1):
+            c.rzz(rng.uniform(-3, 3), q, q + 1)
+        for q in range(n):
+            c.rz(rng.uniform(-3, 3), q)
+    prog = compile_circuit(c, None, reorder=False)
+    rows, npass = emu.schedule(prog)
+    rows = rows[:npass]
+    assert (rows[:, 21] > 0).all()
+    tiles = {tuple(int(x) for x in r[9:21]): int(r[21]) for r in rows}
+    assert tiles[tuple(range(12))] == 1
+    assert tiles[(0, 1) + tuple(range(10, 20))] == 2
+    for g in (20, 25, 26):
+        assert tiles[tuple(range(7)) + tuple(range(g, g + 5))] == 3
+    assert len(tiles) == 5
