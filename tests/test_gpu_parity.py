@@ -509,3 +509,29 @@ def test_stream_engine_mode_c_high_stride_groups(ctx, n, ntraj):
     oc, na, _ = O.compact_ops(RC.ops_of(c), n)
     ref = O.run_trajectories(oc, na, O.PauliNoise.depolarizing(0.3, names=("rx",)), 9, np.arange(2, 2 + ntraj))
     assert np.abs(psi - ref).max() < AMP_TOL
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_engines_agree_on_random_circuits(ctx, seed):
+    """Fuzz: general gate sets, odd tile shapes, mixed eligible / ineligible passes -- k_tile_stream wherever the planner
+    allows it against k_tile_pass everywhere, same frames, psi' within 1e-12."""
+    from dtcsim import backend, capi
+    rng = np.random.default_rng(900 + seed)
+    n = 12 + seed % 6
+    circ = _random_circuit(rng, n, 50 + 5 * seed)
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_quantum_error(dtcsim.depolarizing_error(0.2, 1), ["u1", "u2", "u3", "h"])
+    prog = compile_circuit(circ, nm)
+    h = capi.ProgramHandle(prog, 0, capi.ENGINE_TILE)
+    ntraj = 1 + seed % 4
+    try:
+        capi.set_stream_engine(False)
+        a = backend.evolve(ctx, prog, ntraj, 1, seed, handle=h)
+        sa, fa = a.state.clone(), a.frames_host()
+        capi.set_stream_engine(True)
+        b = backend.evolve(ctx, prog, ntraj, 1, seed, handle=h)
+        fb = b.frames_host()
+    finally:
+        capi.set_stream_engine(None)
+    assert all(np.array_equal(x, y) for x, y in zip(fa, fb))
+    assert float((sa - b.state).abs().max()) < 1e-12
