@@ -15,7 +15,8 @@ def test_c2_bookkeeping():
 
 
 def test_reference_arm_json_line(monkeypatch, capsys):
-    monkeypatch.setattr(bench, "CPU_SAMPLE", [(1, False), (1, True)])       # 3 periods instead of 85: seconds, not minutes
+    monkeypatch.setattr(bench, "CPU_SAMPLE", [(1, False), (1, True)])       # 3 periods instead of 510: seconds, not minutes
+    monkeypatch.setattr(bench, "CPU_TRAJ", 1)
     monkeypatch.delenv("RANK", raising=False)
     args = argparse.Namespace(gpus=1, steps=1, warmup=1, tmax=30, trajectories=1024)
     bench.run_reference(args)
