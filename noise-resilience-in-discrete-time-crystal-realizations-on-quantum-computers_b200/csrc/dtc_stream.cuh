@@ -168,6 +168,39 @@ DTC_HD void stream_phase2(int t, double2* tile, const StreamSlot& tab, const Dtc
     for (int r = 0; r < DTC_NREG; ++r) p[r << 3] = a[r];
 }
 
+// Phase 2 of a pass that lacks one of its three parts (first / last pass of a circuit, rotation-only sweeps of large
+// registers): the absent parts are skipped instead of being executed with zero angles / identity tables.  Kept out of
+// stream_phase2 so that the register allocation of the hot path (all three parts present) is not disturbed.
+DTC_HD void stream_phase2_partial(int t, double2* tile, const StreamSlot& tab, const DtcStreamPass& P, u64 rmA, u64 rmB) {
+    double2 a[DTC_NREG];
+    double2* p = tile + stream_chunk2(t, 0);
+#pragma unroll
+    for (int r = 0; r < DTC_NREG; ++r) a[r] = p[r << 3];
+    if (P.layerA >= 0) {
+        double tA[5];
+        tile_signed_t(P.t1, P.tb, 3, rmA, tA);
+        tile_rot_bits(a, tA, 0, 5);
+    }
+    if (P.layerD >= 0) {
+        const int lane = t & 31, l2 = (lane >> 2) & 1, l8 = (lane >> 3) & 1;
+        const double2 cf0 = cmul(tab.T2[t], tab.F[l2][0]), cf1 = cmul(tab.T2[t], tab.F[l2][1]);
+        const double2 c00 = cmul(cf0, tab.G[l8][0]), c01 = cmul(cf1, tab.G[l8][0]);
+        const double2 c10 = cmul(cf0, tab.G[l8][1]), c11 = cmul(cf1, tab.G[l8][1]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            a[i] = cmul(a[i], cmul(tab.T1c[i], (i & 1) ? c01 : c00));
+            a[i | 16] = cmul(a[i | 16], cmul(tab.T1c[i | 16], (i & 1) ? c11 : c10));
+        }
+    }
+    if (P.layerB >= 0) {
+        double tB[5];
+        tile_signed_t(P.t2, P.tb, 3, rmB, tB);
+        tile_rot_bits(a, tB, 0, 5);
+    }
+#pragma unroll
+    for (int r = 0; r < DTC_NREG; ++r) p[r << 3] = a[r];
+}
+
 // mode C: the only phase.  Thread t <-> passive local bits 0..6, registers <-> local bits 7..11; phase = T1c[r] * T2[t].
 DTC_HD void stream_phaseC(int t, double2* tile, const StreamSlot& tab, const DtcStreamPass& P, u64 rmA, u64 rmB) {
     double tA[5], tB[5];
@@ -177,17 +210,13 @@ DTC_HD void stream_phaseC(int t, double2* tile, const StreamSlot& tab, const Dtc
     double2* p = tile + t;
 #pragma unroll
     for (int r = 0; r < DTC_NREG; ++r) a[r] = p[r << 7];
-    tile_rot_bits(a, tA, 0, 4);
     const double2 c = tab.T2[t];
+    if (P.layerA >= 0) tile_rot_bits(a, tA, 0, 5);
+    if (P.layerD >= 0) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        rot_pair(a[i], a[i | 16], tA[4]);
-        a[i] = cmul(a[i], cmul(tab.T1c[i], c));
-        a[i | 16] = cmul(a[i | 16], cmul(tab.T1c[i | 16], c));
-        rot_pair(a[i], a[i | 16], tB[4]);
-        DTC_SCHED_FENCE();
+        for (int r = 0; r < DTC_NREG; ++r) a[r] = cmul(a[r], cmul(tab.T1c[r], c));
     }
-    tile_rot_bits(a, tB, 0, 4);
+    if (P.layerB >= 0) tile_rot_bits(a, tB, 0, 5);
 #pragma unroll
     for (int r = 0; r < DTC_NREG; ++r) p[r << 7] = a[r];
 }

@@ -225,6 +225,11 @@ __device__ __noinline__ void stream_phase13_call(int t, double2* tile, double t0
     stream_phase13_signed<MODE>(t, tile, tt);
 }
 
+__device__ __noinline__ void stream_phase2_partial_call(int t, double2* tile, const StreamSlot* tab, const DtcStreamPass* P,
+                                                         u64 rmA, u64 rmB) {
+    stream_phase2_partial(t, tile, *tab, *P, rmA, rmB);
+}
+
 struct StreamSmem {
     double2 stage[DTC_STREAM_STAGES][DTC_TILE];
     StreamSlot slot[DTC_STREAM_STAGES];
@@ -373,15 +378,20 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
         } else {
             constexpr int M13 = MODE == 3 ? 1 : MODE;
             double tt[5];
-            stream_signed_s1<M13>(P.t1, P.tb, rmA, tt);
-            stream_phase13_call<M13>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+            if (P.layerA >= 0) {                   // no rotations of layer j in this pass: nothing to do on S1 before the diagonal
+                stream_signed_s1<M13>(P.t1, P.tb, rmA, tt);
+                stream_phase13_call<M13>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+            }
             if (MODE == 1) __syncwarp(); else wg_barrier(wg);
             PROF_LAP(1);
-            stream_phase2(t, tile, slot, P, rmA, rmB);
+            if (P.layerA >= 0 && P.layerD >= 0 && P.layerB >= 0) stream_phase2(t, tile, slot, P, rmA, rmB);
+            else stream_phase2_partial_call(t, tile, &slot, &P, rmA, rmB);
             if (MODE == 1) __syncwarp(); else wg_barrier(wg);
             PROF_LAP(2);
-            stream_signed_s1<M13>(P.t2, P.tb, rmB, tt);
-            stream_phase13_call<M13>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+            if (P.layerB >= 0) {
+                stream_signed_s1<M13>(P.t2, P.tb, rmB, tt);
+                stream_phase13_call<M13>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+            }
         }
         if (rdm_out) {
             wg_barrier(wg);

@@ -86,9 +86,15 @@ static void emu_stream_pass(double2* state, const DtcStreamPass& P, const DtcLay
         for (int t = 0; t < 128; ++t) stream_phaseC(t, stage.data(), tab, P, M.rmA, M.rmB);
     } else {
         constexpr int M13 = MODE == 3 ? 1 : MODE;
-        for (int t = 0; t < 128; ++t) stream_phase13<M13>(t, stage.data(), P.t1, P.tb, M.rmA);
-        for (int t = 0; t < 128; ++t) stream_phase2(t, stage.data(), tab, P, M.rmA, M.rmB);
-        for (int t = 0; t < 128; ++t) stream_phase13<M13>(t, stage.data(), P.t2, P.tb, M.rmB);
+        if (P.layerA >= 0)
+            for (int t = 0; t < 128; ++t) stream_phase13<M13>(t, stage.data(), P.t1, P.tb, M.rmA);
+        const bool all3 = P.layerA >= 0 && P.layerD >= 0 && P.layerB >= 0;
+        for (int t = 0; t < 128; ++t) {
+            if (all3) stream_phase2(t, stage.data(), tab, P, M.rmA, M.rmB);
+            else stream_phase2_partial(t, stage.data(), tab, P, M.rmA, M.rmB);
+        }
+        if (P.layerB >= 0)
+            for (int t = 0; t < 128; ++t) stream_phase13<M13>(t, stage.data(), P.t2, P.tb, M.rmB);
     }
     for (int l = 0; l < DTC_TILE; ++l) st[gidx(l)] = stage[l];
 }
