@@ -115,36 +115,38 @@ DTC_HD double philox_uniform(u64 seed, uint32_t index, uint32_t stream, u64 traj
 // ------------------------------------------------------------------------------------ frames
 // Walk the event list for one trajectory; masks[(layer*4+m)*mstride] |= bits; returns final frame.
 // m = 0: rotation sign bits (bit q), 1/2: D1 slot 0/1 (bit q), 3: D2 (bit = term index).
+// one event of the walk; the frame (fx, fz, ph) is carried by the caller
+DTC_HD void frame_step(const DtcEvent& E, u64 traj_global, u64 seed, u64* masks, int64_t mstride, u64& fx, u64& fz, int& ph) {
+    const int q = E.q0;
+    if (E.type == DTC_EVT_ROT) {
+        if (E.slot == 0 && ((fz >> q) & 1ull)) masks[(int64_t)(E.layer * 4 + 0) * mstride] |= 1ull << q;
+        if (E.k & 1) fx ^= 1ull << q;
+        ph += 3 * E.k;
+    } else if (E.type == DTC_EVT_D1) {
+        if ((fx >> q) & 1ull) masks[(int64_t)(E.layer * 4 + 1 + E.slot) * mstride] |= 1ull << q;
+    } else if (E.type == DTC_EVT_D2 || E.type == DTC_EVT_D2C) {
+        if (((fx >> q) ^ (fx >> E.q1)) & 1ull) masks[(int64_t)(E.layer * 4 + 3) * mstride] |= 1ull << E.slot;
+    } else {
+        const double u = philox_uniform(seed, (uint32_t)E.slot, 0u, traj_global);
+        const int fxq = (int)((fx >> q) & 1ull);
+        if (u < E.c0) {                    // X
+            fx ^= 1ull << q;
+        } else if (u < E.c1) {             // Y = i X Z
+            ph += 1 + 2 * fxq;
+            fx ^= 1ull << q;
+            fz ^= 1ull << q;
+        } else if (u < E.c2) {             // Z
+            ph += 2 * fxq;
+            fz ^= 1ull << q;
+        }
+    }
+}
+
 DTC_HD void frame_walk(u64 traj_global, u64 seed, const DtcEvent* ev, int64_t n_events, u64* masks,
                        int64_t mstride, u64* fx_out, u64* fz_out, int* ph_out) {
     u64 fx = 0, fz = 0;
     int ph = 0;
-    for (int64_t e = 0; e < n_events; ++e) {
-        const DtcEvent E = ev[e];
-        const int q = E.q0;
-        if (E.type == DTC_EVT_ROT) {
-            if (E.slot == 0 && ((fz >> q) & 1ull)) masks[(int64_t)(E.layer * 4 + 0) * mstride] |= 1ull << q;
-            if (E.k & 1) fx ^= 1ull << q;
-            ph += 3 * E.k;
-        } else if (E.type == DTC_EVT_D1) {
-            if ((fx >> q) & 1ull) masks[(int64_t)(E.layer * 4 + 1 + E.slot) * mstride] |= 1ull << q;
-        } else if (E.type == DTC_EVT_D2 || E.type == DTC_EVT_D2C) {
-            if (((fx >> q) ^ (fx >> E.q1)) & 1ull) masks[(int64_t)(E.layer * 4 + 3) * mstride] |= 1ull << E.slot;
-        } else {
-            const double u = philox_uniform(seed, (uint32_t)E.slot, 0u, traj_global);
-            const int fxq = (int)((fx >> q) & 1ull);
-            if (u < E.c0) {                    // X
-                fx ^= 1ull << q;
-            } else if (u < E.c1) {             // Y = i X Z
-                ph += 1 + 2 * fxq;
-                fx ^= 1ull << q;
-                fz ^= 1ull << q;
-            } else if (u < E.c2) {             // Z
-                ph += 2 * fxq;
-                fz ^= 1ull << q;
-            }
-        }
-    }
+    for (int64_t e = 0; e < n_events; ++e) frame_step(ev[e], traj_global, seed, masks, mstride, fx, fz, ph);
     *fx_out = fx;
     *fz_out = fz;
     *ph_out = ph & 3;

@@ -72,12 +72,32 @@ struct dtc_program {
 };
 
 // ------------------------------------------------------------------------------------ kernels
+// The event list is the same for every trajectory: the block stages it through shared memory in chunks (coalesced loads)
+// and each thread walks its own trajectory's frame over the staged chunk.
+#define DTC_FRAMES_CHUNK 256
 __global__ void k_frames(const DtcEvent* __restrict__ ev, long long n_events, u64* __restrict__ masks,
                          long long n_traj, long long traj_offset, u64 seed, u64* __restrict__ fx,
                          u64* __restrict__ fz, int* __restrict__ ph) {
+    __shared__ DtcEvent sev[DTC_FRAMES_CHUNK];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_traj) return;
-    frame_walk((u64)(traj_offset + t), seed, ev, n_events, masks + t, n_traj, fx + t, fz + t, ph + t);
+    const bool live = t < n_traj;
+    u64 x = 0, z = 0;
+    int p = 0;
+    for (long long e0 = 0; e0 < n_events; e0 += DTC_FRAMES_CHUNK) {
+        const int n = (int)((n_events - e0 < DTC_FRAMES_CHUNK) ? n_events - e0 : DTC_FRAMES_CHUNK);
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(ev + e0);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(sev);
+        for (int i = threadIdx.x; i < n * (int)(sizeof(DtcEvent) / 8); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        if (live)
+            for (int e = 0; e < n; ++e) frame_step(sev[e], (u64)(traj_offset + t), seed, masks + t, n_traj, x, z, p);
+        __syncthreads();
+    }
+    if (live) {
+        fx[t] = x;
+        fz[t] = z;
+        ph[t] = p & 3;
+    }
 }
 
 __global__ void k_init_basis(double2* __restrict__ state, int n_local, long long n_traj, u64 index) {
