@@ -380,7 +380,7 @@ class DTCSimulator:
         t0 = time.time()
         torch = self.ctx.torch
         ctx = self.ctx
-        prog0 = compile_circuit(circ, nm, want_dm=False, optimize=self.optimize)
+        prog0 = self._compiled(circ, nm)
         n = prog0.n
         method = self._choose_method(method, n, shots, nm)
         meas = prog0.measures
@@ -478,6 +478,24 @@ class DTCSimulator:
 
             return finish
         return self._experiment(vals, data, prog0, name or circ.name, shots, seed, t0)
+
+    def _compiled(self, circ, nm):
+        """compile_circuit() with a small cache keyed by the circuit's op list and the noise model: sweeps that run the
+        same circuit again (other seeds, other shot counts: shots.py:49) skip the host compile."""
+        noise_key = None
+        if nm is not None:
+            noise_key = (tuple(sorted((k, e.probs) for k, e in nm._all.items())),
+                         tuple(sorted((k, e.probs) for k, e in nm._local.items())))
+        key = (circ.num_qubits, circ.num_clbits, float(circ.global_phase), self.optimize, noise_key,
+               tuple(op.astuple() for op in circ.ops))
+        cache = self.__dict__.setdefault("_prog_cache", {})
+        prog = cache.get(key)
+        if prog is None:
+            prog = compile_circuit(circ, nm, want_dm=False, optimize=self.optimize)
+            if len(cache) >= 128:
+                cache.pop(next(iter(cache)))
+            cache[key] = prog
+        return prog
 
     def _state_buffer(self, n_amps):
         """One state buffer per simulator object, grown on demand (stream-ordered reuse across pipelined circuits)."""

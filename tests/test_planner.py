@@ -265,3 +265,21 @@ def test_inverse_is_inverse():
     full.append(c.inverse(), range(3))
     psi = O.run_statevector(RC.ops_of(full), 3)
     assert abs(abs(psi[0]) - 1) < 1e-12
+
+
+def test_backend_program_cache(disorder):
+    """run() compiles a circuit once per (op list, noise model): a second run of the same circuit reuses the program."""
+    import refcircuits as RC
+    hs, phis = disorder[20][0][0][:6], disorder[20][1][0][:5]
+    c1 = RC.transpiled(RC.qc_body("vacuum", 6, 0.97, hs, phis, 2, 3, True))
+    c2 = RC.transpiled(RC.qc_body("vacuum", 6, 0.97, hs, phis, 2, 3, True))       # equal content, different object
+    c3 = RC.transpiled(RC.qc_body("vacuum", 6, 0.84, hs, phis, 2, 3, True))
+    nm = dtcsim.as_noise_model(RC.noise_model(0.05))
+    nm2 = dtcsim.as_noise_model(RC.noise_model(0.1))
+    sim = dtcsim.AerSimulator()
+    p1 = sim._compiled(dtcsim.as_circuit(c1), nm)
+    assert sim._compiled(dtcsim.as_circuit(c2), nm) is p1
+    assert sim._compiled(dtcsim.as_circuit(c3), nm) is not p1
+    assert sim._compiled(dtcsim.as_circuit(c1), nm2) is not p1
+    assert sim._compiled(dtcsim.as_circuit(c1), None) is not p1
+    assert len(sim._prog_cache) == 4
