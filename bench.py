@@ -174,9 +174,219 @@ def workload_config(args):
                         f"autocorr t=0..{args.tmax - 1} ({2 * args.tmax} circuits), {args.trajectories} Pauli trajectories each",
             "tmax": args.tmax, "trajectories": args.trajectories, "state_bytes_n21": 16 << (L + 1),
             "register": "ancilla factorised out of the device register (n = 20, 16 MiB per trajectory); see DESIGN.md",
-            "l2_policy": "inputs larger than L2: each sweep streams trajectories x 32 MiB states",
+            "l2_policy": f"inputs larger than L2: every launch streams the whole batch ({args.trajectories} trajectories x "
+                         f"{(16 << L) >> 20} MiB states of the n = {L} register = {(args.trajectories * (16 << L)) >> 30} GiB) once",
             "parallelism": f"disorder instances x{args.gpus} (weak), allreduce of sums"}
 
+
+
+# ------------------------------------------------------------------------------------------ extra legs (sub-records)
+def strong_leg(args, ctx, dist, rank, world, progs, handles, state, bt, points):
+    """Strong scaling on the SAME job: config C2 on ONE disorder instance, the 1024 trajectories of every circuit split
+    over the ranks (dist.shard_range; global Philox trajectory ids, so the counts equal the 1-GPU run), one all-reduce.
+    Launches shrink by the number of ranks, so k_frames, the read-out kernels and the host enqueue weigh more."""
+    import torch
+    from dtcsim import backend, dist as D
+    NT = args.trajectories
+    a0, b0 = D.shard_range(NT, rank, world)
+    sums = torch.zeros(len(points), 2, dtype=torch.float64, device=ctx.device)
+
+    def step(seed):
+        sums.zero_()
+        pending = []
+        for i, (prog, h) in enumerate(zip(progs, handles)):
+            for a in range(a0, b0, bt):
+                nt = min(bt, b0 - a)
+                batch = backend.evolve(ctx, prog, nt, a, seed + i, handle=h, state=state, fused_rdm=True)
+                pending.append((i, batch, batch.readout_rdm() if prog.small else None))
+        for i, batch, rdm in pending:
+            pr = batch.outcome_probs(rdm)
+            ez = pr[:, 0] - pr[:, 1]
+            sums[i, 0] += ez.sum()
+            sums[i, 1] += (ez * ez).sum()
+        dist.all_reduce(sums)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    step(900)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    step(1234)
+    enq = time.perf_counter() - t0                      # host time to enqueue the whole step
+    e1.record()
+    sync_all()
+    sweep_ms = 0.0
+    for h, prog in zip(handles, progs):
+        if prog.n_main >= 12:
+            sweep_ms += h.pass_time()[0]
+    ms = torch.tensor([e0.elapsed_time(e1), sweep_ms, enq * 1e3], dtype=torch.float64, device=ctx.device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step, sweep_ms, enq_ms = (float(x) for x in ms.tolist())
+    periods = periods_of(points) * NT
+    return {"scaling": "strong", "workload": "C2 on one disorder instance, trajectories of each circuit split over the ranks",
+            "value": periods / (ms_step * 1e-3), "unit": "periods/s", "ms_per_step": ms_step, "steps": 1,
+            "trajectories_per_rank": b0 - a0,
+            "sweep_kernels_ms": sweep_ms, "non_sweep_share": max(0.0, 1.0 - sweep_ms / ms_step),
+            "host_enqueue_ms": enq_ms,
+            "note": "non_sweep_share = 1 - (k_tile_stream time / step time): k_frames, read-out kernels, launch gaps, all-reduce"}
+
+
+def sharded_circuit(dtcsim, L, g, hs, phis, t, echo):
+    """dtc_qasm.py:70-91 circuit shape (L qubits, no ancilla): t periods, optionally followed by their inverse."""
+    c = dtcsim.QuantumCircuit(L, L)
+    uf = dtcsim.QuantumCircuit(L)
+    for i in range(L):
+        uf.rx(np.pi * g, i)
+    for i in range(0, L - 1, 2):
+        uf.rzz(phis[i], i, i + 1)
+    for i in range(1, L - 1, 2):
+        uf.rzz(phis[i], i, i + 1)
+    for i in range(L):
+        uf.rz(hs[i], i)
+    for _ in range(t):
+        c.append(uf, range(L))
+    if echo:
+        inv = uf.inverse()
+        for _ in range(t):
+            c.append(inv, range(L))
+    c.measure_all()
+    return dtcsim.lower_level0(c)
+
+
+def sharded_leg(args, dist, rank, world, local, hbm_peak):
+    """Config C5: one statevector of L = 31 + log2(P) qubits sharded on its top log2(P) qubits (32 GiB per GPU), 10 periods
+    forward + 10 inverse (so every <Z_q> must return to +1 exactly), and an L = 22 noisy trajectory against the C oracle."""
+    import torch
+    import dtcsim
+    from dtcsim import sharded
+    g = int(round(np.log2(world)))
+    out = {}
+
+    def allred_on(dev):
+        def f(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            dist.all_reduce(t)
+            return t.cpu().numpy()
+        return f
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity at a size the oracle finishes in seconds: L = 22, one noisy trajectory, vs the gate-by-gate C oracle
+    Lc = 22
+    rng = np.random.default_rng(Lc)
+    hs = rng.random(Lc) * 2 * np.pi - np.pi                      # generate_disorder.py:16-18
+    phis = rng.random(Lc - 1) * np.pi - 1.5 * np.pi
+    circ = sharded_circuit(dtcsim, Lc, 0.97, hs, phis, 3, False)
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_quantum_error(dtcsim.depolarizing_error(0.05, 1), ["u1", "u2", "u3"], warnings=False)
+    eng = sharded.CudaShardEngine(Lc, Lc - g, rank, world, local)
+    res = sharded.ShardedStatevector(Lc, rank, world, eng, all_reduce=allred_on(eng.ctx.device)).run(circ, nm, seed=1234, trajectory=3)
+    transport = eng.transport
+    eng.close()
+    del eng
+    dev = torch.zeros(1, dtype=torch.float64, device=torch.device("cuda", local))
+    if rank == 0:
+        from oracle import c_oracle as CO
+        from oracle import oracle as O
+        oc, na, _ = O.compact_ops([o.astuple() for o in circ.ops], Lc)
+        psi = CO.run_trajectory(oc, na, O.PauliNoise.depolarizing(0.05), 1234, 3)
+        p = np.abs(psi) ** 2
+        idx = np.arange(1 << Lc)
+        want = np.array([np.sum(p * (1.0 - 2.0 * ((idx >> q) & 1))) for q in range(Lc)])
+        dev[0] = float(np.abs(want - np.array(res["expect_z"])).max())
+    dist.all_reduce(dev)
+    out["oracle_max_dev"] = float(dev.item())
+    out["oracle_check"] = f"L={Lc} noisy trajectory (p=0.05, 3 periods), <Z_q> of all qubits vs the gate-by-gate C oracle"
+
+    # ---- the timed run
+    L = 31 + g
+    nl = L - g
+    rng = np.random.default_rng(34)
+    hs = rng.random(L) * 2 * np.pi - np.pi
+    phis = rng.random(L - 1) * np.pi - 1.5 * np.pi
+    torch.cuda.empty_cache()
+    eng = sharded.CudaShardEngine(L, nl, rank, world, local)
+    allred = allred_on(eng.ctx.device)
+    sharded.ShardedStatevector(L, rank, world, eng, all_reduce=allred).run(sharded_circuit(dtcsim, L, 0.97, hs, phis, 1, True))
+    T = args.sharded_periods
+    circ = sharded_circuit(dtcsim, L, 0.97, hs, phis, T, True)
+    sv = sharded.ShardedStatevector(L, rank, world, eng, all_reduce=allred)
+    eng.passes = 0
+    eng.passes_weighted = 0.0
+    eng.sliced_exchanges = 0
+    sync_all()
+    t0 = time.perf_counter()
+    res = sv.run(circ)
+    sync_all()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=eng.ctx.device)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    ez = np.array(res["expect_z"])
+    periods = 2 * T
+    shard_bytes = 16 << nl
+    wire = shard_bytes * (world - 1) // world
+    t_hbm = 2 * shard_bytes / (hbm_peak * 1e9)               # one read + one write of the shard per period
+    t_link = wire / 770e9                                    # measured NVLink peer-copy bandwidth per direction
+    out.update({"workload": f"C5: L={L} statevector sharded on its top {g} qubits ({shard_bytes >> 30} GiB per GPU), "
+                            f"{T} periods forward + {T} inverse, complex128",
+                "value": periods / dt, "unit": "periods/s", "seconds": dt, "ms_per_period": 1e3 * dt / periods,
+                "norm": res["norm"], "echo_max_dev": float(np.abs(ez - 1).max()),
+                "state_sweeps_per_period": eng.passes_weighted / periods, "exchanges": sv.stats["exchanges"],
+                "exchanges_overlapped_with_sweeps": eng.sliced_exchanges, "transport": transport,
+                "exchange_gbs_per_rank_per_direction": sv.stats["exchange_bytes_per_rank"] / dt / 1e9,
+                "hbm_algorithmic_gbs_per_rank": eng.passes_weighted * 2 * shard_bytes / dt / 1e9,
+                "floor_ms_per_period": {"hbm": 1e3 * t_hbm, "nvlink_770": 1e3 * t_link},
+                "frac_of_floor": max(t_hbm, t_link) / (dt / periods),
+                "timer": "wall clock between barriers, max over ranks (includes the final <Z> reduction)"})
+    out["ok"] = bool(abs(res["norm"] - 1) < 1e-9 and np.abs(ez - 1).max() < 1e-9 and out["oracle_max_dev"] < 1e-10)
+    eng.close()
+    del eng, sv
+    torch.cuda.empty_cache()
+    return out
+
+
+def sweep_leg(args, ctx, dist, rank, world, noise):
+    """Config C4 through the product front-end dtcsim.run_sweep: g values (generate_params.py:6) x polarisations
+    (pol.py:336) x t x echo on disorder row 0, points dealt over the ranks, one all-reduce."""
+    import torch
+    import dtcsim
+    from dtcsim import sweeps
+    g_list = list(sweeps.G_GRID) if args.sweep_g == "grid" else [float(x) for x in args.sweep_g.split(",")]
+    pols = args.sweep_pol.split(",")
+    hs, phis = load_disorder(0)
+    sim = dtcsim.AerSimulator(noise_model=noise, device="GPU", cuStateVec_enable=True, cuda_device=ctx.index)
+    t_values = list(range(args.sweep_tmax))
+    rec = {}
+    for pol in pols:                                  # one call per polarisation so that passes / period can be reported
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        r = dtcsim.run_sweep(sim, L, g_list, hs[None, :], phis[None, :], t_values, (False, True), (pol,), shots=args.trajectories,
+                             seed_simulator=1234, rank=rank, world=world)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        dt = time.perf_counter() - t0
+        c = sweeps.autocorr_circuit(L, g_list[0], hs, phis, 4, echo=False, polarization=pol)
+        prog = dtcsim.compile_circuit(c, dtcsim.as_noise_model(noise), optimize=True)
+        from dtcsim import capi
+        h = capi.ProgramHandle(prog, ctx.index)
+        rec[pol] = {"periods_per_s": r["periods"] / dt, "seconds": dt, "points": r["points"],
+                    "sweeps_per_period_t4": h.num_passes / 4.0,
+                    "autocorr_g0_t1": float(r["mean"][0, 0, 0, 1]) if len(t_values) > 1 else None}
+        h.close()
+    return {"workload": f"C4: L=20, g in {g_list}, pol in {pols}, t=0..{args.sweep_tmax - 1} forward+echo, "
+                        f"{args.trajectories} trajectories per point, points dealt over {world} rank(s)",
+            "by_polarization": rec}
 
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
@@ -280,11 +490,14 @@ def run_ours(args):
     roof = None
     n_stream = int(sum(h.num_stream_passes for h in handles))
     n_pass_all = int(sum(h.num_passes for h in handles))
-    traffic = None
+    traffic, traffic_src = None, None
     tf = os.path.join(ROOT, "profiles", "ncu_tile_stream_traffic.json")      # from the committed ncu --set full capture
     if os.path.exists(tf):
         with open(tf) as fh:
-            traffic = float(json.load(fh)["dram_bytes_per_algorithmic_byte"]) * bytes_per_launch   # per full-traffic launch
+            tj = json.load(fh)
+        traffic = float(tj["dram_bytes_per_algorithmic_byte"]) * bytes_per_launch   # per full-traffic launch
+        traffic_src = ("not measured in this run: DRAM bytes / algorithmic byte of the committed ncu --set full capture "
+                       f"({tj.get('source', 'profiles/')}) x this run's bytes_per_launch")
     if pass_n:
         avg_ms = pass_ms / pass_n
         # algorithmic bytes of the timed launches: a full pass reads and writes the batch once; the first pass of a
@@ -296,8 +509,7 @@ def run_ours(args):
                 "stream_passes": n_stream, "passes": n_pass_all, "avg_launch_ms": avg_ms, "launches_timed": pass_n,
                 "bytes_per_launch": bytes_per_launch, "half_traffic_launches": half_passes,
                 "algorithmic_bytes_timed": alg_bytes, "peak_source": peak_src,
-                "register_qubits": nmax,
-                "periods_frac_n21_model": (value / world) * (2 * 16 * (1 << (L + 1))) / (peak * 1e9),
+                "register_qubits": nmax, "traffic_source": traffic_src,
                 "periods_frac_actual_register": (value / world) * (2 * 16 * (1 << nmax)) / (peak * 1e9)}
 
     # ---- end to end through the public API (host circuits in, counts out)
@@ -314,6 +526,9 @@ def run_ours(args):
 
         e2e_pass(77)
         sync_all()
+        # the timed pass pays the host compile of every circuit, as a real sweep does (it never repeats a circuit):
+        # drop the programs the warm-up pass left in the simulator's cache
+        sim.__dict__.get("_prog_cache", {}).clear()
         t0 = time.perf_counter()
         res = e2e_pass(1234)
         sync_all()
@@ -321,9 +536,27 @@ def run_ours(args):
         if dist is not None:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": periods_step / float(dt.item()), "unit": "periods/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "seconds": float(dt.item()), "timer": "host wall clock around one run(list of circuits) call + get_counts",
+               "d2h_bytes_per_step": int(d2h), "seconds": float(dt.item()), "timer": "host wall clock around one run(list of 60 host circuits) call + get_counts; program cache cleared first, "
+                        "so the host compile, table upload, frames, sweeps, read-out and the device->host copies are all inside",
                "autocorr_t1": res[1] if len(res) > 1 else None}
 
+    extra = {}
+    if world > 1 and not args.no_strong:
+        extra["strong"] = strong_leg(args, ctx, dist, rank, world, progs, handles, state, bt, points)
+    if args.sweep_g:
+        extra["c4_sweep"] = sweep_leg(args, ctx, dist, rank, world, noise)
+    if world > 1 and not args.no_sharded:
+        # the C2 buffers go first: the sharded state takes 64 GiB per GPU
+        for h in handles:
+            h.close()
+        del state, sums
+        if not args.no_e2e:
+            sim._state = None
+        torch.cuda.empty_cache()
+        try:
+            extra["sharded"] = sharded_leg(args, dist, rank, world, local, peak)
+        except Exception as exc:                      # the headline line must still be printed
+            extra["sharded"] = {"error": repr(exc)[:400]}
     if rank == 0:
         cpu = None
         if not args.no_cpu:
@@ -336,6 +569,7 @@ def run_ours(args):
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
                 "passes_per_sweep": int(sum(h.num_passes for h in handles)), "periods_per_sweep": periods_of(points),
                 "autocorr_forward_t1_t2": [float(autocorr[1]), float(autocorr[2])] if args.tmax > 2 else None}
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -351,6 +585,12 @@ def main():
     ap.add_argument("--tmax", type=int, default=30, help="sweep t = 0..tmax-1 (30 = BASELINE config)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-record")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded-statevector (C5) sub-record")
+    ap.add_argument("--sharded-periods", type=int, default=10, help="C5: periods forward (+ the same number inverse)")
+    ap.add_argument("--sweep-g", default="", help="C4 sub-record: 'grid' (generate_params.py:6) or comma-separated g values")
+    ap.add_argument("--sweep-pol", default="x,y,xy,yx", help="C4 sub-record: polarisations (pol.py:336)")
+    ap.add_argument("--sweep-tmax", type=int, default=10, help="C4 sub-record: t = 0..tmax-1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -104,6 +104,9 @@ int dtc_set_stream_engine(int enable);
  * tests lower it to exercise that path on small registers. */
 int dtc_set_high_stride_bit(int bit);
 int dtc_program_num_stream_passes(const dtc_program *p, int *n_passes);
+/* Persistent CTAs k_tile_stream launches (default 0 = one per SM).  A smaller grid leaves SMs to kernels that must run
+ * at the same time on other streams (NCCL send/recv while a sharded state is exchanged, sharded.py). */
+int dtc_set_stream_ctas(int n_ctas);
 
 /* Kernel timing for roofline accounting: when enabled, dtc_program_run() brackets its pass loop with
  * CUDA events on the launching stream; dtc_program_pass_time() waits for the last run and returns the

@@ -312,7 +312,7 @@ class DTCSimulator:
         self.max_memory_bytes = max_memory_bytes
         self.optimize = bool(optimize)       # read-out factorisation (plan.compile_circuit(optimize=True))
         self.engine = {"auto": capi.ENGINE_AUTO, "generic": capi.ENGINE_GENERIC, "tile": capi.ENGINE_TILE}[engine]
-        self.options = dict(device=device, cuStateVec_enable=cuStateVec_enable, **ignored)
+        self.sim_options = dict(device=device, cuStateVec_enable=cuStateVec_enable, **ignored)   # accepted, unused
         self._ctx = None
 
     def set_options(self, **kw):
@@ -322,7 +322,7 @@ class DTCSimulator:
             elif k == "shots":
                 self.default_shots = v
             else:
-                self.options[k] = v
+                self.sim_options[k] = v
 
     @property
     def ctx(self):
@@ -341,6 +341,12 @@ class DTCSimulator:
         seed = self.seed_simulator if seed_simulator is None else seed_simulator
         if seed is None:
             seed = int.from_bytes(os.urandom(6), "little")
+        if isinstance(seed, (list, tuple, np.ndarray)):          # one seed per circuit (sweeps.run_sweep)
+            if len(seed) != len(circ_list):
+                raise ValueError("seed_simulator list must have one entry per circuit")
+            seeds = [int(x) for x in seed]
+        else:
+            seeds = [int(seed) + i for i in range(len(circ_list))]
         nm = as_noise_model(self.noise_model if noise_model is None else noise_model)
         method = self.method if method is None else method
         # A list of circuits is pipelined: circuit i+1 is compiled and enqueued while the GPU still works
@@ -350,7 +356,7 @@ class DTCSimulator:
         handles = []
         try:
             for i, c in enumerate(circ_list):
-                r = self._run_one(as_circuit(c), shots, int(seed) + i, nm, method, getattr(c, "name", None), handles)
+                r = self._run_one(as_circuit(c), shots, seeds[i], nm, method, getattr(c, "name", None), handles)
                 if pending is not None:
                     exps[pending[0]] = pending[1]()
                     pending = None
@@ -400,7 +406,13 @@ class DTCSimulator:
         data = {"method": method, "n_qubits": n, "register_qubits": prog0.n_main, "active_qubits": prog0.active,
                 "seed_simulator": seed}
         if method == "density_matrix":
-            prog = compile_circuit(circ, nm, want_dm=True)
+            # rho is built by its own compile (no read-out factorisation), whose internal bit order differs from
+            # prog0's: the measured bits must come from THAT program
+            prog = self._compiled(circ, nm, want_dm=True)
+            meas = prog.measures
+            mq = [q for q, _ in meas]
+            cbits = np.array([c for _, c in meas], dtype=np.int64)
+            data["register_qubits"] = prog.n
             rho = run_density_matrix(ctx, prog)
             probs = ctx.empty(1 << k, torch.float64)
             _, qp = capi.i32(mq)
@@ -479,19 +491,20 @@ class DTCSimulator:
             return finish
         return self._experiment(vals, data, prog0, name or circ.name, shots, seed, t0)
 
-    def _compiled(self, circ, nm):
+    def _compiled(self, circ, nm, want_dm=False):
         """compile_circuit() with a small cache keyed by the circuit's op list and the noise model: sweeps that run the
         same circuit again (other seeds, other shot counts: shots.py:49) skip the host compile."""
         noise_key = None
         if nm is not None:
             noise_key = (tuple(sorted((k, e.probs) for k, e in nm._all.items())),
                          tuple(sorted((k, e.probs) for k, e in nm._local.items())))
-        key = (circ.num_qubits, circ.num_clbits, float(circ.global_phase), self.optimize, noise_key,
+        optimize = self.optimize and not want_dm
+        key = (circ.num_qubits, circ.num_clbits, float(circ.global_phase), optimize, want_dm, noise_key,
                tuple(op.astuple() for op in circ.ops))
         cache = self.__dict__.setdefault("_prog_cache", {})
         prog = cache.get(key)
         if prog is None:
-            prog = compile_circuit(circ, nm, want_dm=False, optimize=self.optimize)
+            prog = compile_circuit(circ, nm, want_dm=want_dm, optimize=optimize)
             if len(cache) >= 128:
                 cache.pop(next(iter(cache)))
             cache[key] = prog
@@ -567,4 +580,64 @@ class DTCSimulator:
         return out
 
 
+TARGET_OPERATIONS = ("cx", "id", "rz", "sx", "u1", "u2", "u3", "measure")
+
+
+def make_backendv2_class(base=DTCSimulator):
+    """DTCSimulator as a qiskit ``BackendV2``: the reference hands its backend to the transpiler --
+    ``generate_preset_pass_manager(optimization_level=0, backend=backend, initial_layout=..., routing_method=None)``
+    (fast.py:181-189) -- which needs ``backend.target``.  The Target lists exactly what AerSimulator offers once the
+    reference's noise model is attached (NoiseModel basis gates id/rz/sx/cx + the noisy u1/u2/u3, plus measure) as
+    ideal, all-to-all instructions on `num_qubits` >= 31 qubits (the scripts' snake layout uses physical index 30,
+    fast.py:177; routing_method=None), so the level-0 lowering comes out as the committed gate_counts_*.csv show.
+    Imports qiskit at call time; raises ImportError when it is absent."""
+    from qiskit.circuit import Measure, Parameter
+    from qiskit.circuit.library import CXGate, IGate, RZGate, SXGate, U1Gate, U2Gate, U3Gate
+    from qiskit.providers import BackendV2, Options
+    from qiskit.transpiler import Target
+
+    class DTCSimulatorV2(base, BackendV2):
+        __doc__ = base.__doc__
+
+        def __init__(self, *args, num_qubits=None, **kw):
+            BackendV2.__init__(self, provider=None, name=base.name, description="dtcsim B200-native DTC Floquet simulator",
+                               backend_version="0.2.0")
+            base.__init__(self, *args, **kw)
+            self._n_target = int(num_qubits or base.num_qubits)
+            self._target = None
+
+        @property
+        def target(self):
+            if self._target is None:
+                th, ph, lam = Parameter("theta"), Parameter("phi"), Parameter("lam")
+                t = Target(num_qubits=self._n_target, description="dtcsim: ideal all-to-all basis of the reference's Aer setup")
+                for gate in (CXGate(), IGate(), RZGate(lam), SXGate(), U1Gate(lam), U2Gate(ph, lam), U3Gate(th, ph, lam),
+                             Measure()):
+                    t.add_instruction(gate, None)          # properties None: available on every qubit (pair)
+                self._target = t
+            return self._target
+
+        @property
+        def max_circuits(self):
+            return None
+
+        @classmethod
+        def _default_options(cls):
+            return Options(shots=1024, seed_simulator=None, method="automatic")
+
+        def run(self, run_input, **options):
+            return base.run(self, run_input, **options)
+
+        def set_options(self, **fields):
+            return base.set_options(self, **fields)
+
+    DTCSimulatorV2.__name__ = DTCSimulatorV2.__qualname__ = "DTCSimulator"
+    return DTCSimulatorV2
+
+
+DTCSimulatorBase = DTCSimulator
+try:                                   # qiskit present: be a real BackendV2 (usable as backend= in the pass manager)
+    DTCSimulator = make_backendv2_class(DTCSimulatorBase)
+except ImportError:
+    pass
 AerSimulator = DTCSimulator

@@ -40,6 +40,7 @@ _SIGS = {
     "dtc_program_fused_rdm": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_vp)]),
     "dtc_set_stream_engine": (ctypes.c_int, [ctypes.c_int]),
     "dtc_set_high_stride_bit": (ctypes.c_int, [ctypes.c_int]),
+    "dtc_set_stream_ctas": (ctypes.c_int, [ctypes.c_int]),
     "dtc_program_num_stream_passes": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_last_run_flags": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
@@ -88,6 +89,11 @@ def load():
 def set_high_stride_bit(bit=15):
     """Groups starting at or above this internal bit use five-qubit tiles of 2 KB runs (default 15)."""
     check(load().dtc_set_high_stride_bit(int(bit)))
+
+
+def set_stream_ctas(n=0):
+    """Persistent CTAs per k_tile_stream launch (0: one per SM)."""
+    check(load().dtc_set_stream_ctas(int(n)))
 
 
 def set_stream_engine(enable):

@@ -37,23 +37,73 @@ static int fail(int code, const std::string& msg) {
             return fail(DTC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
     } while (0)
 
-// Table memory of a program comes from the device's stream-ordered pool (kept warm: release threshold = max), because
-// cudaFree costs tens of milliseconds on a device whose address space holds multi-GiB state buffers and run()
-// creates and destroys one program per circuit.
-static cudaError_t table_alloc(void** ptr, size_t bytes, int device) {
-    static bool tuned[16] = {false};
-    if (device >= 0 && device < 16 && !tuned[device]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        tuned[device] = true;
+// ---- per-device library state.  The library never leaves the caller's current device changed (DeviceGuard) and does
+// not touch the process-wide default memory pool: program tables come from a PRIVATE stream-ordered pool (kept warm:
+// cudaFree costs tens of milliseconds on a device whose address space holds multi-GiB state buffers, and run() creates
+// and destroys one program per circuit) and are uploaded on a private non-blocking stream, so that creating the program
+// of circuit i+1 never waits for the GPU work of circuit i that is queued on the caller's stream (a synchronous
+// cudaMemcpy on the legacy default stream would).
+#define DTC_MAX_DEVICES 16
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && device >= 0 && device != prev) err = cudaSetDevice(device);
     }
-    return cudaMallocAsync(ptr, bytes, 0);
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+// device that owns a (device) pointer; the current device if the pointer is unknown to the runtime
+static int device_of(const void* ptr) {
+    cudaPointerAttributes a;
+    if (ptr && cudaPointerGetAttributes(&a, ptr) == cudaSuccess && a.type == cudaMemoryTypeDevice) return a.device;
+    cudaGetLastError();
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
 }
-static void table_free(void* ptr) {
-    if (ptr) cudaFreeAsync(ptr, 0);
+struct DeviceState {
+    bool ready = false;
+    cudaMemPool_t pool = nullptr;
+    cudaStream_t upload = nullptr;
+};
+static DeviceState g_dev[DTC_MAX_DEVICES];
+static cudaError_t device_state(int device, DeviceState** out) {       // call with `device` current
+    if (device < 0 || device >= DTC_MAX_DEVICES) return cudaErrorInvalidDevice;
+    DeviceState& D = g_dev[device];
+    if (!D.ready) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaError_t e = cudaMemPoolCreate(&D.pool, &props);
+        if (e != cudaSuccess) return e;
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(D.pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        e = cudaStreamCreateWithFlags(&D.upload, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        D.ready = true;
+    }
+    *out = &D;
+    return cudaSuccess;
+}
+// allocate + fill a table on the device's upload stream (host data is staged before the call returns)
+static cudaError_t table_upload(void** ptr, const void* host, size_t bytes, size_t min_bytes, int device) {
+    DeviceState* D;
+    cudaError_t e = device_state(device, &D);
+    if (e != cudaSuccess) return e;
+    e = cudaMallocFromPoolAsync(ptr, bytes > min_bytes ? bytes : min_bytes, D->pool, D->upload);
+    if (e != cudaSuccess) return e;
+    if (bytes) e = cudaMemcpyAsync(*ptr, host, bytes, cudaMemcpyHostToDevice, D->upload);
+    return e;
+}
+static void table_free(void* ptr, int device) {
+    if (ptr && device >= 0 && device < DTC_MAX_DEVICES && g_dev[device].ready) cudaFreeAsync(ptr, g_dev[device].upload);
 }
 
 struct dtc_program {
@@ -67,6 +117,9 @@ struct dtc_program {
     int fused_local_bit = -1;            // tile-local position of the read-out qubit in the last pass (-1: not fusable)
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t uploaded = nullptr;      // tables are on the device (recorded on the upload stream)
+    cudaEvent_t last_use = nullptr;      // end of the last dtc_program_run / dtc_program_readout on the caller's stream
+    bool used = false;
     int last_launches = 0;
     bool last_gen_first = false, last_fused = false;     // what the last dtc_program_run did (traffic accounting)
 };
@@ -857,6 +910,7 @@ static int stream_tensor_map(CUtensorMap* tm, void* state, int n_local, int g, i
 }
 
 static int g_stream_override = -1;      // dtc_set_stream_engine(); -1: environment / default
+static int g_stream_ctas = 0;           // dtc_set_stream_ctas(); 0: one persistent CTA per SM
 static bool stream_enabled() {
     if (g_stream_override >= 0) return g_stream_override != 0;
     static const bool on = []() {
@@ -894,14 +948,18 @@ int dtc_program_create(int n_qubits, int n_layers, dtc_program** out) {
 int dtc_program_destroy(dtc_program* p) {
     if (!p) return DTC_OK;
     if (p->h.device >= 0) {
-        cudaSetDevice(p->h.device);
-        if (p->d_events) cudaDeviceSynchronize();      // kernels of this program may still run on the caller's stream
+        DeviceGuard guard(p->h.device);
+        // kernels of this program may still be queued on the caller's stream: the tables are freed in stream order
+        // AFTER the last use (no host synchronisation)
+        if (p->used && p->last_use && g_dev[p->h.device].ready) cudaStreamWaitEvent(g_dev[p->h.device].upload, p->last_use, 0);
+        table_free(p->d_events, p->h.device);
+        table_free(p->d_layers, p->h.device);
+        table_free(p->d_small_idx, p->h.device);
+        if (p->ev0) cudaEventDestroy(p->ev0);
+        if (p->ev1) cudaEventDestroy(p->ev1);
+        if (p->uploaded) cudaEventDestroy(p->uploaded);
+        if (p->last_use) cudaEventDestroy(p->last_use);
     }
-    table_free(p->d_events);
-    table_free(p->d_layers);
-    table_free(p->d_small_idx);
-    if (p->ev0) cudaEventDestroy(p->ev0);
-    if (p->ev1) cudaEventDestroy(p->ev1);
     delete p;
     return DTC_OK;
 }
@@ -953,12 +1011,14 @@ int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
     } else {
         return fail(DTC_ERR_INVALID, "unknown engine");
     }
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.err);
     const size_t eb = p->h.events.size() * sizeof(DtcEvent), lb = p->h.layers.size() * sizeof(DtcLayer);
-    CUDA_TRY(table_alloc((void**)&p->d_events, eb ? eb : 16, device));
-    CUDA_TRY(table_alloc((void**)&p->d_layers, lb, device));
-    if (eb) CUDA_TRY(cudaMemcpy(p->d_events, p->h.events.data(), eb, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(p->d_layers, p->h.layers.data(), lb, cudaMemcpyHostToDevice));
+    CUDA_TRY(table_upload((void**)&p->d_events, p->h.events.data(), eb, 16, device));
+    CUDA_TRY(table_upload((void**)&p->d_layers, p->h.layers.data(), lb, 16, device));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->uploaded, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->last_use, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(p->uploaded, g_dev[device].upload));
     static bool attr_set[16] = {false};
     if (device >= 0 && device < 16 && !attr_set[device]) {
         const int smb = (int)sizeof(TileSmem);
@@ -1017,7 +1077,9 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     const bool keep = init_index == DTC_INIT_KEEP, zero = init_index == DTC_INIT_ZERO;
     if (!keep && !zero && (init_index >> h.n_local)) return fail(DTC_ERR_INVALID, "init_index out of range");
     cudaStream_t s = (cudaStream_t)stream;
-    CUDA_TRY(cudaSetDevice(h.device));
+    DeviceGuard guard(h.device);
+    CUDA_TRY(guard.err);
+    CUDA_TRY(cudaStreamWaitEvent(s, p->uploaded, 0));
     u64 *masks, *fx, *fz;
     int* ph;
     ws_pointers(h, workspace, n_traj, &masks, &fx, &fz, &ph);
@@ -1057,7 +1119,8 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
                     const int rc = stream_tensor_map(&tm, state, h.n_local, S.g, n_traj, S.mode);
                     if (rc != DTC_OK) return rc;
                 }
-                const unsigned sgrid = (unsigned)(grid < n_sms ? grid : n_sms);
+                const int max_ctas = (g_stream_ctas > 0 && g_stream_ctas < n_sms) ? g_stream_ctas : n_sms;
+                const unsigned sgrid = (unsigned)(grid < max_ctas ? grid : max_ctas);
                 const size_t ssb = sizeof(StreamSmem) + 128;
                 const u64 init = (ip == 0 && gen_first) ? (u64)init_index : (u64)DTC_INIT_KEEP;
                 double2* rdm_out = nullptr;
@@ -1105,6 +1168,8 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     }
     if (p->profiling) CUDA_TRY(cudaEventRecord(p->ev1, s));
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(p->last_use, s));
+    p->used = true;
     return DTC_OK;
 }
 
@@ -1139,11 +1204,13 @@ int dtc_program_set_readout(dtc_program* p, int64_t n_small, const int64_t* smal
     for (int64_t e = 0; e < n_small; ++e)
         if (small_events[e] < 0 || small_events[e] >= (int64_t)p->h.events.size())
             return fail(DTC_ERR_INVALID, "read-out plan: event index out of range");
-    CUDA_TRY(cudaSetDevice(p->h.device));
-    table_free(p->d_small_idx);
+    DeviceGuard guard(p->h.device);
+    CUDA_TRY(guard.err);
+    if (p->used) CUDA_TRY(cudaStreamWaitEvent(g_dev[p->h.device].upload, p->last_use, 0));
+    table_free(p->d_small_idx, p->h.device);
     p->d_small_idx = nullptr;
-    CUDA_TRY(table_alloc((void**)&p->d_small_idx, sizeof(long long) * (size_t)(n_small ? n_small : 1), p->h.device));
-    if (n_small) CUDA_TRY(cudaMemcpy(p->d_small_idx, small_events, sizeof(long long) * (size_t)n_small, cudaMemcpyHostToDevice));
+    CUDA_TRY(table_upload((void**)&p->d_small_idx, small_events, sizeof(long long) * (size_t)n_small, 16, p->h.device));
+    CUDA_TRY(cudaEventRecord(p->uploaded, g_dev[p->h.device].upload));
     p->small = S;
     p->n_small = n_small;
     return DTC_OK;
@@ -1176,9 +1243,14 @@ int dtc_program_readout(const dtc_program* p, const void* rdm, void* workspace, 
     u64 *masks, *fx, *fz;
     int* ph;
     ws_pointers(p->h, workspace, n_traj, &masks, &fx, &fz, &ph);
+    DeviceGuard guard(p->h.device);
+    CUDA_TRY(guard.err);
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, p->uploaded, 0));
     k_readout_small<<<(unsigned)((n_traj + 63) / 64), 64, 0, (cudaStream_t)stream>>>(p->small, p->d_events, p->d_small_idx, p->n_small,
                                                                                     (const double2*)rdm, masks, fx, n_traj, probs);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(p->last_use, (cudaStream_t)stream));
+    const_cast<dtc_program*>(p)->used = true;
     return DTC_OK;
 }
 
@@ -1190,6 +1262,12 @@ int dtc_set_high_stride_bit(int bit) {
 
 int dtc_set_stream_engine(int enable) {
     g_stream_override = enable < 0 ? -1 : (enable != 0);
+    return DTC_OK;
+}
+
+int dtc_set_stream_ctas(int n_ctas) {
+    if (n_ctas < 0) return fail(DTC_ERR_INVALID, "n_ctas must be >= 0");
+    g_stream_ctas = n_ctas;
     return DTC_OK;
 }
 
@@ -1230,6 +1308,8 @@ int dtc_materialize(void* state, int n_local, int64_t n_traj, const uint64_t* fx
                     const int32_t* ph, void* scratch, void* stream) {
     (void)scratch;
     if (!state || !fx || !fz || !ph) return fail(DTC_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device_of(state));
+    CUDA_TRY(guard.err);
     const long long ne = n_traj << n_local;
     k_materialize<<<(unsigned)((ne + 255) / 256), 256, 0, (cudaStream_t)stream>>>((double2*)state, n_local, n_traj,
                                                                                  (const u64*)fx, (const u64*)fz, ph);
@@ -1247,6 +1327,8 @@ static int chunks_for(int n_local) {
 int dtc_probs(const void* state, int n_local, int64_t n_traj, int k, const int32_t* qubits,
               const uint64_t* fx, double* out, void* stream) {
     if (!state || !out || k < 0 || k > 12 || (k > 0 && !qubits)) return fail(DTC_ERR_INVALID, "bad argument (k <= 12)");
+    DeviceGuard guard(device_of(state));
+    CUDA_TRY(guard.err);
     cudaStream_t s = (cudaStream_t)stream;
     int* dq = nullptr;
     CUDA_TRY(cudaMallocAsync(&dq, sizeof(int) * (k ? k : 1), s));
@@ -1262,6 +1344,8 @@ int dtc_probs(const void* state, int n_local, int64_t n_traj, int k, const int32
 
 int dtc_rdm(const void* state, int n_local, int64_t n_traj, int k, const int32_t* qubits, void* out, void* stream) {
     if (!state || !out || k < 0 || k > 2 || k > n_local || (k > 0 && !qubits)) return fail(DTC_ERR_INVALID, "bad argument (k <= 2)");
+    DeviceGuard guard(device_of(state));
+    CUDA_TRY(guard.err);
     if (k == 2 && qubits[0] == qubits[1]) return fail(DTC_ERR_INVALID, "duplicate qubit");
     cudaStream_t s = (cudaStream_t)stream;
     int* dq = nullptr;
@@ -1283,6 +1367,8 @@ int dtc_rdm(const void* state, int n_local, int64_t n_traj, int k, const int32_t
 
 int dtc_expect_z(const void* state, int n_local, int64_t n_traj, const uint64_t* fx, double* out, void* stream) {
     if (!state || !out || n_local > DTC_MAXQ) return fail(DTC_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device_of(state));
+    CUDA_TRY(guard.err);
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)n_traj * n_local, s));
     const int cpt = chunks_for(n_local);
@@ -1294,6 +1380,8 @@ int dtc_expect_z(const void* state, int n_local, int64_t n_traj, const uint64_t*
 int dtc_sample_rows(const double* probs, int64_t n_rows, int n_cols, int n_samples, uint64_t seed,
                     int64_t traj_offset, int32_t* out, void* stream) {
     if (!probs || !out || n_rows < 1 || n_cols < 1 || n_samples < 1) return fail(DTC_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device_of(probs));
+    CUDA_TRY(guard.err);
     const long long n = n_rows * n_samples;
     k_sample_rows<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(probs, n_rows, n_cols, n_samples, seed,
                                                                                 traj_offset, out);
@@ -1304,6 +1392,8 @@ int dtc_sample_rows(const double* probs, int64_t n_rows, int n_cols, int n_sampl
 int dtc_sample_states_multi(const void* state, int n_local, int64_t n_traj, int n_samples, uint64_t seed, int64_t traj_offset,
                             const uint64_t* fx, double* scratch, uint64_t* out, void* stream) {
     if (!state || !scratch || !out || n_traj < 1 || n_samples < 1) return fail(DTC_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device_of(state));
+    CUDA_TRY(guard.err);
     cudaStream_t s = (cudaStream_t)stream;
     const int cb = n_local < 12 ? n_local : 12;
     const long long nblk = n_traj << (n_local - cb);
@@ -1323,6 +1413,8 @@ int dtc_sample_states(const void* state, int n_local, int64_t n_traj, uint64_t s
 // ---- density matrix
 int dtc_dm_init(void* rho, int n, uint64_t basis_index, void* stream) {
     if (!rho || n < 1 || n > 13 || (basis_index >> n)) return fail(DTC_ERR_INVALID, "bad argument (n <= 13)");
+    DeviceGuard guard(device_of(rho));
+    CUDA_TRY(guard.err);
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(rho, 0, sizeof(double2) << (2 * n), s));
     k_init_basis<<<1, 32, 0, s>>>((double2*)rho, 2 * n, 1, basis_index | (basis_index << n));
@@ -1332,6 +1424,8 @@ int dtc_dm_init(void* rho, int n, uint64_t basis_index, void* stream) {
 
 int dtc_dm_rot(void* rho, int n, int qubit, double theta, void* stream) {
     if (!rho || n < 1 || n > 13 || qubit < 0 || qubit >= n) return fail(DTC_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device_of(rho));
+    CUDA_TRY(guard.err);
     cudaStream_t s = (cudaStream_t)stream;
     const double c = cos(0.5 * theta), sn = sin(0.5 * theta);
     const long long np = 1ll << (2 * n - 1);
@@ -1344,6 +1438,8 @@ int dtc_dm_rot(void* rho, int n, int qubit, double theta, void* stream) {
 int dtc_dm_diag(void* rho, int n, int n1, const int32_t* q1, const double* a, int n2, const int32_t* qi,
                 const int32_t* qj, const double* b, void* stream) {
     if (!rho || n < 1 || n > 13 || n1 < 0 || n2 < 0) return fail(DTC_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device_of(rho));
+    CUDA_TRY(guard.err);
     cudaStream_t s = (cudaStream_t)stream;
     int *dq1 = nullptr, *dqi = nullptr, *dqj = nullptr;
     double *da = nullptr, *db = nullptr;
@@ -1372,6 +1468,8 @@ int dtc_dm_diag(void* rho, int n, int n1, const int32_t* q1, const double* a, in
 
 int dtc_dm_pauli_channel(void* rho, int n, int qubit, double px, double py, double pz, void* stream) {
     if (!rho || n < 1 || n > 13 || qubit < 0 || qubit >= n) return fail(DTC_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device_of(rho));
+    CUDA_TRY(guard.err);
     const long long ng = 1ll << (2 * n - 2);
     k_dm_channel<<<(unsigned)((ng + 255) / 256), 256, 0, (cudaStream_t)stream>>>((double2*)rho, n, qubit, px, py, pz);
     CUDA_TRY(cudaGetLastError());
@@ -1380,6 +1478,8 @@ int dtc_dm_pauli_channel(void* rho, int n, int qubit, double px, double py, doub
 
 int dtc_dm_probs(const void* rho, int n, int k, const int32_t* qubits, double* out, void* stream) {
     if (!rho || !out || n < 1 || n > 13 || k < 0 || k > n || (k > 0 && !qubits)) return fail(DTC_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device_of(rho));
+    CUDA_TRY(guard.err);
     cudaStream_t s = (cudaStream_t)stream;
     int* dq = nullptr;
     CUDA_TRY(cudaMallocAsync(&dq, sizeof(int) * (k + 1), s));
@@ -1395,6 +1495,8 @@ int dtc_dm_probs(const void* rho, int n, int k, const int32_t* qubits, double* o
 
 static int shard_move(const void* state, void* buf, int n_local, int g, const int32_t* lq, int unpack, void* stream) {
     if (!state || !buf || g < 1 || g > 6 || g > n_local || !lq) return fail(DTC_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device_of(state));
+    CUDA_TRY(guard.err);
     cudaStream_t s = (cudaStream_t)stream;
     int* dl = nullptr;
     CUDA_TRY(cudaMallocAsync(&dl, sizeof(int) * g, s));

@@ -6,12 +6,16 @@ set) at n = 34-35, where one state is 256-512 GiB.
 
 Layout: global basis index = (rank << n_local) | local index.  Per layer R_j D_j:
   * diagonal terms need no communication -- the rank bits enter the phases (`rank_bits` of the C ABI);
-  * rotations act on local qubits only, so the qubits that are currently global are exchanged with g local
-    qubits whose rotation of this layer is already done: pack (k_shard_pack) -> all_to_all_single over
-    NVLink -> unpack, and the new qubit->bit permutation is kept (no swap back): ONE exchange per layer.
+  * rotations act on local qubits only, so the g qubits that are currently global are exchanged with the top g local
+    qubits once per layer, and the new qubit->bit permutation is kept (no swap back).
+Schedule of one period (steady state; X = the qubits that were global, now at the top local bits):
+    T   one sweep of the whole shard on the top tile group:  R_j|X -> D_j -> R_{j+1}|top group        (look-ahead)
+    S   slice by slice (slice d = the amplitudes whose top g local bits spell d = what rank d receives):
+        the sweeps of R_{j+1} on the other local qubits, then slice d is pushed to rank d over NVLink on a side
+        stream while the next slice is swept -- the exchange of layer j+1 hides behind these sweeps.
 Noise: the trajectory's Paulis are sampled on the host with the same Philox contract as the device
-(`philox_uniform`), and the Pauli frame is tracked on the host while the circuit is cut into per-exchange
-segments, so each segment is an ideal program with sign-resolved angles |theta'| <= pi/2.
+(`philox_uniform`), and the Pauli frame is tracked on the host while the circuit is cut into segments, so each
+segment is an ideal program with sign-resolved angles |theta'| <= pi/2.
 
 The local work goes through an engine object (`CudaShardEngine` binds libdtcsim through capi;
 tests/test_sharded_cpu.py plugs a numpy engine to check this host logic with gloo on CPU).
@@ -23,6 +27,7 @@ import numpy as np
 from . import plan
 
 PI = math.pi
+TOP_GROUP = 5      # qubits of a high-stride tile group (mode C of k_tile_stream: 7 passive low bits + 5 qubits)
 _M0, _M1, _W0, _W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
 
 
@@ -172,27 +177,44 @@ class ShardedStatevector:
         applied = set()
         j = 0
         M = len(layers)
+        sliced = hasattr(self.engine, "exchange_sliced") and g > 0
+        top = max(g, min(TOP_GROUP, nl - g))       # bits [nl - top, nl): the tile group the exchanged qubits land in
         while j < M:
             rot, d1, d2 = layers[j]
             todo = {q: th for q, th in rot.items() if q not in applied}
             glob = [q for q in todo if phys[q] >= nl]
             if glob:
                 loc = {q: th for q, th in todo.items() if phys[q] < nl}
-                if loc:
-                    prog = _SegmentProgram(n, nl)
-                    prog.add_layer_rot(1, loc, phys)
-                    self.engine.run_segment(prog, first)
+                lq = list(range(nl - g, nl))       # the top g local bits go out
+                if sliced:
+                    # rotations still due on the outgoing bits (first layer of a run): one sweep of the whole shard on
+                    # the top group; everything below then rides with the exchange, slice by slice
+                    if any(phys[q] >= nl - g for q in loc):
+                        grp = {q: th for q, th in loc.items() if phys[q] >= nl - top}
+                        prog = _SegmentProgram(n, nl)
+                        prog.add_layer_rot(1, grp, phys)
+                        self.engine.run_segment(prog, first)
+                        first = False
+                        self.stats["segments"] += 1
+                        applied |= set(grp)
+                        loc = {q: th for q, th in loc.items() if q not in grp}
+                    prog = None
+                    if loc:
+                        prog = _SegmentProgram(n, nl - g)
+                        prog.add_layer_rot(1, loc, phys)
+                        self.stats["segments"] += 1
+                    self.engine.exchange_sliced(prog, lq, first)
                     first = False
-                    self.stats["segments"] += 1
                     applied |= set(loc)
-                # swap the g global bits with g local qubits whose layer-j rotation is done (or that have none)
-                cand = [q for q in range(n) if phys[q] < nl and (q in applied or q not in rot)]
-                if len(cand) < g:
-                    raise ValueError("not enough finished local qubits to exchange with the global ones")
-                cand.sort(key=lambda q: -phys[q])
-                out_q = cand[:g]
-                lq = sorted(phys[q] for q in out_q)
-                self.engine.exchange(lq)
+                else:
+                    if loc:
+                        prog = _SegmentProgram(n, nl)
+                        prog.add_layer_rot(1, loc, phys)
+                        self.engine.run_segment(prog, first)
+                        first = False
+                        self.stats["segments"] += 1
+                        applied |= set(loc)
+                    self.engine.exchange(lq)
                 self.stats["exchanges"] += 1
                 self.stats["exchange_bytes_per_rank"] += (16 << nl) * (self.world - 1) // self.world
                 inv = {phys[q]: q for q in range(n)}
@@ -206,6 +228,10 @@ class ShardedStatevector:
             nxt = {}
             if j + 1 < M:
                 nxt = {q: th for q, th in layers[j + 1][0].items() if phys[q] < nl}
+                if sliced and any(phys[q] >= nl for q in layers[j + 1][0]):
+                    # an exchange follows: look ahead on the top group only (this segment stays ONE sweep);
+                    # the other local rotations of layer j+1 are swept slice by slice under the exchange
+                    nxt = {q: th for q, th in nxt.items() if phys[q] >= nl - top}
                 prog.add_layer_rot(2, nxt, phys)
             self.engine.run_segment(prog, first)
             first = False
@@ -223,20 +249,104 @@ class ShardedStatevector:
         return {"expect_z": ez, "norm": float(tot[n]), "frame": (fx, fz, ph), "phys": list(phys)}
 
 
-class CudaShardEngine:
-    """Local shard on one GPU: libdtcsim for the fused passes, k_shard_pack + all_to_all_single for exchanges."""
+class ThreadFabric:
+    """P emulated ranks inside ONE process on ONE GPU (one thread per rank): lets the `-m gpu` tests drive the sharded
+    path -- rank bits, slice programs, the exchange permutation -- through the C ABI without a multi-GPU box.  Every
+    rank registers its two buffers; an exchange is device copies between them, fenced by thread barriers."""
 
-    def __init__(self, n, n_local, rank, world, device_index, group=None):
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.bar = threading.Barrier(world, timeout=300)
+        self.bufs = [None] * world          # per rank: {"a": tensor, "b": tensor}
+
+    def register(self, rank, a, b):
+        self.bufs[rank] = {"a": a, "b": b}
+        self.bar.wait()
+
+    def all_reduce(self, rank, arr):
+        if not hasattr(self, "_red"):
+            self._red = [None] * self.world
+        self._red[rank] = np.asarray(arr, dtype=np.float64).copy()
+        self.bar.wait()
+        tot = sum(self._red)
+        self.bar.wait()
+        return tot
+
+
+class CudaShardEngine:
+    """Local shard on one GPU: libdtcsim for the fused sweeps; the exchange is
+       * `symm`   (default for world > 1): both state buffers live in symmetric memory (torch.distributed._symmetric_memory:
+                  every rank maps every peer's buffers), a finished slice is pushed into the peer's receive buffer by the
+                  copy engines over NVLink on a side stream while the SMs sweep the next slice; one device-side barrier
+                  per exchange;
+       * `nccl`   fallback: pairwise ncclSend/ncclRecv per slice on the side stream (k_tile_stream then leaves a few SMs
+                  to the NCCL kernels), or a single all_to_all_single when `overlap` is off;
+       * `thread` ranks emulated by threads on one GPU (ThreadFabric; tests)."""
+
+    NCCL_SMS = 20            # SMs left to the NCCL send/recv kernels while sweeps and exchange overlap (nccl mode)
+
+    def __init__(self, n, n_local, rank, world, device_index, group=None, transport=None, overlap=True, fabric=None):
         import torch
         from . import backend, capi
         self.torch, self.capi = torch, capi
         self.n, self.n_local, self.rank, self.world, self.group = n, n_local, rank, world, group
         self.ctx = backend.DeviceContext(device_index)
-        self.a = self.ctx.empty(1 << n_local, torch.complex128)
-        self.b = self.ctx.empty(1 << n_local, torch.complex128)
+        self.overlap = bool(overlap)
+        self.fabric = fabric
+        if transport is None:
+            transport = "thread" if fabric is not None else ("symm" if world > 1 else "none")
+        self.transport = transport
+        self.hdl = {}
+        numel = 1 << n_local
+        c128 = torch.complex128
+        if transport == "symm":
+            try:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                bufs = []
+                for _ in range(2):
+                    t = symm_mem.empty(2 * numel, dtype=torch.float64, device=self.ctx.device)
+                    h = symm_mem.rendezvous(t, grp)
+                    bufs.append((t, h))
+                self.a, self.b = bufs[0][0].view(c128), bufs[1][0].view(c128)
+                self.hdl = {self.a.data_ptr(): bufs[0][1], self.b.data_ptr(): bufs[1][1]}
+            except Exception as exc:                      # no peer mapping on this box: NCCL send/recv instead
+                self.transport = transport = "nccl"
+                self.symm_error = repr(exc)
+        if transport != "symm":
+            self.a = self.ctx.empty(numel, c128)
+            self.b = self.ctx.empty(numel, c128)
+        if transport == "thread":
+            fabric.register(rank, self.a, self.b)
+        self.comm = torch.cuda.Stream(device=self.ctx.index) if world > 1 else None
+        self._handles = {}
         self.passes = 0
         self.fast_exchanges = 0
+        self.sliced_exchanges = 0
         self.timing = None          # set to {} to collect wall-clock seconds per component (synchronises after each)
+
+    # ---- programs: one handle (+ workspace) per distinct segment, kept for the life of the engine
+    def _handle(self, prog, n_local):
+        ev = prog.arrays()
+        key = (n_local, prog.n_layers) + tuple(ev[k].tobytes() for k in ("type", "layer", "q0", "q1", "slot", "val"))
+        hit = self._handles.get(key)
+        if hit is None:
+            capi = self.capi
+            h = capi.ProgramHandle(prog, self.ctx.index, capi.ENGINE_AUTO, n_local)
+            wsb = h.workspace_bytes(1)
+            hit = (h, self.ctx.empty(wsb, self.torch.uint8), wsb)
+            if len(self._handles) >= 256:
+                old = self._handles.pop(next(iter(self._handles)))
+                old[0].close()                            # tables are freed in stream order after their last use
+            self._handles[key] = hit
+        return hit
+
+    def close(self):
+        for h, _ws, _b in self._handles.values():
+            h.close()
+        self._handles = {}
 
     def _timed(self, key, t0):
         if self.timing is not None:
@@ -244,44 +354,151 @@ class CudaShardEngine:
             self.torch.cuda.synchronize(self.ctx.index)
             self.timing[key] = self.timing.get(key, 0.0) + time.perf_counter() - t0
 
+    def _run(self, prog, ptr, n_local, init, rank_bits):
+        h, ws, wsb = self._handle(prog, n_local)
+        h.run(ptr, 1, 0, 0, ws.data_ptr(), wsb, self.ctx.stream, init_index=init, rank_bits=rank_bits)
+        self.passes_weighted += h.num_passes * (1 << n_local) / float(1 << self.n_local)
+        return h.num_passes
+
+    passes_weighted = 0.0           # state sweeps in units of the whole shard (a slice sweep counts 1 / 2^g)
+
     def run_segment(self, prog, first):
         import time
         capi = self.capi
         t0 = time.perf_counter()
-        h = capi.ProgramHandle(prog, self.ctx.index, capi.ENGINE_AUTO, self.n_local)
-        self._timed("segment_setup", t0)
-        t0 = time.perf_counter()
-        wsb = h.workspace_bytes(1)
-        ws = self.ctx.empty(wsb, self.torch.uint8)
         init = capi.INIT_KEEP if not first else (0 if self.rank == 0 else capi.INIT_ZERO)
-        h.run(self.a.data_ptr(), 1, 0, 0, ws.data_ptr(), wsb, self.ctx.stream, init_index=init, rank_bits=self.rank)
-        self.passes += h.num_passes
-        self.torch.cuda.current_stream(self.ctx.index).synchronize()     # ws / handle are freed on return
+        self.passes += self._run(prog, self.a.data_ptr(), self.n_local, init, self.rank)
         self._timed("segment_sweeps", t0)
-        t0 = time.perf_counter()
-        h.close()
-        self._timed("segment_teardown", t0)
 
+    # ---- exchange
     def exchange(self, lq):
-        import torch.distributed as dist
+        """Swap the g global qubits with the local bits lq (whole shard at once, no overlap)."""
+        import time
         capi, lib = self.capi, self.capi.load()
         g = len(lq)
-        f64 = self.torch.float64
+        t0 = time.perf_counter()
         if list(lq) == list(range(self.n_local - g, self.n_local)):
             # the outgoing qubits are the top local bits: chunk d of the state IS what rank d receives and the incoming
-            # chunks land where they belong, so pack and unpack are identities -- one all-to-all, no extra sweeps
-            import time
-            t0 = time.perf_counter()
-            dist.all_to_all_single(self.b.view(f64), self.a.view(f64), group=self.group)
-            self.a, self.b = self.b, self.a
-            self.fast_exchanges += 1
+            # chunks land where they belong, so pack and unpack are identities -- no extra sweeps
+            self.exchange_sliced(None, lq, False)
             self._timed("all_to_all", t0)
             return
+        import torch.distributed as dist
+        f64 = self.torch.float64
         _, lp = capi.i32(lq)
         capi.check(lib.dtc_shard_pack(self.a.data_ptr(), self.b.data_ptr(), self.n_local, g, lp, self.ctx.stream))
-        dist.all_to_all_single(self.a.view(f64), self.b.view(f64), group=self.group)
-        capi.check(lib.dtc_shard_unpack(self.a.data_ptr(), self.b.data_ptr(), self.n_local, g, lp, self.ctx.stream))
+        if self.transport == "thread":
+            raise ValueError("ThreadFabric exchanges the top local bits only")
+        tmp = self.ctx.empty(1 << self.n_local, self.torch.complex128)
+        dist.all_to_all_single(tmp.view(f64), self.b.view(f64), group=self.group)
+        capi.check(lib.dtc_shard_unpack(tmp.data_ptr(), self.b.data_ptr(), self.n_local, g, lp, self.ctx.stream))
+        self._swap()
+        self._timed("all_to_all", t0)
+
+    def _swap(self):
         self.a, self.b = self.b, self.a
+
+    def exchange_sliced(self, prog, lq, first):
+        """Exchange of the top g local bits with the g global bits, fused with `prog` (rotations on the lower local
+        qubits, or None): slice d -- the part of the shard rank d will own -- is swept and then sent while the next
+        slice is swept.  Remote slices go first (staggered so that every rank sends to and receives from one peer
+        at a time), the slice that stays on this rank last."""
+        torch, capi = self.torch, self.capi
+        g, P, r = len(lq), self.world, self.rank
+        assert list(lq) == list(range(self.n_local - g, self.n_local)) and (1 << g) == P
+        nls = self.n_local - g
+        S = 1 << nls
+        cur = torch.cuda.current_stream(self.ctx.index)
+        a, b = self.a, self.b
+        self.sliced_exchanges += 1
+        self.fast_exchanges += 1
+
+        def sweep(d):
+            if prog is None:
+                if first:
+                    a[d * S:(d + 1) * S].zero_()
+                    if r == 0 and d == 0:
+                        a[0:1].fill_(1.0)
+                return
+            init = capi.INIT_KEEP if not first else (0 if (r == 0 and d == 0) else capi.INIT_ZERO)
+            self._run(prog, a.data_ptr() + 16 * d * S, nls, init, (r << g) | d)
+
+        if prog is not None:
+            self.passes += self._handle(prog, nls)[0].num_passes
+
+        if self.transport == "thread":
+            # emulated ranks: all sweeps, barrier, every rank pulls its slices from the others' buffers, barrier
+            for d in range(P):
+                sweep(d)
+            torch.cuda.synchronize(self.ctx.index)
+            self.fabric.bar.wait()
+            for src in range(P):
+                b[src * S:(src + 1) * S].copy_(self.fabric.bufs[src]["a"][r * S:(r + 1) * S])
+            torch.cuda.synchronize(self.ctx.index)
+            self.fabric.bar.wait()
+            self._swap()
+            self.fabric.bufs[r] = {"a": self.a, "b": self.b}
+            self.fabric.bar.wait()
+            return
+
+        if not self.overlap or self.transport == "none":
+            for d in range(P):
+                sweep(d)
+            if P > 1:
+                import torch.distributed as dist
+                f64 = torch.float64
+                dist.all_to_all_single(b.view(f64), a.view(f64), group=self.group)
+                self._swap()
+            return
+
+        order = [(r + s) % P for s in range(1, P)] + [r]
+        comm = self.comm
+        if self.transport == "symm":
+            hb = self.hdl[b.data_ptr()]
+            for d in order:
+                sweep(d)
+                if d == r:
+                    b[r * S:(r + 1) * S].copy_(a[r * S:(r + 1) * S], non_blocking=True)
+                    continue
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    peer_b = hb.get_buffer(d, (2 * S,), torch.float64, 2 * r * S)     # slot r of rank d's receive buffer
+                    peer_b.copy_(a[d * S:(d + 1) * S].view(torch.float64), non_blocking=True)
+            comm.wait_stream(cur)                # ... and this rank has finished reading its send buffer
+            with torch.cuda.stream(comm):
+                hb.barrier(channel=0)            # every push into every receive buffer has completed
+            cur.wait_stream(comm)
+            self._swap()
+            return
+
+        # nccl: pairwise send / recv per step on the side stream; the sweeps leave NCCL_SMS SMs to those kernels
+        import torch.distributed as dist
+        f64 = torch.float64
+        capi.set_stream_ctas(max(1, torch.cuda.get_device_properties(self.ctx.index).multi_processor_count - self.NCCL_SMS))
+        try:
+            works = []
+            for s_, d in enumerate(order):
+                sweep(d)
+                if d == r:
+                    b[r * S:(r + 1) * S].copy_(a[r * S:(r + 1) * S], non_blocking=True)
+                    continue
+                src = (r - (s_ + 1)) % P
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    ops = [dist.P2POp(dist.isend, a[d * S:(d + 1) * S].view(f64), d, group=self.group),
+                           dist.P2POp(dist.irecv, b[src * S:(src + 1) * S].view(f64), src, group=self.group)]
+                    works += dist.batch_isend_irecv(ops)
+            with torch.cuda.stream(comm):
+                for w in works:
+                    w.wait()
+            cur.wait_stream(comm)
+        finally:
+            capi.set_stream_ctas(0)
+        self._swap()
 
     def expect_z_partial(self):
         capi, lib, torch = self.capi, self.capi.load(), self.torch

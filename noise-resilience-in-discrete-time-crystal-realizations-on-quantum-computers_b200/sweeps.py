@@ -1,0 +1,148 @@
+"""Batched sweep front-end: the loops the reference's drivers run one circuit at a time.
+
+The reference evaluates a sweep point by point -- `get_single_out` / `get_instances` loop over t, echo and disorder
+instances (fast.py:217-239), `for pol in ["x","y","xy","yx"]` over polarisations (pol.py:336,349-373), the parameter
+grid over g (generate_params.py:6) -- and every point pays backend construction + transpile + one `run()`
+(fast.py:156,181-192,211).  `run_sweep` takes the whole grid at once: it builds the same circuits (same gate sequence,
+same level-0 lowering, same snake layout), deals the points to the ranks of the process group (dist.deal_units), runs
+each rank's share through ONE pipelined `run(list)` call and sums the results with one all-reduce.  The numbers are
+what the per-point loop returns: <Z_ancilla> from the counts of `shots` Pauli trajectories per point
+(compute_z_expectation, fast.py:92-109), seeds `seed + point index`, independent of the number of ranks.
+"""
+import math
+
+import numpy as np
+
+from .ir import QuantumCircuit
+from .lowering import SNAKE_LAYOUT, lower_level0
+
+PI = math.pi
+POLARIZATIONS = ("x", "y", "xy", "yx", "circular_left", "circular_right", "circular_static")
+G_GRID = (0.5, 0.55, 0.6, 0.65, 0.7, 0.75, 0.8, 0.85, 0.9, 0.95, 1.0)      # generate_params.py:6
+
+
+def floquet_period(L, g, phis, hs, polarization="x", time_step=0, circular_frequency=1.0):
+    """One period U_F on circuit qubits 1..L (qubit 0 is the ancilla): kick layer in the given polarisation
+    (pol.py:110-122, circ-pol.py:110-140), RZZ on even then odd bonds, RZ fields (fast.py:111-121)."""
+    sub = QuantumCircuit(L + 1)
+    for i in range(L):
+        q = i + 1
+        if polarization == "x":
+            sub.rx(PI * g, q)
+        elif polarization == "y":
+            sub.ry(PI * g, q)
+        elif polarization == "xy":
+            sub.rx(PI * g / 2, q)
+            sub.ry(PI * g / 2, q)
+        elif polarization == "yx":
+            sub.ry(PI * g / 2, q)
+            sub.rx(PI * g / 2, q)
+        elif polarization in ("circular_left", "circular_right"):
+            sgn = 1.0 if polarization == "circular_left" else -1.0
+            sub.rx(PI * g * math.cos(circular_frequency * time_step) / math.sqrt(2), q)
+            sub.ry(sgn * PI * g * math.sin(circular_frequency * time_step) / math.sqrt(2), q)
+        elif polarization == "circular_static":
+            sub.rx(PI * g / math.sqrt(2), q)
+            sub.ry(PI * g / math.sqrt(2), q)
+        else:
+            raise ValueError(f"unknown polarization {polarization!r}")
+    for i in range(0, L - 1, 2):
+        sub.rzz(float(phis[i]), i + 1, i + 2)
+    for i in range(1, L - 1, 2):
+        sub.rzz(float(phis[i]), i + 1, i + 2)
+    for i in range(L):
+        sub.rz(float(hs[i]), i + 1)
+    return sub
+
+
+def autocorr_circuit(L, g, hs, phis, t, qubit=None, echo=False, polarization="x", initial_state="vacuum",
+                     g_values=None, pol_schedule=None, circular_frequency=1.0, transpile=True):
+    """The reference's Hadamard-test autocorrelation circuit (fast.py:124-147) for t periods.
+
+    g_values: per-step g (ctrl-g.py:196-241; step k uses g_values[k], the echo undoes the steps in reverse order);
+    pol_schedule: callable step -> polarisation (xy-cycle.py:141-157).  transpile=True applies the level-0 lowering
+    with the snake layout (fast.py:176-190), i.e. returns what the scripts hand to backend.run()."""
+    qubit = L // 2 if qubit is None else int(qubit)
+    circ = QuantumCircuit(L + 1, 1)
+    if initial_state == "neel":
+        for i in range(1, L + 1):
+            if i % 2 == 0:
+                circ.x(i)
+    elif initial_state != "vacuum":
+        raise ValueError(f"unknown initial state {initial_state!r}")
+    circ.h(0)
+    circ.cz(qubit + 1, 0)
+
+    def period(step):
+        gg = g if g_values is None else g_values[step]
+        pol = polarization if pol_schedule is None else pol_schedule(step)
+        return floquet_period(L, gg, phis, hs, pol, step, circular_frequency)
+
+    for step in range(t):
+        circ.append(period(step), range(L + 1))
+    if echo:
+        for step in range(t - 1, -1, -1):
+            circ.append(period(step).inverse(), range(L + 1))
+    circ.cz(qubit + 1, 0)
+    circ.h(0)
+    circ.measure(0, 0)
+    if not transpile:
+        return circ
+    if L + 1 > len(SNAKE_LAYOUT):
+        return lower_level0(circ)
+    return lower_level0(circ, SNAKE_LAYOUT[:L + 1])
+
+
+def xy_cycle_schedule(block=5):
+    """Polarisation alternating x / y every `block` steps (xy-cycle.py:144-156)."""
+    return lambda step: "x" if (step // block) % 2 == 0 else "y"
+
+
+def sweep_points(g_list, polarizations, instances, t_values, echoes):
+    """Flattened grid in the order the reference's nested loops visit it: g, polarisation, echo, instance, t."""
+    return [(gi, pi, ei, ii, ti) for gi in range(len(g_list)) for pi in range(len(polarizations))
+            for ei in range(len(echoes)) for ii in range(len(instances)) for ti in range(len(t_values))]
+
+
+def run_sweep(sim, L, g_list, hs, phis, t_values, echoes=(False, True), polarizations=("x",), qubit=None,
+              initial_state="vacuum", shots=1024, seed_simulator=1234, rank=0, world=1, group=None,
+              circular_frequency=1.0, chunk=64):
+    """Whole autocorrelation sweep in one call.
+
+    sim: DTCSimulator (with its noise model) bound to this rank's GPU.  hs [n_inst, >= L], phis [n_inst, >= L-1]: disorder
+    rows (hs_L*.csv / phis_L*.csv).  Returns a dict with
+      "autocorr"  float64 [len(g_list), len(polarizations), len(echoes), n_inst, len(t_values)]: <Z_ancilla> per point
+                  from counts, as `qc_qiskit` returns it (fast.py:213);
+      "mean"      the instance average [g, pol, echo, t]  (get_instances, fast.py:228-239);
+      "points", "periods": number of circuits and of Floquet periods x shots simulated over all ranks.
+    With world > 1 every rank must call it (one all-reduce at the end); results are identical on all ranks and
+    identical to a single-rank call with the same seed."""
+    from . import dist as D
+    from .backend import compute_z_expectation
+    hs = np.atleast_2d(np.asarray(hs, dtype=np.float64))
+    phis = np.atleast_2d(np.asarray(phis, dtype=np.float64))
+    n_inst = hs.shape[0]
+    pts = sweep_points(g_list, polarizations, range(n_inst), t_values, echoes)
+    mine = D.deal_units(len(pts), rank, world)
+    shape = (len(g_list), len(polarizations), len(echoes), n_inst, len(t_values))
+    out = np.zeros(shape, dtype=np.float64)
+    periods = 0
+    for a in range(0, len(mine), chunk):                      # bounded host memory: circuits are built chunk by chunk
+        idx = mine[a:a + chunk]
+        circs = []
+        for k in idx:
+            gi, pi, ei, ii, ti = pts[k]
+            t = int(t_values[ti])
+            circs.append(autocorr_circuit(L, g_list[gi], hs[ii], phis[ii], t, qubit, echoes[ei], polarizations[pi],
+                                          initial_state, circular_frequency=circular_frequency))
+            periods += t * (2 if echoes[ei] else 1) * shots
+        if not circs:
+            continue
+        # per-circuit seeds = seed + GLOBAL point index, so the result does not depend on how the points are dealt
+        res = sim.run(circs, shots=shots, seed_simulator=[int(seed_simulator) + int(k) for k in idx]).result()
+        for j, k in enumerate(idx):
+            out[pts[k]] = compute_z_expectation(res.get_counts(j), 1)[0]
+    tot = np.concatenate([out.reshape(-1), [float(periods)]])
+    tot = D.all_reduce_sum(tot, group, sim.ctx.device if world > 1 else None)
+    out = tot[:-1].reshape(shape)
+    return {"autocorr": out, "mean": out.mean(axis=3), "points": len(pts), "periods": int(round(tot[-1]))}

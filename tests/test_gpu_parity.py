@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA library (through its C ABI / the AerSimulator-compatible backend) against
 the CPU oracle on identical inputs.  Tolerances (BASELINE.json north_star): noiseless and per-trajectory
-statevector amplitudes 1e-10, density-matrix expectation values 1e-8, shot/trajectory estimates 3-4 sigma.
+statevector amplitudes 1e-10, density-matrix expectation values 1e-8, shot/trajectory estimates within 3 sigma --
+held family-wise over the points of a test (conftest.family_z: per-point bound 3.0 for one point, 3.5 for six).
 """
 import numpy as np
 import pytest
@@ -8,7 +9,7 @@ import pytest
 import dtcsim
 import program_interp as PI
 import refcircuits as RC
-from conftest import golden_csv
+from conftest import family_z, golden_csv
 from dtcsim import compile_circuit
 from oracle import c_oracle as CO
 from oracle import dtc_circuits as C
@@ -273,10 +274,112 @@ def test_L20_trajectory_statistics(disorder):
         ez = dtcsim.backend.compute_z_expectation(counts, 1)[0]
         exact = 0.95 ** 6 * O.lightcone_zq(20, 0.97, hs, phis, t, 10, 0.05, echo=echo)
         sig = np.sqrt((1 - exact ** 2) / 1024)
-        assert abs(ez - exact) < 4 * sig
-        assert abs(res.expectation_z()[0] - exact) < 4 * sig          # trajectory mean of exact probabilities
+        zf = family_z(6)                                              # 2 circuits x 3 comparisons in this test
+        assert abs(ez - exact) < zf * sig
+        assert abs(res.expectation_z()[0] - exact) < zf * sig         # trajectory mean of exact probabilities
         ref = df["av_autocorr_echo" if echo else "av_autocorr"][t]
-        assert abs(ez - ref) < 4 * np.sqrt(2) * sig
+        assert abs(ez - ref) < zf * np.sqrt(2) * sig                  # two independent 1024-shot estimates
+
+
+def test_L20_circular_and_controlled_g_through_run(disorder):
+    """The circular-polarisation and time-dependent-g anchors of SURVEY 8c through run() at full size (n = 21, 1024
+    trajectories): circ-pol.py:162-174 (per-step rx/ry angles, two noisy u3 per qubit per period) and g-opt.py:530-545
+    (step k uses g_history_inst1[k]); against the exact light-cone value and the reference's committed Aer output."""
+    hs, phis = disorder[20][0][0], disorder[20][1][0]
+    sim = dtcsim.AerSimulator(noise_model=RC.noise_model(0.05), device="GPU", cuStateVec_enable=True)
+    dfc = golden_csv("ref_L20_circ_circular_left.csv")
+    dfg = golden_csv("ref_L20_controlled_iter5.csv")
+    gh = [float(x) for x in dfg["g_history_inst1"]]
+    cases = []
+    # circular_left, forward t = 2 and echo t = 1
+    for t, echo in ((2, False), (1, True)):
+        ops, _, _ = C.autocorr_gates("vacuum", 20, 0.97, hs, phis, t, 10, echo, polarization="circular_left",
+                                     circular_frequency=1.0)
+        pf = lambda step: C.uf_gates(20, 0.97, phis, hs, "circular_left", time_step=step, circular_frequency=1.0)
+        exact = 0.95 ** 6 * O.lightcone_zq(20, 0.97, hs, phis, t, 10, 0.05, echo=echo, period_fn=pf)
+        cases.append((ops, exact, dfc["av_autocorr_echo" if echo else "av_autocorr"][t]))
+    # time-dependent g (row i <-> i+1 periods), forward 3 periods and echo 2 periods
+    for t, echo in ((3, False), (2, True)):
+        ops, _, _ = C.autocorr_gates("vacuum", 20, None, hs, phis, t, 10, echo, g_values=gh)
+        pf = lambda step: C.uf_gates(20, gh[step], phis, hs, "x")
+        exact = 0.95 ** 6 * O.lightcone_zq(20, None, hs, phis, t, 10, 0.05, echo=echo, period_fn=pf)
+        cases.append((ops, exact, dfg["echo_adaptive_inst1" if echo else "forward_adaptive_inst1"][t - 1]))
+    zf = family_z(2 * len(cases))
+    for i, (ops, exact, ref) in enumerate(cases):
+        circ = dtcsim.QuantumCircuit(31, 1)
+        for nm_, qs, ps, cs in C.lower_level0(ops, C.SNAKE_LAYOUT):
+            circ._add(nm_, qs, ps, cs)
+        res = sim.run(circ, shots=1024, seed_simulator=4321 + i).result()
+        assert res.data()["method"] == "statevector" and res.data()["n_qubits"] == 21
+        ez = dtcsim.backend.compute_z_expectation(res.get_counts(), 1)[0]
+        sig = np.sqrt((1 - exact ** 2) / 1024)
+        assert abs(ez - exact) < zf * sig, (i, ez, exact)
+        assert abs(ez - ref) < zf * np.sqrt(2) * sig, (i, ez, ref)
+
+
+def test_xy_cycle_amplitudes_vs_oracle(ctx, disorder):
+    """xy-cycle.py:141-157: the kick polarisation alternates x / y every 5 steps.  t = 7 crosses the switch; noisy
+    trajectory amplitudes (forward and echo) against the oracle at 1e-10."""
+    L = 11
+    hs, phis = disorder[20][0][2][:L], disorder[20][1][2][:L - 1]
+    sched = lambda step: "x" if (step // 5) % 2 == 0 else "y"
+    for echo in (False, True):
+        ops, _, _ = C.autocorr_gates("vacuum", L, 0.97, hs, phis, 7, L // 2, echo, pol_schedule=sched)
+        low = C.lower_level0(ops, C.SNAKE_LAYOUT)
+        circ = dtcsim.QuantumCircuit(31, 1)
+        for nm_, qs, ps, cs in low:
+            circ._add(nm_, qs, ps, cs)
+        oc, na, _ = O.compact_ops(low, 31)
+        prog = compile_circuit(circ, RC.noise_model(0.05))
+        psi, _ = _evolve_true(ctx, prog, 5, 11, 2024, engine=2)
+        ref = O.run_trajectories(oc, na, O.PauliNoise.depolarizing(0.05), 2024, np.arange(11, 16))
+        assert np.abs(psi - ref).max() < AMP_TOL
+
+
+def test_full_size_L20_counts_equal_c_oracle(disorder):
+    """get_counts() of the factorised n = 20 pipeline (k_frames -> k_tile_stream -> fused read-out -> k_readout_small ->
+    k_sample_rows) == the gate-by-gate C oracle on the full n = 21 register, trajectory by trajectory, at the size of
+    BASELINE config C2 (64 trajectories, forward and echo)."""
+    from oracle import philox
+    hs, phis = disorder[20][0][0], disorder[20][1][0]
+    sim = dtcsim.AerSimulator(noise_model=RC.noise_model(0.05), device="GPU", cuStateVec_enable=True)
+    onoise = O.PauliNoise.depolarizing(0.05)
+    shots = 64
+    for t, echo, seed in ((3, False, 1234), (2, True, 77)):
+        circ = RC.transpiled(RC.qc_body("vacuum", 20, 0.97, hs, phis, t, 10, echo))
+        res = sim.run(circ, shots=shots, seed_simulator=seed).result()
+        assert res.data()["register_qubits"] == 20 and res.data()["n_qubits"] == 21
+        oc, na, _ = O.compact_ops(RC.ops_of(circ), 31)
+        (mq, _c), = O.measured_map(oc)
+        buf = np.empty(1 << na, dtype=np.complex128)
+        vals, p1s = [], []
+        for tr in range(shots):
+            psi = CO.run_trajectory(oc, na, onoise, seed, tr, out=buf)
+            p1 = CO.prob1(psi, na, mq)
+            u = philox.uniform(seed, 0, philox.STREAM_MEASURE, np.array([tr], dtype=np.uint64))[0]
+            vals.append(int(O.sample_outcome(np.cumsum([1.0 - p1, p1]), u)))
+            p1s.append(p1)
+        want = O.counts_dict(vals, 1)
+        assert res.get_counts() == want, (t, echo, res.get_counts(), want)
+        assert abs(res.expectation_z()[0] - (1 - 2 * np.mean(p1s))) < 1e-10
+
+
+def test_density_matrix_every_probe_qubit(disorder):
+    """run() on the exact density-matrix path for EVERY probe site q (and t = 0): the measured bit must be taken from the
+    program that built rho (its bit order differs from the factorised trajectory program's)."""
+    sim = dtcsim.AerSimulator(noise_model=RC.noise_model(0.05), device="GPU", cuStateVec_enable=True)
+    onoise = O.PauliNoise.depolarizing(0.05)
+    for L, row in ((4, 4), (6, 20)):
+        hs, phis = disorder[row][0][0][:L], disorder[row][1][0][:L - 1]
+        for q in range(L):
+            for t, echo in ((0, False), (3, False), (2, True)):
+                circ = RC.transpiled(RC.qc_body("vacuum", L, 0.84, hs, phis, t, q, echo), backend=sim)
+                res = sim.run(circ, shots=1024, seed_simulator=11).result()
+                assert res.data()["method"] == "density_matrix"
+                want, info = O.run_counts(RC.ops_of(circ), 31, 1, shots=1024, noise=onoise, seed=11)
+                pr = info["probabilities"]
+                assert abs(res.expectation_z()[0] - (pr[0] - pr[1])) < DM_TOL, (L, q, t, echo)
+                assert res.get_counts() == want, (L, q, t, echo)
 
 
 def test_noiseless_echo_returns_to_start(disorder):
@@ -535,3 +638,66 @@ def test_engines_agree_on_random_circuits(ctx, seed):
         capi.set_stream_engine(None)
     assert all(np.array_equal(x, y) for x, y in zip(fa, fb))
     assert float((sa - b.state).abs().max()) < 1e-12
+
+
+# ---- sharded statevector (config C5) through the C ABI
+def _dtc_chain_circuit(L, t, rng, echo=False):
+    hs = rng.random(L) * 2 * np.pi - np.pi                      # generate_disorder.py:16-18
+    phis = rng.random(L - 1) * np.pi - 1.5 * np.pi
+    ops, _, _ = C.dtc_qasm_gates("1", L, 0.97, hs, phis, t)
+    if echo:
+        body = [o for o in ops if o[0] != "measure"]
+        ops = body + C.inverse_gates([o for o in body if o[0] != "x"]) + [o for o in ops if o[0] == "measure"]
+    low = C.lower_level0(ops)
+    circ = dtcsim.QuantumCircuit(L, L)
+    for nm_, qs, ps, cs in low:
+        circ._add(nm_, qs, ps, cs)
+    return circ, low
+
+
+@pytest.mark.parametrize("world,L,high_bit", [(1, 14, 15), (2, 16, 15), (4, 17, 9), (2, 18, 10)])
+def test_sharded_engine_vs_oracle(world, L, high_bit):
+    """CudaShardEngine + ShardedStatevector (rank bits in the diagonal phases, one-sweep top-group segments, slice
+    programs fused with the exchange, qubit permutation kept) against the oracle: a noisy trajectory of the dtc_qasm.py
+    circuit shape.  world > 1: the ranks are emulated by threads on this one GPU (sharded.ThreadFabric)."""
+    import threading
+    from dtcsim import capi, sharded
+    rng = np.random.default_rng(34 + L)
+    circ, low = _dtc_chain_circuit(L, 3, rng)
+    noise = RC.noise_model(0.2)
+    g = int(np.log2(world))
+    fabric = sharded.ThreadFabric(world) if world > 1 else None
+    results, errors = [None] * world, []
+
+    def work(rank):
+        try:
+            eng = sharded.CudaShardEngine(L, L - g, rank, world, 0, fabric=fabric)
+            allred = (lambda a: fabric.all_reduce(rank, a)) if fabric else None
+            sv = sharded.ShardedStatevector(L, rank, world, eng, all_reduce=allred)
+            r = sv.run(circ, noise, seed=11, trajectory=5)
+            results[rank] = (r, dict(sv.stats), eng.sliced_exchanges)
+            eng.close()
+        except Exception as exc:                      # surfaces in the main thread; peers fail on the broken barrier
+            errors.append(exc)
+            if fabric:
+                fabric.bar.abort()
+
+    capi.set_high_stride_bit(high_bit)
+    try:
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+    finally:
+        capi.set_high_stride_bit(15)
+    assert not errors, errors
+    oc, na, _ = O.compact_ops(low, L)
+    psi = O.run_trajectories(oc, na, O.PauliNoise.depolarizing(0.2), 11, [5])[0]
+    idx = np.arange(1 << L)
+    want = np.array([np.sum(np.abs(psi) ** 2 * (1 - 2 * ((idx >> q) & 1))) for q in range(L)])
+    for r, stats, n_sliced in results:
+        assert abs(r["norm"] - 1) < 1e-11
+        assert np.abs(np.array(r["expect_z"]) - want).max() < AMP_TOL
+        if world > 1:
+            assert stats["exchanges"] == n_sliced > 0 and stats["exchanges"] <= stats["layers"]

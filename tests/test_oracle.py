@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import golden_csv
+from conftest import family_z, golden_csv
 from oracle import c_oracle as CO
 from oracle import dtc_circuits as C
 from oracle import oracle as O
@@ -72,21 +72,32 @@ def _chi2(model, data, shots=1024):
     return float(np.mean(((data - model) / sig) ** 2))
 
 
+def _zmax(model, data, shots=1024):
+    """Largest |data - model| in units of the binomial standard error of a `shots`-shot estimate of `model`.
+    Compared with conftest.family_z(N): the 3-sigma bar of BASELINE.json's north_star held family-wise over N points."""
+    model, data = np.asarray(model), np.asarray(data)
+    sig = np.sqrt(np.maximum(1 - model ** 2, 1e-3) / shots)
+    return float(np.abs((data - model) / sig).max())
+
+
 @pytest.mark.parametrize("gain", ["0.01", "0.05"])
 def test_l4_committed_csv_statistics(disorder, gain):
-    """Reference's own 1024-shot Aer output (autocorr_data_L4/*gain*.csv): chi^2/dof ~ 1, all within 4.5 sigma."""
+    """Reference's own 1024-shot Aer output (autocorr_data_L4/*gain*.csv): chi^2/dof ~ 1 and every point within the
+    family-wise 3-sigma bound (conftest.family_z over the 2T points of each column pair)."""
     df = golden_csv(f"ref_L4_adaptive_gain{gain}.csv")
     T = len(df)
     fwd = [_l4_signal(disorder, 0.84, 0.05, i + 1, False) for i in range(T)]      # row i <-> t = i+1 (ctrl-g.py:412-416)
     ech = [_l4_signal(disorder, 0.84, 0.05, i + 1, True) for i in range(T)]
     c = _chi2(fwd + ech, list(df["av_autocorr_standard"]) + list(df["av_autocorr_echo_standard"]))
     assert 0.5 < c < 1.6, c
+    assert _zmax(fwd + ech, list(df["av_autocorr_standard"]) + list(df["av_autocorr_echo_standard"])) < family_z(2 * T)
     # adaptive columns: per-step g from the committed g_history (time-dependent-g circuits, ctrl-g.py:196-241)
     gh = list(df["g_history_inst1"])
     fa = [_l4_signal(disorder, 0.84, 0.05, i + 1, False, g_values=gh) for i in range(T)]
     ea = [_l4_signal(disorder, 0.84, 0.05, i + 1, True, g_values=gh) for i in range(T)]
     c2 = _chi2(fa + ea, list(df["forward_adaptive_inst1"]) + list(df["echo_adaptive_inst1"]))
     assert 0.5 < c2 < 1.6, c2
+    assert _zmax(fa + ea, list(df["forward_adaptive_inst1"]) + list(df["echo_adaptive_inst1"])) < family_z(2 * T)
 
 
 @pytest.mark.parametrize("pol", ["x", "y", "xy", "yx"])
@@ -105,8 +116,62 @@ def test_l20_polarization_csv_statistics(disorder, pol):
         model.append(anc * O.lightcone_zq(20, 0.97, hs, phis, t, 10, 0.05, echo=True, polarization=pol))
         data.append(df["av_autocorr_echo"][t])
     z = (np.array(data) - np.array(model)) / np.sqrt(np.maximum(1 - np.array(model) ** 2, 1e-3) / 1024)
-    assert np.abs(z).max() < 4.0, z
+    assert np.abs(z).max() < family_z(len(z)), z
     assert np.mean(z ** 2) < 2.5, z
+
+
+@pytest.mark.parametrize("pol", ["x", "y", "circular_left", "circular_right"])
+def test_l20_circular_csv_statistics(disorder, pol):
+    """autocorr_data_L20_circular-polarization/*pol{x,y,circular_left,circular_right}*.csv (circ-pol.py:110-173: per-step
+    kick angles pi g cos(w k)/sqrt 2, +-pi g sin(w k)/sqrt 2 with w = --circular_frequency = 1.0, echo undoing the steps
+    in reverse order) vs exact light-cone values with hs_L20/phis_L20 row 0."""
+    hs, phis = disorder[20][0][0], disorder[20][1][0]
+    df = golden_csv(f"ref_L20_circ_{pol}.csv")
+    two_layers = pol.startswith("circular")          # rx + ry per qubit per period: 2L noisy u3
+    tmax_f, tmax_e = (3, 1) if two_layers else (4, 2)
+    anc = 0.95 ** 6
+
+    def period(step):
+        return C.uf_gates(20, 0.97, phis, hs, pol, time_step=step, circular_frequency=1.0)
+
+    model, data = [], []
+    for t in range(0, tmax_f + 1):
+        model.append(anc * O.lightcone_zq(20, 0.97, hs, phis, t, 10, 0.05, period_fn=period))
+        data.append(df["av_autocorr"][t])
+    for t in range(0, tmax_e + 1):
+        model.append(anc * O.lightcone_zq(20, 0.97, hs, phis, t, 10, 0.05, echo=True, period_fn=period))
+        data.append(df["av_autocorr_echo"][t])
+    assert _zmax(model, data) < family_z(len(model)), (model, data)
+    assert _chi2(model, data) < 2.5
+
+
+def test_l20_controlled_g_csv_statistics(disorder):
+    """controlled-autocorr_data_L20/*optimization_iter5*.csv (g-opt.py:530-545): row i is the circuit of i+1 periods whose
+    step k uses g_history_inst1[k] (time-dependent g, echo undoing the steps in reverse order); the fixed-g baselines
+    g = 0.84 and g = 0.97 (g-opt.py get_instances) sit in the *_standard_* columns.  hs_L20/phis_L20 row 0."""
+    hs, phis = disorder[20][0][0], disorder[20][1][0]
+    df = golden_csv("ref_L20_controlled_iter5.csv")
+    gh = [float(x) for x in df["g_history_inst1"]]
+    anc = 0.95 ** 6
+    model, data = [], []
+    for i in range(4):                               # forward: i+1 periods, light cone of 2i+1 sites
+        t = i + 1
+        pf = lambda step: C.uf_gates(20, gh[step], phis, hs, "x")
+        model.append(anc * O.lightcone_zq(20, None, hs, phis, t, 10, 0.05, period_fn=pf))
+        data.append(df["forward_adaptive_inst1"][i])
+        for g, col in ((0.84, "forward_standard_g84_inst1"), (0.97, "forward_standard_g97_inst1")):
+            model.append(anc * O.lightcone_zq(20, g, hs, phis, t, 10, 0.05))
+            data.append(df[col][i])
+    for i in range(2):                               # echo: 2(i+1) periods
+        t = i + 1
+        pf = lambda step: C.uf_gates(20, gh[step], phis, hs, "x")
+        model.append(anc * O.lightcone_zq(20, None, hs, phis, t, 10, 0.05, echo=True, period_fn=pf))
+        data.append(df["echo_adaptive_inst1"][i])
+        for g, col in ((0.84, "echo_standard_g84_inst1"), (0.97, "echo_standard_g97_inst1")):
+            model.append(anc * O.lightcone_zq(20, g, hs, phis, t, 10, 0.05, echo=True))
+            data.append(df[col][i])
+    assert _zmax(model, data) < family_z(len(model)), (model, data)
+    assert _chi2(model, data) < 2.0
 
 
 def test_gate_counts_match_reference(disorder, gate_counts):

@@ -29,27 +29,32 @@ class NumpyShardEngine:
             self.psi[:] = 0
             if self.rank == 0:
                 self.psi[0] = 1.0
+        self._apply(self.psi, self.nl, self.rank, prog)
+
+    @staticmethod
+    def _apply(psi, nl, rank_bits, prog):
+        """Events of `prog` on a register of nl local bits whose higher index bits spell rank_bits."""
         ev = prog.arrays()
-        idx = np.arange(1 << self.nl)
+        idx = np.arange(1 << nl)
 
         def z(b):
-            if b < self.nl:
+            if b < nl:
                 return 1.0 - 2.0 * ((idx >> b) & 1)
-            return np.full(1 << self.nl, 1.0 - 2.0 * ((self.rank >> (b - self.nl)) & 1))
+            return np.full(1 << nl, 1.0 - 2.0 * ((rank_bits >> (b - nl)) & 1))
 
         for e in range(len(ev["type"])):
             t, q0, q1, val = int(ev["type"][e]), int(ev["q0"][e]), int(ev["q1"][e]), float(ev["val"][e])
             if t == 0:
-                assert q0 < self.nl, "rotation on a global qubit"
+                assert q0 < nl, "rotation on a global qubit"
                 c, s = np.cos(val / 2), np.sin(val / 2)
-                v = self.psi.reshape(-1, 2, 1 << q0)
+                v = psi.reshape(-1, 2, 1 << q0)
                 x0, x1 = v[:, 0, :].copy(), v[:, 1, :].copy()
                 v[:, 0, :] = c * x0 - 1j * s * x1
                 v[:, 1, :] = c * x1 - 1j * s * x0
             elif t == 1:
-                self.psi *= np.exp(-0.5j * val * z(q0))
+                psi *= np.exp(-0.5j * val * z(q0))
             else:
-                self.psi *= np.exp(-0.5j * val * z(q0) * z(q1))
+                psi *= np.exp(-0.5j * val * z(q0) * z(q1))
 
     def exchange(self, lq):
         import torch
@@ -81,7 +86,31 @@ class NumpyShardEngine:
         return np.array([np.sum(p * (1.0 - 2.0 * ((idx >> b) & 1))) for b in range(self.nl)]), float(p.sum())
 
 
-def _worker(rank, world, port, out):
+class NumpySlicedEngine(NumpyShardEngine):
+    """Adds the fused form the CUDA engine offers: the program of the lower local qubits is applied slice by slice
+    (slice d = what rank d receives, rank bits extended by d), then the top g local bits are exchanged."""
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self.sliced = 0
+
+    def exchange_sliced(self, prog, lq, first):
+        g = len(lq)
+        assert list(lq) == list(range(self.nl - g, self.nl))
+        if first:
+            self.psi[:] = 0
+            if self.rank == 0:
+                self.psi[0] = 1.0
+        S = 1 << (self.nl - g)
+        if prog is not None:
+            assert prog.n_main == self.nl - g
+            for d in range(1 << g):
+                self._apply(self.psi[d * S:(d + 1) * S], self.nl - g, (self.rank << g) | d, prog)
+        self.exchange(lq)
+        self.sliced += 1
+
+
+def _worker(rank, world, port, out, sliced=False):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -115,9 +144,11 @@ def _worker(rank, world, port, out):
 
     res = []
     for traj in (0, 5):
-        eng = NumpyShardEngine(L, L - int(np.log2(world)), rank, world)
+        eng = (NumpySlicedEngine if sliced else NumpyShardEngine)(L, L - int(np.log2(world)), rank, world)
         sv = sharded.ShardedStatevector(L, rank, world, eng, all_reduce=allred)
         r = sv.run(circ, noise, seed=11, trajectory=traj)
+        if sliced:
+            assert eng.sliced == sv.stats["exchanges"] > 0
         res.append((r["expect_z"], r["norm"], sv.stats["exchanges"], sv.stats["layers"]))
     if rank == 0:
         oc, na, _ = O.compact_ops(low, L)
@@ -131,12 +162,12 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_sharded_statevector_matches_oracle(world):
+@pytest.mark.parametrize("world,sliced", [(2, False), (4, False), (2, True), (4, True)])
+def test_sharded_statevector_matches_oracle(world, sliced):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out, sliced)) for r in range(world)]
     for p in procs:
         p.start()
     res, want = out.get(timeout=300)
