@@ -388,6 +388,69 @@ def sweep_leg(args, ctx, dist, rank, world, noise):
                         f"{args.trajectories} trajectories per point, points dealt over {world} rank(s)",
             "by_polarization": rec}
 
+
+# ------------------------------------------------------------------------------------------ config C3 (exact density matrix)
+def run_c3(args):
+    """BASELINE config C3: L = 12 exact noisy density-matrix evolution (rho = 2^24 complex128 = 256 MiB), 20 periods,
+    hs_L20/phis_L20 row 0 entries 0..11, g = 0.97, p = 0.05, observable <Z_6>.  One step = the 20-period evolution."""
+    import torch
+    import dtcsim
+    from dtcsim import backend
+    n, T = 12, 20
+    hs, phis = load_disorder(0)
+    hs, phis = hs[:n], phis[:n - 1]
+    c = dtcsim.QuantumCircuit(n, 1)
+    for _ in range(T):
+        for i in range(n):
+            c.rx(np.pi * G, i)
+        for i in range(0, n - 1, 2):
+            c.rzz(phis[i], i, i + 1)
+        for i in range(1, n - 1, 2):
+            c.rzz(phis[i], i, i + 1)
+        for i in range(n):
+            c.rz(hs[i], i)
+    c.measure(6, 0)
+    noise = dtcsim.NoiseModel()
+    noise.add_all_qubit_quantum_error(dtcsim.depolarizing_error(P_NOISE, 1), ["u1", "u2", "u3"], warnings=False)
+    prog = dtcsim.compile_circuit(dtcsim.lower_level0(c), dtcsim.as_noise_model(noise), want_dm=True)
+    ctx = backend.DeviceContext(0)
+    stats = {}
+    for _ in range(max(args.warmup, 3)):
+        rho = backend.run_density_matrix(ctx, prog, stats)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(args.steps, 20)
+    e0.record()
+    for _ in range(steps):
+        rho = backend.run_density_matrix(ctx, prog, stats)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / steps
+    d = 1 << n
+    diag = rho.view(d, d).diagonal().real.cpu().numpy()
+    ez = float(np.sum(diag * (1.0 - 2.0 * ((np.arange(d) >> prog.bit_of[6]) & 1))))
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_file))["hbm_gbs"]) if os.path.exists(peaks_file) else 6650.0
+    b_alg = 2 * 16 * (1 << (2 * n))                       # SURVEY 8d: one read + one write of rho per period
+    value = T / (ms * 1e-3)
+    ach = value * b_alg / 1e9
+    sweeps = stats["sweeps"]
+    line = {"metric": METRIC, "value": value, "unit": "periods/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
+            "data": "synthetic",
+            "config": {"workload": "C3: L=12 exact noisy density matrix (2^24 complex128 = 256 MiB), g=0.97, depolarizing p=0.05, "
+                                   "20 periods, <Z_6>", "l2_policy": "rho (256 MiB) is larger than L2"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "kernel": "k_dm_tile", "sweeps_per_period": sweeps / T,
+                         "per_sweep_gbs": sweeps * b_alg / (ms * 1e-3) / 1e9,
+                         "note": "achieved = periods/s x 2 x 16 B x 4^12 (SURVEY 8d byte model: ONE read + write of rho per period); "
+                                 "per_sweep_gbs = what each of the sweeps_per_period passes over rho sustains"},
+            "expect_z6_after_20_periods": ez, "trace": float(diag.sum()), "gpu_launches": steps * (2 * sweeps + 2), "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -583,6 +646,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--trajectories", type=int, default=1024)
     ap.add_argument("--tmax", type=int, default=30, help="sweep t = 0..tmax-1 (30 = BASELINE config)")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3"], help="C2 (default, the headline) or C3 (exact density matrix)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-record")
@@ -594,6 +658,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "C3":
+        run_c3(args)
     else:
         run_ours(args)
 

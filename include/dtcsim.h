@@ -177,6 +177,14 @@ int dtc_dm_diag(void *rho, int n, int n1, const int32_t *q1, const double *a,
                 int n2, const int32_t *qi, const int32_t *qj, const double *b, void *stream);
 int dtc_dm_pauli_channel(void *rho, int n, int qubit, double px, double py, double pz, void *stream);
 int dtc_dm_probs(const void *rho, int n, int k, const int32_t *qubits, double *out, void *stream);
+/* A whole density-matrix program in one call (Aer method density_matrix inside run(), fast.py:211, for n <= 13).  Segments in
+ * circuit order: seg_type[i] = 0 rotations RX(val) on q0, 1 diagonal terms exp(-i val Z_q0 / 2) (q1 < 0) or
+ * exp(-i val Z_q0 Z_q1 / 2), 2 Pauli channels (probs[k][3] = pX, pY, pZ) on q0; items of segment i are
+ * [seg_off[i], seg_off[i+1]).  A rotation segment and the channel segment that follows it are applied per qubit in one
+ * sweep of rho for up to six qubits at a time; a diagonal segment is folded into the load of the next sweep.
+ * n_sweeps_or_null: number of passes over rho the call made. */
+int dtc_dm_run(void *rho, int n, int n_seg, const int32_t *seg_type, const int32_t *seg_off, const int32_t *q0,
+               const int32_t *q1, const double *val, const double *probs, int *n_sweeps_or_null, void *stream);
 
 /* ---- sharded statevector support (top log2(P) qubits global) ------------------------------ */
 /* Pack / unpack for the all-to-all that exchanges the g = log2(P) global qubits with local qubits

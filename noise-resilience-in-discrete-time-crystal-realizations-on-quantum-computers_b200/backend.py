@@ -200,8 +200,33 @@ def sample_rows(ctx, probs, n_samples, seed, traj_offset):
     return out.view(rows, n_samples)
 
 
-def run_density_matrix(ctx, prog):
-    """Exact noisy evolution of rho (Aer method density_matrix); returns the rho tensor (2^n x 2^n, [col,row])."""
+def flatten_dm_segments(segments):
+    """prog.dm_segments -> the flat arrays of dtc_dm_run (seg_type, seg_off, q0, q1, val, probs)."""
+    seg_type, seg_off, q0, q1, val, probs = [], [0], [], [], [], []
+    for seg in segments:
+        if seg[0] == "R":
+            seg_type.append(0)
+            for q, th in seg[1]:
+                q0.append(q); q1.append(-1); val.append(th); probs.append((0.0, 0.0, 0.0))
+        elif seg[0] == "D":
+            seg_type.append(1)
+            for q, a in seg[1].items():
+                q0.append(q); q1.append(-1); val.append(a); probs.append((0.0, 0.0, 0.0))
+            for (i, j), b in seg[2].items():
+                q0.append(i); q1.append(j); val.append(b); probs.append((0.0, 0.0, 0.0))
+        else:
+            seg_type.append(2)
+            for q, pr in seg[1]:
+                q0.append(q); q1.append(-1); val.append(0.0); probs.append(tuple(pr))
+        seg_off.append(len(q0))
+    return (np.asarray(seg_type, dtype=np.int32), np.asarray(seg_off, dtype=np.int32), np.asarray(q0, dtype=np.int32),
+            np.asarray(q1, dtype=np.int32), np.asarray(val, dtype=np.float64),
+            np.asarray(probs, dtype=np.float64).reshape(-1, 3))
+
+
+def run_density_matrix(ctx, prog, stats=None):
+    """Exact noisy evolution of rho (Aer method density_matrix); returns the rho tensor (2^n x 2^n, [col,row]).
+    One C-ABI call for the whole program (dtc_dm_run); stats["sweeps"] = passes over rho it made."""
     torch = ctx.torch
     lib = capi.load()
     n = prog.n
@@ -210,21 +235,13 @@ def run_density_matrix(ctx, prog):
     rho = ctx.empty(1 << (2 * n), torch.complex128)
     s = ctx.stream
     capi.check(lib.dtc_dm_init(rho.data_ptr(), n, 0, s))
-    for seg in prog.dm_segments:
-        if seg[0] == "R":
-            for q, th in seg[1]:
-                capi.check(lib.dtc_dm_rot(rho.data_ptr(), n, int(q), float(th), s))
-        elif seg[0] == "D":
-            _, d1, d2 = seg
-            q1, q1p = capi.i32(list(d1.keys()))
-            a, ap = capi.f64(list(d1.values()))
-            qi, qip = capi.i32([k[0] for k in d2])
-            qj, qjp = capi.i32([k[1] for k in d2])
-            b, bp = capi.f64(list(d2.values()))
-            capi.check(lib.dtc_dm_diag(rho.data_ptr(), n, len(q1), q1p, ap, len(qi), qip, qjp, bp, s))
-        else:
-            for q, (px, py, pz) in seg[1]:
-                capi.check(lib.dtc_dm_pauli_channel(rho.data_ptr(), n, int(q), px, py, pz, s))
+    st, so, q0, q1, val, pr = flatten_dm_segments(prog.dm_segments)
+    sweeps = ctypes.c_int(0)
+    capi.check(lib.dtc_dm_run(rho.data_ptr(), n, len(st), st.ctypes.data_as(capi.c_i32p), so.ctypes.data_as(capi.c_i32p),
+                              q0.ctypes.data_as(capi.c_i32p), q1.ctypes.data_as(capi.c_i32p),
+                              val.ctypes.data_as(capi.c_f64p), pr.ctypes.data_as(capi.c_f64p), ctypes.byref(sweeps), s))
+    if stats is not None:
+        stats["sweeps"] = sweeps.value
     return rho
 
 
@@ -412,7 +429,6 @@ class DTCSimulator:
             meas = prog.measures
             mq = [q for q, _ in meas]
             cbits = np.array([c for _, c in meas], dtype=np.int64)
-            data["register_qubits"] = prog.n
             rho = run_density_matrix(ctx, prog)
             probs = ctx.empty(1 << k, torch.float64)
             _, qp = capi.i32(mq)

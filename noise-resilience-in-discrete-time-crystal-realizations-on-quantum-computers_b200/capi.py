@@ -59,6 +59,8 @@ _SIGS = {
     "dtc_dm_pauli_channel": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                             ctypes.c_double, c_vp]),
     "dtc_dm_probs": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_i32p, c_vp, c_vp]),
+    "dtc_dm_run": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_i32p, c_i32p, c_i32p, c_i32p, c_f64p, c_f64p,
+                                  ctypes.POINTER(ctypes.c_int), c_vp]),
     "dtc_shard_pack": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i32p, c_vp]),
     "dtc_shard_unpack": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i32p, c_vp]),
 }

@@ -827,6 +827,108 @@ __global__ void k_dm_channel(double2* __restrict__ rho, int n, int q, double px,
     rho[i10] = make_double2(oA * e10.x + oB * e01.x, oA * e10.y + oB * e01.y);
 }
 
+
+// ---- density matrix, fused: one sweep of rho applies, to up to six qubits at once, the rotation on the row bit, its
+// conjugate on the column bit and the Pauli channel that follows (a 2 x 2 block of rho per qubit), with the diagonal layer
+// that precedes them folded into the load.  rho is a 2n-bit vector (index = row + 2^n col); a tile holds 2^TB elements:
+// optional passive row bits {0,1} (64 B runs) + the row and column bits of the pass's qubits.
+#define DTC_DM_MAXQ 6
+#define DTC_DM_THREADS 256
+struct DmQubitOp {
+    int lr, lc;                      // tile-local positions of the qubit's row / column bit (lr < lc)
+    double c, s;                     // cos, sin of theta/2 (row: RX(theta), column: its conjugate)
+    double dA, dB, oA, oB;           // channel: diagonal block mixing (r == c), off-diagonal block mixing (r != c)
+};
+struct DmTilePass {
+    int n, tile_bits, nq, has_diag;
+    int tb[12];                      // global bit of tile-local bit l
+    int seg_n, seg_src[8], seg_len[8], seg_dst[8];     // CTA index -> global base (bits outside the tile)
+    DmQubitOp q[DTC_DM_MAXQ];
+};
+struct DmDiagTerms {
+    int n1, n2;
+    int q1[16];
+    double a[16];
+    int qi[DTC_MAXT], qj[DTC_MAXT];
+    double b[DTC_MAXT];
+};
+
+// T[x] = exp(-i phi(x)), phi(x) = sum_k a_k z_k(x)/2 + sum_k b_k z_i z_j /2 : rho[r,c] *= T[r] conj(T[c])
+__global__ void k_dm_phase_table(double2* __restrict__ T, int n, const __grid_constant__ DmDiagTerms D) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= (1 << n)) return;
+    double ang = 0.0;
+    for (int k = 0; k < D.n1; ++k) ang += 0.5 * D.a[k] * (double)(1 - 2 * ((x >> D.q1[k]) & 1));
+    for (int k = 0; k < D.n2; ++k) ang += 0.5 * D.b[k] * (double)(1 - 2 * (((x >> D.qi[k]) ^ (x >> D.qj[k])) & 1));
+    double sn, cs;
+    sincos(ang, &sn, &cs);
+    T[x] = make_double2(cs, -sn);
+}
+
+__global__ void k_dm_apply_table(double2* __restrict__ rho, int n, const double2* __restrict__ T) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1ll << (2 * n))) return;
+    const double2 tr = T[(u64)i & ((1ull << n) - 1)], tc = T[(u64)i >> n];
+    rho[i] = cmul(rho[i], cmul(tr, make_double2(tc.x, -tc.y)));
+}
+
+__global__ void __launch_bounds__(DTC_DM_THREADS)
+k_dm_tile(double2* __restrict__ rho, const __grid_constant__ DmTilePass P, const double2* __restrict__ T) {
+    extern __shared__ __align__(16) double2 dm_tile[];
+    const int tid = threadIdx.x, ne = 1 << P.tile_bits;
+    u64 base = 0;
+    for (int k = 0; k < P.seg_n; ++k)
+        base |= (((u64)blockIdx.x >> P.seg_src[k]) & ((1ull << P.seg_len[k]) - 1)) << P.seg_dst[k];
+    const u64 rmask = (1ull << P.n) - 1;
+    for (int i = tid; i < ne; i += DTC_DM_THREADS) {
+        u64 g = base;
+#pragma unroll
+        for (int l = 0; l < 12; ++l)
+            if (l < P.tile_bits && ((i >> l) & 1)) g |= 1ull << P.tb[l];
+        double2 v = rho[g];
+        if (P.has_diag) {
+            const double2 tr = T[g & rmask], tc = T[g >> P.n];
+            v = cmul(v, cmul(tr, make_double2(tc.x, -tc.y)));
+        }
+        dm_tile[i] = v;
+    }
+    __syncthreads();
+    for (int k = 0; k < P.nq; ++k) {
+        const DmQubitOp& Q = P.q[k];
+        const int lowr = (1 << Q.lr) - 1, lowc = (1 << Q.lc) - 1;
+        for (int gidx = tid; gidx < (ne >> 2); gidx += DTC_DM_THREADS) {
+            int x = ((gidx & ~lowr) << 1) | (gidx & lowr);          // zero at bit lr
+            x = ((x & ~lowc) << 1) | (x & lowc);                    // zero at bit lc (lc > lr)
+            const int i00 = x, i10 = x | (1 << Q.lr), i01 = x | (1 << Q.lc), i11 = i10 | i01;   // i<row bit><column bit>
+            double2 e00 = dm_tile[i00], e10 = dm_tile[i10], e01 = dm_tile[i01], e11 = dm_tile[i11];
+            const double c = Q.c, s = Q.s;
+            // rows: [[c, -i s], [-i s, c]] on (r = 0, r = 1) for each column bit
+            double2 a00 = make_double2(c * e00.x + s * e10.y, c * e00.y - s * e10.x);
+            double2 a10 = make_double2(c * e10.x + s * e00.y, c * e10.y - s * e00.x);
+            double2 a01 = make_double2(c * e01.x + s * e11.y, c * e01.y - s * e11.x);
+            double2 a11 = make_double2(c * e11.x + s * e01.y, c * e11.y - s * e01.x);
+            // columns: the conjugate [[c, +i s], [+i s, c]] on (c = 0, c = 1) for each row bit
+            e00 = make_double2(c * a00.x - s * a01.y, c * a00.y + s * a01.x);
+            e01 = make_double2(c * a01.x - s * a00.y, c * a01.y + s * a00.x);
+            e10 = make_double2(c * a10.x - s * a11.y, c * a10.y + s * a11.x);
+            e11 = make_double2(c * a11.x - s * a10.y, c * a11.y + s * a10.x);
+            // Pauli channel on the (row bit, column bit) block
+            dm_tile[i00] = make_double2(Q.dA * e00.x + Q.dB * e11.x, Q.dA * e00.y + Q.dB * e11.y);
+            dm_tile[i11] = make_double2(Q.dA * e11.x + Q.dB * e00.x, Q.dA * e11.y + Q.dB * e00.y);
+            dm_tile[i10] = make_double2(Q.oA * e10.x + Q.oB * e01.x, Q.oA * e10.y + Q.oB * e01.y);
+            dm_tile[i01] = make_double2(Q.oA * e01.x + Q.oB * e10.x, Q.oA * e01.y + Q.oB * e10.y);
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < ne; i += DTC_DM_THREADS) {
+        u64 g = base;
+#pragma unroll
+        for (int l = 0; l < 12; ++l)
+            if (l < P.tile_bits && ((i >> l) & 1)) g |= 1ull << P.tb[l];
+        rho[g] = dm_tile[i];
+    }
+}
+
 __global__ void k_dm_probs(const double2* __restrict__ rho, int n, int k, const int* __restrict__ qubits,
                            double* __restrict__ out) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1473,6 +1575,155 @@ int dtc_dm_pauli_channel(void* rho, int n, int qubit, double px, double py, doub
     const long long ng = 1ll << (2 * n - 2);
     k_dm_channel<<<(unsigned)((ng + 255) / 256), 256, 0, (cudaStream_t)stream>>>((double2*)rho, n, qubit, px, py, pz);
     CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
+
+
+// Whole density-matrix program in one call (replaces a per-gate launch loop on the host side): segments of rotations (type 0),
+// diagonal terms (1) and Pauli channels (2) in circuit order.  Rotation + channel segments that follow each other are fused
+// per qubit; their qubits are swept in groups of up to six per pass; a diagonal segment becomes a phase table that the next
+// pass applies while loading (or one elementwise pass if nothing follows).
+int dtc_dm_run(void* rho, int n, int n_seg, const int32_t* seg_type, const int32_t* seg_off, const int32_t* q0,
+               const int32_t* q1, const double* val, const double* probs, int* n_sweeps, void* stream) {
+    if (!rho || n < 1 || n > 13 || n_seg < 0 || (n_seg > 0 && (!seg_type || !seg_off || !q0 || !q1 || !val || !probs)))
+        return fail(DTC_ERR_INVALID, "bad argument (n <= 13)");
+    DeviceGuard guard(device_of(rho));
+    CUDA_TRY(guard.err);
+    cudaStream_t s = (cudaStream_t)stream;
+    static bool attr_set[DTC_MAX_DEVICES] = {false};
+    {
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < DTC_MAX_DEVICES && !attr_set[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(k_dm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
+            attr_set[dev] = true;
+        }
+    }
+    double2* T = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&T, sizeof(double2) << n, s));
+    bool diag_pending = false;
+    int sweeps = 0;
+    const int TB = (2 * n < 12) ? 2 * n : 12;
+    struct QOp { bool used; double theta, px, py, pz; };
+    int i = 0;
+    while (i < n_seg) {
+        if (seg_type[i] == 1) {
+            if (diag_pending) {                          // two diagonal segments in a row: flush the first
+                const long long ne = 1ll << (2 * n);
+                k_dm_apply_table<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>((double2*)rho, n, T);
+                ++sweeps;
+            }
+            DmDiagTerms D;
+            memset(&D, 0, sizeof(D));
+            for (int k = seg_off[i]; k < seg_off[i + 1]; ++k) {
+                if (q0[k] < 0 || q0[k] >= n || q1[k] >= n) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "diagonal term: qubit out of range"); }
+                if (q1[k] < 0) {
+                    if (D.n1 >= 16) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "too many one-body terms"); }
+                    D.q1[D.n1] = q0[k]; D.a[D.n1] = val[k]; ++D.n1;
+                } else {
+                    if (D.n2 >= DTC_MAXT) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "too many two-body terms in one segment"); }
+                    D.qi[D.n2] = q0[k]; D.qj[D.n2] = q1[k]; D.b[D.n2] = val[k]; ++D.n2;
+                }
+            }
+            k_dm_phase_table<<<((1 << n) + 127) / 128, 128, 0, s>>>(T, n, D);
+            diag_pending = true;
+            ++i;
+            continue;
+        }
+        // a layer of qubit operations: [rotations] [channels]
+        QOp ops[16];
+        for (int q = 0; q < 16; ++q) ops[q] = QOp{false, 0.0, 0.0, 0.0, 0.0};
+        int j = i;
+        if (seg_type[j] == 0) {
+            for (int k = seg_off[j]; k < seg_off[j + 1]; ++k) {
+                if (q0[k] < 0 || q0[k] >= n || ops[q0[k]].used) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "rotation segment: bad or repeated qubit"); }
+                ops[q0[k]].used = true;
+                ops[q0[k]].theta = val[k];
+            }
+            ++j;
+        }
+        if (j < n_seg && seg_type[j] == 2) {
+            bool seen[16] = {false};
+            for (int k = seg_off[j]; k < seg_off[j + 1]; ++k) {
+                if (q0[k] < 0 || q0[k] >= n || seen[q0[k]]) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "channel segment: bad or repeated qubit"); }
+                seen[q0[k]] = true;
+                QOp& o = ops[q0[k]];
+                o.used = true;
+                o.px = probs[3 * k]; o.py = probs[3 * k + 1]; o.pz = probs[3 * k + 2];
+            }
+            ++j;
+        } else if (j == i) {
+            cudaFreeAsync(T, s);
+            return fail(DTC_ERR_INVALID, "unknown segment type");
+        }
+        i = j;
+        // groups of qubits per sweep
+        int todo[16], nt = 0;
+        for (int q = 0; q < n; ++q)
+            if (ops[q].used) todo[nt++] = q;
+        int pos = 0;
+        while (pos < nt) {
+            DmTilePass P;
+            memset(&P, 0, sizeof(P));
+            P.n = n;
+            P.tile_bits = TB;
+            const bool low_pair = (todo[pos] == 0 && pos + 1 < nt && todo[pos + 1] == 1) || 2 * n <= 12;
+            const int passive = low_pair ? 0 : (TB >= 4 ? 2 : 0);           // row bits {0,1}: 64 B runs
+            int cap = (TB - passive) / 2;
+            if (cap > DTC_DM_MAXQ) cap = DTC_DM_MAXQ;
+            int grp[DTC_DM_MAXQ], ng = 0;
+            while (pos < nt && ng < cap) {
+                if (passive && todo[pos] < 2) {              // qubit 0 or 1 without its partner: it takes a pass of its own kind
+                    if (ng) break;
+                    grp[ng++] = todo[pos++];
+                    break;
+                }
+                grp[ng++] = todo[pos++];
+            }
+            // tile bits: passive row bits (unless they belong to a qubit of the group), then row bits, then column bits, ascending;
+            // spare positions are filled with the lowest unused row bits (they ride along untouched)
+            u64 used = 0;
+            for (int k = 0; k < ng; ++k) used |= (1ull << grp[k]) | (1ull << (grp[k] + n));
+            if (passive) used |= 3ull;
+            for (int b = 0; b < 2 * n && dtc_popc(used) < TB; ++b) used |= 1ull << b;
+            int l = 0;
+            for (int b = 0; b < 2 * n; ++b)
+                if ((used >> b) & 1ull) P.tb[l++] = b;
+            P.nq = ng;
+            for (int k = 0; k < ng; ++k) {
+                DmQubitOp& Q = P.q[k];
+                for (int m = 0; m < TB; ++m) {
+                    if (P.tb[m] == grp[k]) Q.lr = m;
+                    if (P.tb[m] == grp[k] + n) Q.lc = m;
+                }
+                const QOp& o = ops[grp[k]];
+                Q.c = cos(0.5 * o.theta); Q.s = sin(0.5 * o.theta);
+                Q.dA = 1.0 - o.px - o.py; Q.dB = o.px + o.py;
+                Q.oA = 1.0 - o.px - o.py - 2.0 * o.pz; Q.oB = o.px - o.py;
+            }
+            int src = 0, p2 = 0;
+            while (p2 < 2 * n) {
+                if ((used >> p2) & 1ull) { ++p2; continue; }
+                int len = 0;
+                while (p2 + len < 2 * n && !((used >> (p2 + len)) & 1ull)) ++len;
+                if (P.seg_n >= 8) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "internal: too many index segments"); }
+                P.seg_src[P.seg_n] = src; P.seg_len[P.seg_n] = len; P.seg_dst[P.seg_n] = p2; ++P.seg_n;
+                src += len; p2 += len;
+            }
+            P.has_diag = diag_pending ? 1 : 0;
+            diag_pending = false;
+            k_dm_tile<<<1u << (2 * n - TB), DTC_DM_THREADS, sizeof(double2) << TB, s>>>((double2*)rho, P, T);
+            ++sweeps;
+        }
+    }
+    if (diag_pending) {
+        const long long ne = 1ll << (2 * n);
+        k_dm_apply_table<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>((double2*)rho, n, T);
+        ++sweeps;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(T, s));
+    if (n_sweeps) *n_sweeps = sweeps;
     return DTC_OK;
 }
 
