@@ -466,6 +466,10 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = backend.DeviceContext(local)
+    if args.no_resident:
+        capi.RESIDENT = False
+    if args.resident_mb:
+        capi.set_resident_bytes(args.resident_mb << 20)
     hs, phis = load_disorder(rank)                      # weak scaling: one disorder instance per rank (C4)
     points = sweep_points(args.tmax)
     noise = dtcsim.NoiseModel()
@@ -483,6 +487,7 @@ def run_ours(args):
     state = ctx.empty(bt << nmax, torch.complex128)
     sums = torch.zeros(len(points), 2, dtype=torch.float64, device=ctx.device)
     launches = [0]
+    resident = [0]
 
     def step(seed):
         sums.zero_()
@@ -494,7 +499,9 @@ def run_ours(args):
                 # read-out: the density matrix of site q comes out of the last pass (fused) or of a dtc_rdm reduction
                 # taken now (the state buffer is reused by the next circuit); k_readout_small finishes it below
                 pending.append((i, batch, batch.readout_rdm() if prog.small else None))
-                launches[0] += 1 + h.num_passes + (1 if batch.fused_rdm is not None else 2)
+                # kernels of this run (frames + sweeps: one persistent launch in resident execution) + read-out kernels
+                launches[0] += h.last_run_info()[1] + (1 if batch.fused_rdm is not None else 2)
+                resident[0] += int(getattr(batch, "resident", False))
         for i, batch, rdm in pending:
             pr = batch.outcome_probs(rdm)
             ez = pr[:, 0] - pr[:, 1]
@@ -517,7 +524,8 @@ def run_ours(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches[0] = 0
-    pass_ms, pass_n, half_passes = 0.0, 0, 0
+    resident[0] = 0
+    pass_ms, pass_n, half_passes, n_timed_launches = 0.0, 0, 0, 0
     e0.record()
     for k in range(args.steps):
         step(1234 + k)
@@ -529,6 +537,7 @@ def run_ours(args):
             ms, n = h.pass_time()
             pass_ms += ms
             pass_n += n
+            n_timed_launches += 1 if h.last_run_info()[0] else n
             half_passes += sum(h.last_run_flags())        # passes that only write (generated start) or only read (fused read-out)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
@@ -554,23 +563,28 @@ def run_ours(args):
     n_stream = int(sum(h.num_stream_passes for h in handles))
     n_pass_all = int(sum(h.num_passes for h in handles))
     traffic, traffic_src = None, None
-    tf = os.path.join(ROOT, "profiles", "ncu_tile_stream_traffic.json")      # from the committed ncu --set full capture
+    tf = os.path.join(ROOT, "profiles", "ncu_tile_resident_traffic.json" if resident[0] > 0 else "ncu_tile_stream_traffic.json")
     if os.path.exists(tf):
         with open(tf) as fh:
             tj = json.load(fh)
-        traffic = float(tj["dram_bytes_per_algorithmic_byte"]) * bytes_per_launch   # per full-traffic launch
+        traffic = float(tj["dram_bytes_per_algorithmic_byte"]) * bytes_per_launch   # per full-traffic sweep
         traffic_src = ("not measured in this run: DRAM bytes / algorithmic byte of the committed ncu --set full capture "
                        f"({tj.get('source', 'profiles/')}) x this run's bytes_per_launch")
+    is_resident = resident[0] > 0
     if pass_n:
-        avg_ms = pass_ms / pass_n
+        avg_ms = pass_ms / max(n_timed_launches, 1)
         # algorithmic bytes of the timed launches: a full pass reads and writes the batch once; the first pass of a
         # circuit only writes it (generated start) and a fused last pass only reads it
         alg_bytes = bytes_per_launch * (pass_n - 0.5 * half_passes)
         ach = alg_bytes / (pass_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "kernel": "k_tile_stream" if 2 * n_stream >= n_pass_all else "k_tile_pass",
-                "stream_passes": n_stream, "passes": n_pass_all, "avg_launch_ms": avg_ms, "launches_timed": pass_n,
-                "bytes_per_launch": bytes_per_launch, "half_traffic_launches": half_passes,
+                "kernel": "k_tile_resident" if is_resident else ("k_tile_stream" if 2 * n_stream >= n_pass_all else "k_tile_pass"),
+                "stream_passes": n_stream, "passes": n_pass_all, "avg_launch_ms": avg_ms, "launches_timed": n_timed_launches,
+                "sweeps_timed": pass_n, "bytes_per_sweep": bytes_per_launch,
+                "bytes_per_launch": alg_bytes / max(n_timed_launches, 1), "half_traffic_sweeps": half_passes,
+                "execution": ("resident: one persistent launch per circuit runs all its sweeps over groups of trajectories whose "
+                              "states stay in L2 (algorithmic bytes are what a sweep-per-pass execution moves through HBM; see "
+                              "traffic for the DRAM bytes actually moved)") if is_resident else "one launch per sweep, batch streamed through HBM",
                 "algorithmic_bytes_timed": alg_bytes, "peak_source": peak_src,
                 "register_qubits": nmax, "traffic_source": traffic_src,
                 "periods_frac_actual_register": (value / world) * (2 * 16 * (1 << nmax)) / (peak * 1e9)}
@@ -630,7 +644,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "complex128", "data": "synthetic", "config": workload_config(args),
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
-                "passes_per_sweep": int(sum(h.num_passes for h in handles)), "periods_per_sweep": periods_of(points),
+                "passes_per_sweep": n_pass_all, "periods_per_sweep": periods_of(points),
                 "autocorr_forward_t1_t2": [float(autocorr[1]), float(autocorr[2])] if args.tmax > 2 else None}
         line.update(extra)
         print(json.dumps(line), flush=True)
@@ -649,6 +663,8 @@ def main():
     ap.add_argument("--config", default="C2", choices=["C2", "C3"], help="C2 (default, the headline) or C3 (exact density matrix)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-resident", action="store_true", help="one launch per sweep, batch streamed through HBM (round-1 execution)")
+    ap.add_argument("--resident-mb", type=int, default=0, help="state MiB kept in flight per group in resident execution (default 64)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-record")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded-statevector (C5) sub-record")
     ap.add_argument("--sharded-periods", type=int, default=10, help="C5: periods forward (+ the same number inverse)")

@@ -137,6 +137,23 @@ int dtc_program_readout(const dtc_program *p, const void *rdm, void *workspace, 
 int dtc_program_set_fused_rdm(dtc_program *p, int enable, int *active_or_null);
 int dtc_program_fused_rdm(const dtc_program *p, void *workspace, int64_t n_traj, void **rdm);
 
+/* Resident execution (read-out-only runs; replaces the whole per-shot evolution loop of AerSimulator.run(), fast.py:211,
+ * in ONE persistent launch).  When every pass of the program runs on the streaming engine and the fused read-out is active
+ * (dtc_program_set_fused_rdm), the trajectories are processed in groups of `group` that go through ALL passes before the
+ * next group starts and share `group` state slots, so the sweeps read and write L2-resident data instead of streaming the
+ * batch through HBM once per pass.  resident_info(): eligibility, group size and the scratch bytes (group x 2^n_local
+ * complex128) run_resident() needs instead of a state buffer for the whole batch.  The result is the fused read-out density
+ * matrix (dtc_program_fused_rdm) and the frames, exactly as after dtc_program_run with the fused read-out; the scratch
+ * buffer holds no defined state afterwards.  Returns DTC_ERR_UNSUPPORTED when the program is not eligible.
+ * dtc_set_resident_bytes(): state bytes kept in flight per group (default 64 MiB of the 126 MB L2). */
+int dtc_set_resident_bytes(size_t bytes);
+int dtc_program_resident_info(const dtc_program *p, int64_t n_traj, int *eligible, int *group, size_t *scratch_bytes);
+int dtc_program_run_resident(dtc_program *p, void *scratch, size_t scratch_bytes, int64_t n_traj, int64_t traj_offset,
+                             uint64_t seed, uint64_t init_index, uint64_t rank_bits, void *workspace,
+                             size_t workspace_bytes, void *stream);
+/* *resident = 1 if the last run used resident execution; *kernel_launches = kernels that run launched. */
+int dtc_program_last_run_info(const dtc_program *p, int *resident, int *kernel_launches);
+
 /* ---- state utilities ---------------------------------------------------------------------- */
 /* In-place psi' -> psi_true for each trajectory (used for amplitude-level parity / save_statevector). */
 int dtc_materialize(void *state, int n_local, int64_t n_traj, const uint64_t *fx, const uint64_t *fz,

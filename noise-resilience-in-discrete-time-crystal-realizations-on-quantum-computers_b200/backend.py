@@ -178,13 +178,23 @@ def evolve(ctx, prog, n_traj, traj_offset=0, seed=0, engine=capi.ENGINE_AUTO, ha
         handle = capi.ProgramHandle(prog, ctx.index, engine)
     n = handle.n_local
     need = n_traj << n
-    if state is None or state.numel() < need:
-        state = ctx.empty(need, torch.complex128)
     wsb = handle.workspace_bytes(n_traj)
     ws = ctx.empty(wsb, torch.uint8)
     fused = handle.set_fused_rdm(bool(fused_rdm) and getattr(prog, "small", None) is not None)
-    handle.run(state.data_ptr(), n_traj, traj_offset, seed, ws.data_ptr(), wsb, ctx.stream, init_index=init_index)
+    resident, group, scratch_bytes = handle.resident_info(n_traj) if (fused and capi.RESIDENT) else (False, 0, 0)
+    if resident:
+        # read-out-only run of a program whose passes all stream: one persistent launch, `group` L2-resident state slots
+        need = scratch_bytes // 16
+        if state is None or state.numel() < need:
+            state = ctx.empty(need, torch.complex128)
+        handle.run_resident(state.data_ptr(), scratch_bytes, n_traj, traj_offset, seed, ws.data_ptr(), wsb, ctx.stream,
+                            init_index=init_index)
+    else:
+        if state is None or state.numel() < need:
+            state = ctx.empty(need, torch.complex128)
+        handle.run(state.data_ptr(), n_traj, traj_offset, seed, ws.data_ptr(), wsb, ctx.stream, init_index=init_index)
     batch = TrajectoryBatch(ctx, handle, state[:need], ws, n_traj, traj_offset)
+    batch.resident = resident
     if fused:
         off = handle.fused_rdm_ptr(ws.data_ptr(), n_traj) - ws.data_ptr()
         batch.fused_rdm = ws[off:off + 64 * n_traj].view(torch.complex128).view(n_traj, 2, 2)
@@ -461,7 +471,14 @@ class DTCSimulator:
             per = 16 << nm_
             budget = self.max_memory_bytes or int(0.7 * ctx.free_bytes())
             bt = max(1, min(shots, budget // per))
-            state = self._state_buffer(bt << nm_)
+            state = None
+            if k <= MAX_PROB_QUBITS and prog0.small is not None and capi.RESIDENT and handle.set_fused_rdm(True):
+                resident, _g, sbytes = handle.resident_info(shots)
+                if resident:                              # whole batch in one persistent launch, a few L2-resident state slots
+                    bt = shots
+                    state = self._state_buffer(sbytes // 16)
+            if state is None:
+                state = self._state_buffer(bt << nm_)
             queued = []                                   # per batch: (offset, n, device columns / indices, device prob sums)
             ez_sum = None                                 # wide measurements: sum over trajectories of <Z_q> (device)
             for a in range(0, shots, bt):

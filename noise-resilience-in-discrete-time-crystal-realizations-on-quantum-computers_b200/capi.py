@@ -41,6 +41,12 @@ _SIGS = {
     "dtc_set_stream_engine": (ctypes.c_int, [ctypes.c_int]),
     "dtc_set_high_stride_bit": (ctypes.c_int, [ctypes.c_int]),
     "dtc_set_stream_ctas": (ctypes.c_int, [ctypes.c_int]),
+    "dtc_set_resident_bytes": (ctypes.c_int, [ctypes.c_size_t]),
+    "dtc_program_resident_info": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                                 ctypes.POINTER(ctypes.c_size_t)]),
+    "dtc_program_run_resident": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_i64, c_i64, c_u64, c_u64, c_u64, c_vp,
+                                                ctypes.c_size_t, c_vp]),
+    "dtc_program_last_run_info": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_num_stream_passes": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_last_run_flags": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
@@ -96,6 +102,14 @@ def set_high_stride_bit(bit=15):
 def set_stream_ctas(n=0):
     """Persistent CTAs per k_tile_stream launch (0: one per SM)."""
     check(load().dtc_set_stream_ctas(int(n)))
+
+
+def set_resident_bytes(nbytes=64 << 20):
+    """State bytes a resident run keeps in flight (trajectories per group x state size; L2 is 126 MB)."""
+    check(load().dtc_set_resident_bytes(int(nbytes)))
+
+
+RESIDENT = True          # module switch: evolve() uses resident execution for read-out-only runs when the program is eligible
 
 
 def set_stream_engine(enable):
@@ -177,6 +191,24 @@ class ProgramHandle:
         check(load().dtc_program_run(self._h, state_ptr, int(n_traj), int(traj_offset),
                                      int(seed) & 0xFFFFFFFFFFFFFFFF, int(init_index), int(rank_bits),
                                      ws_ptr, ws_bytes, stream))
+
+    def resident_info(self, n_traj):
+        """(eligible, trajectories per group, scratch bytes) for dtc_program_run_resident."""
+        e, g, b = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_size_t(0)
+        check(load().dtc_program_resident_info(self._h, int(n_traj), ctypes.byref(e), ctypes.byref(g), ctypes.byref(b)))
+        return bool(e.value), g.value, b.value
+
+    def run_resident(self, scratch_ptr, scratch_bytes, n_traj, traj_offset, seed, ws_ptr, ws_bytes, stream, init_index=0,
+                     rank_bits=0):
+        check(load().dtc_program_run_resident(self._h, scratch_ptr, int(scratch_bytes), int(n_traj), int(traj_offset),
+                                              int(seed) & 0xFFFFFFFFFFFFFFFF, int(init_index), int(rank_bits),
+                                              ws_ptr, ws_bytes, stream))
+
+    def last_run_info(self):
+        """(resident execution used, kernels launched) of the last run."""
+        r, k = ctypes.c_int(0), ctypes.c_int(0)
+        check(load().dtc_program_last_run_info(self._h, ctypes.byref(r), ctypes.byref(k)))
+        return bool(r.value), k.value
 
     def set_fused_rdm(self, enable=True):
         """Let the last pass reduce the read-out qubit's density matrix instead of storing the state (factorised

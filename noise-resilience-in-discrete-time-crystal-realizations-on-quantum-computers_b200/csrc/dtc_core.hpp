@@ -431,7 +431,19 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err, int fi
         const u64 next = (j + 1 < M) ? P.layers[j + 1].rot_any : 0ull;
         // a layer with nothing left to do (no rotation outstanding, identity diagonal) needs no sweep of its own:
         // its successor's rotations ride with that layer's diagonal instead (segments of a sharded run start so)
-        if (!rem && j + 1 < M && L.n_terms == 0 && !L.d1_any[0] && !L.d1_any[1] && L.cr == 1.0 && L.ci == 0.0) {
+        // The last layer of a segment whose rotations all ran as the look-ahead of the previous pass and whose "diagonal" is
+        // only the real normalisation constant of those tan-form rotations: the constant moves into the previous layer's
+        // constant (everything is linear) instead of costing a sweep of its own.  Idempotent (the constant becomes 1).
+        if (!rem && j == M - 1 && j >= 1 && L.n_terms == 0 && !L.d1_any[0] && !L.d1_any[1] && L.ci == 0.0 && L.cr != 1.0 &&
+            !P.passes.empty() && P.passes.back().layerD == j - 1 && P.passes.back().layerB == j) {
+            P.layers[j - 1].cr *= L.cr;
+            P.layers[j - 1].ci *= L.cr;
+            P.layers[j].cr = 1.0;
+        }
+        const bool trivial_d = L.n_terms == 0 && !L.d1_any[0] && !L.d1_any[1] && L.cr == 1.0 && L.ci == 0.0;
+        if (!rem && trivial_d && (j + 1 < M || !P.passes.empty())) {
+            // (the last layer too: its rotations were applied as the look-ahead of the previous pass and its diagonal is
+            //  the identity -- segments of a sharded run end so)
             ++j;
             done = 0;
             continue;
@@ -471,7 +483,7 @@ static inline bool dtc_schedule_tile(DtcProgramHost& P, std::string& err, int fi
         T.n_local = n;
         T.n_total = P.n_qubits;
         T.layerA = SA ? j : -1;
-        T.layerD = complete ? j : -1;
+        T.layerD = (complete && !trivial_d) ? j : -1;      // an identity diagonal layer costs no tables and no multiplies
         T.layerB = (complete && SB) ? j + 1 : -1;
         for (int l = 0; l < DTC_TILE_BITS; ++l) {
             const int q = T.tb[l];
@@ -558,6 +570,18 @@ static inline size_t dtc_workspace_bytes(const DtcProgramHost& P, int64_t n_traj
     b += (size_t)n_traj * sizeof(int);
     b = (b + 255) & ~(size_t)255;
     b += (size_t)n_traj * 4 * sizeof(double2);       // fused read-out: reduced density matrix of one qubit per trajectory
+    b = (b + 255) & ~(size_t)255;
+    // resident execution: one completion counter per (trajectory slot, pass), groups of at most 64 slots
+    b += ((size_t)n_traj + 64) * (P.passes.empty() ? 1 : P.passes.size()) * sizeof(int);
+    return (b + 255) & ~(size_t)255;
+}
+
+// offset of the completion counters of k_tile_resident inside the workspace
+static inline size_t dtc_workspace_cnt_offset(const DtcProgramHost& P, int64_t n_traj) {
+    size_t b = (size_t)(P.n_layers * 4 + 2) * (size_t)n_traj * sizeof(u64);
+    b += (size_t)n_traj * sizeof(int);
+    b = (b + 255) & ~(size_t)255;
+    b += (size_t)n_traj * 4 * sizeof(double2);
     return (b + 255) & ~(size_t)255;
 }
 

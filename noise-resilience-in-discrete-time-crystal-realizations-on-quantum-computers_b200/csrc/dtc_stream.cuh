@@ -36,6 +36,7 @@ struct DtcStreamPass {
     int n_local, g;                // B: tile bits 2..11 = global bits g..g+9
     int layerA, layerD, layerB;
     int two;                       // = 2: opaque trip count that keeps shared code blocks rolled (instruction footprint)
+    int tmap_slot;                 // k_tile_resident: which of its two tensor maps this pass uses (non-contiguous tiles)
     int tb[DTC_TILE_BITS];
     double t1[DTC_TILE_BITS], t2[DTC_TILE_BITS];
     u64 tile_mask;

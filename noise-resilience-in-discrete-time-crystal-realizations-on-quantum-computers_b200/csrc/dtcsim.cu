@@ -117,6 +117,11 @@ struct dtc_program {
     int fused_local_bit = -1;            // tile-local position of the read-out qubit in the last pass (-1: not fusable)
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DtcStreamPass* d_spasses = nullptr;  // pass descriptors on the device (k_tile_resident looks them up per work item)
+    bool resident_ok = false;            // every pass runs on the streaming engine and at most two tensor maps are needed
+    int tmap_mode[2] = {0, 0}, tmap_g[2] = {0, 0}, n_tmaps = 0;
+    bool last_resident = false;
+    int last_kernel_launches = 0;
     cudaEvent_t uploaded = nullptr;      // tables are on the device (recorded on the upload stream)
     cudaEvent_t last_use = nullptr;      // end of the last dtc_program_run / dtc_program_readout on the caller's stream
     bool used = false;
@@ -490,6 +495,250 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
     }
     PROF_FLUSH(8, t == 0 && wg == 0);
     PROF_FLUSH(12, t == 0 && wg == 1);
+}
+
+
+// ------------------------------------------------------------------------------------ k_tile_resident
+// The whole pass schedule of a circuit in ONE persistent launch, ordered so that the states stay in L2 (126 MB): the
+// trajectories are taken in groups of G (G x 2^n_local x 16 B ~ 64 MiB), a group runs through ALL passes before the next
+// group starts, and every group reuses the same G state slots -- the sweeps read and write L2, not HBM.  Work items
+// (group, pass, slot, tile) are numbered in that order and dealt to the CTAs round robin; an item may be loaded once every
+// tile of the same slot in the previous pass (for pass 0: in the last pass of the previous group) has been stored, which
+// per-(pass, slot) completion counters in global memory track.  The dependency of an item lies G x tiles-per-state items
+// earlier in the order, further than the CTAs' pipelines reach, so the counters are polled but rarely waited on.
+// Roles, stage ring, tables and phases are those of k_tile_stream; the pass descriptor is looked up per item.
+struct ResidentPlan {
+    int n_local, n_passes, G, last_G;      // G: state slots = trajectories per group (last_G: of the last group)
+    int nt_bits;                            // tiles per state = 1 << nt_bits
+    int gen_first, fused_last, rdm_local_bit;
+    long long n_traj, n_groups, items_per_group, total_items;
+    u64 init_index, rank_bits;
+};
+struct ResidentItem {
+    int p, j;                               // pass, state slot
+    u64 T, traj;                            // tile within the state, trajectory within the batch
+    long long seq;                          // group * n_passes + pass
+};
+__device__ __forceinline__ ResidentItem resident_decode(long long w, const ResidentPlan& R) {
+    ResidentItem it;
+    const long long gi = w / R.items_per_group;
+    const int Gi = (gi == R.n_groups - 1) ? R.last_G : R.G;
+    const long long r = w - gi * R.items_per_group;
+    const long long per_pass = (long long)Gi << R.nt_bits;
+    it.p = (int)(r / per_pass);
+    const long long rr = r - (long long)it.p * per_pass;
+    it.j = (int)(rr >> R.nt_bits);
+    it.T = (u64)(rr & ((1ll << R.nt_bits) - 1));
+    it.traj = (u64)(gi * R.G + it.j);
+    it.seq = gi * R.n_passes + it.p;
+    return it;
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(DTC_STREAM_THREADS, 1)
+k_tile_resident(double2* __restrict__ state, const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+                const __grid_constant__ ResidentPlan R, const DtcStreamPass* __restrict__ passes,
+                const DtcLayer* __restrict__ layers, const u64* __restrict__ masks, int* __restrict__ cnt,
+                double2* __restrict__ rdm_out) {
+    extern __shared__ unsigned char smraw[];
+    StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smraw + ((128u - (smem_u32(smraw) & 127u)) & 127u));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long K = (R.total_items - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x;
+    const int nt = 1 << R.nt_bits;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < DTC_STREAM_STAGES; ++s) {
+            mbar_init(smem_u32(&sm.full[s]), 2);
+            mbar_init(smem_u32(&sm.done[s]), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 4 * DTC_STREAM_WG) {
+        // ---- TMA driver: an event loop that never blocks on another CTA while it has a store to issue
+        if ((tid & 31) != 0) return;
+        long long load_k = 0, store_k = 0;
+        int pend[4], n_pend = 0;                          // counters of items stored but not yet signalled
+        while (store_k < K) {
+            bool progressed = false;
+            if (load_k < K && load_k < store_k + DTC_STREAM_STAGES) {
+                const ResidentItem it = resident_decode((long long)blockIdx.x + load_k * gridDim.x, R);
+                bool ok = true;
+                if (it.seq > 0) ok = ld_acquire_gpu(cnt + (it.seq - 1) * R.G + it.j) >= nt;
+                if (ok) {
+                    const int s = (int)(load_k % DTC_STREAM_STAGES);
+                    if (it.p == 0 && R.gen_first) {
+                        mbar_arrive(smem_u32(&sm.full[s]));
+                    } else {
+                        asm volatile("fence.proxy.async;" ::: "memory");       // acquired generic-proxy view -> TMA read
+                        const DtcStreamPass& P = passes[it.p];
+                        stream_tma_load(P, P.tmap_slot ? &tmap1 : &tmap0, state, ((u64)it.j << R.nt_bits) | it.T,
+                                        smem_u32(sm.stage[s]), smem_u32(&sm.full[s]));
+                    }
+                    ++load_k;
+                    progressed = true;
+                }
+            }
+            if (store_k < load_k) {
+                const int s = (int)(store_k % DTC_STREAM_STAGES);
+                if (mbar_test(smem_u32(&sm.done[s]), (uint32_t)((store_k / DTC_STREAM_STAGES) & 1))) {
+                    const ResidentItem it = resident_decode((long long)blockIdx.x + store_k * gridDim.x, R);
+                    const int ci = (int)(it.seq * R.G + it.j);
+                    if (R.fused_last && it.p == R.n_passes - 1) {
+                        atomicAdd(cnt + ci, 1);               // read-only item: complete as soon as the stage has been consumed
+                    } else {
+                        const DtcStreamPass& P = passes[it.p];
+                        stream_tma_store(P, P.tmap_slot ? &tmap1 : &tmap0, state, ((u64)it.j << R.nt_bits) | it.T, smem_u32(sm.stage[s]));
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the stage may be reloaded
+                        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");           // all earlier stores have landed
+                        if (n_pend) {
+                            asm volatile("fence.proxy.async;" ::: "memory");
+                            __threadfence();
+                            for (int i = 0; i < n_pend; ++i) atomicAdd(cnt + pend[i], 1);
+                            n_pend = 0;
+                        }
+                        pend[n_pend++] = ci;
+                    }
+                    ++store_k;
+                    progressed = true;
+                }
+            }
+            if (!progressed) {
+                if (n_pend) {                              // idle: publish what has been stored (bounded wait on the TMA engine only)
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    for (int i = 0; i < n_pend; ++i) atomicAdd(cnt + pend[i], 1);
+                    n_pend = 0;
+                } else {
+                    __nanosleep(64);
+                }
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (n_pend) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __threadfence();
+            for (int i = 0; i < n_pend; ++i) atomicAdd(cnt + pend[i], 1);
+        }
+        return;
+    }
+    if (warp > 4 * DTC_STREAM_WG) {
+        // ---- table builder of stage s
+        const int lane = tid & 31, s = warp - (4 * DTC_STREAM_WG + 1);
+        StreamBuild& bl = sm.build[s];
+        StreamSlot& slot = sm.slot[s];
+        uint32_t par = 1;
+        for (long long k = s; k < K; k += DTC_STREAM_STAGES) {
+            const ResidentItem it = resident_decode((long long)blockIdx.x + k * gridDim.x, R);
+            const DtcStreamPass& P = passes[it.p];
+            const StreamMasks M = stream_load_masks(P, masks, R.n_traj, it.traj);
+            const u64 base = stream_tile_base(it.T, P);
+            if (P.layerD >= 0) {
+                const DtcLayer& L = layers[P.layerD];
+                stream_build1(lane, bl, P, L, base | (R.rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
+                __syncwarp();
+                stream_build2(lane, bl, P, L);
+                __syncwarp();
+            }
+            if (k >= DTC_STREAM_STAGES) mbar_wait(smem_u32(&sm.done[s]), par);      // slot s is free again
+            stream_build3(lane, bl, slot, P);
+            if (lane == 0) { slot.rmA = M.rmA; slot.rmB = M.rmB; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.full[s]));
+            par ^= 1u;
+        }
+        return;
+    }
+    // ---- compute warpgroups
+    const int wg = warp >> 2, t = tid & 127;
+    for (long long k = wg; k < K; k += DTC_STREAM_WG) {
+        const int s = (int)(k % DTC_STREAM_STAGES);
+        const uint32_t u = (uint32_t)(k / DTC_STREAM_STAGES);
+        const ResidentItem it = resident_decode((long long)blockIdx.x + k * gridDim.x, R);
+        const DtcStreamPass& P = passes[it.p];
+        const int mode = P.mode;
+        if (u > 0) mbar_wait(smem_u32(&sm.done[s]), (u - 1) & 1u);
+        mbar_wait(smem_u32(&sm.full[s]), u & 1u);
+        if (mode != 1) wg_barrier(wg);
+        double2* tile = sm.stage[s];
+        const StreamSlot& slot = sm.slot[s];
+        const u64 rmA = slot.rmA, rmB = slot.rmB;
+        if (it.p == 0 && R.gen_first) {
+            const u64 base = stream_tile_base(it.T, P);
+#pragma unroll
+            for (int r = 0; r < DTC_NREG; ++r) tile[t + 128 * r] = make_double2(0.0, 0.0);
+            const bool has = R.init_index != DTC_INIT_ZERO && ((R.init_index ^ base) & ~P.tile_mask) == 0;
+            if (!has) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(smem_u32(&sm.done[s]));
+                continue;
+            }
+            wg_barrier(wg);
+            if (t == 0) {
+                int l = 0;
+                for (int b = 0; b < DTC_TILE_BITS; ++b) l |= (int)((R.init_index >> P.tb[b]) & 1ull) << b;
+                tile[l] = make_double2(1.0, 0.0);
+            }
+            wg_barrier(wg);
+        }
+        if (mode == 3) {
+            stream_phaseC(t, tile, slot, P, rmA, rmB);
+        } else {
+            double tt[5];
+            if (P.layerA >= 0) {
+                if (mode == 1) {
+                    stream_signed_s1<1>(P.t1, P.tb, rmA, tt);
+                    stream_phase13_call<1>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+                } else {
+                    stream_signed_s1<2>(P.t1, P.tb, rmA, tt);
+                    stream_phase13_call<2>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+                }
+            }
+            if (mode == 1) __syncwarp(); else wg_barrier(wg);
+            if (P.layerA >= 0 && P.layerD >= 0 && P.layerB >= 0) stream_phase2(t, tile, slot, P, rmA, rmB);
+            else stream_phase2_partial_call(t, tile, &slot, &P, rmA, rmB);
+            if (mode == 1) __syncwarp(); else wg_barrier(wg);
+            if (P.layerB >= 0) {
+                if (mode == 1) {
+                    stream_signed_s1<1>(P.t2, P.tb, rmB, tt);
+                    stream_phase13_call<1>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+                } else {
+                    stream_signed_s1<2>(P.t2, P.tb, rmB, tt);
+                    stream_phase13_call<2>(t, tile, tt[0], tt[1], tt[2], tt[3], tt[4]);
+                }
+            }
+        }
+        if (R.fused_last && it.p == R.n_passes - 1) {
+            wg_barrier(wg);
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            stream_rdm_pairs(t, tile, R.rdm_local_bit, acc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+            if ((t & 31) == 0) {
+                double* dst = reinterpret_cast<double*>(rdm_out + (it.traj << 2));
+                atomicAdd(dst + 0, acc[0]);
+                atomicAdd(dst + 2, acc[2]);
+                atomicAdd(dst + 3, acc[3]);
+                atomicAdd(dst + 4, acc[2]);
+                atomicAdd(dst + 5, -acc[3]);
+                atomicAdd(dst + 6, acc[1]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(smem_u32(&sm.done[s]));
+    }
 }
 
 // ---- generic engine
@@ -1057,6 +1306,7 @@ int dtc_program_destroy(dtc_program* p) {
         table_free(p->d_events, p->h.device);
         table_free(p->d_layers, p->h.device);
         table_free(p->d_small_idx, p->h.device);
+        table_free(p->d_spasses, p->h.device);
         if (p->ev0) cudaEventDestroy(p->ev0);
         if (p->ev1) cudaEventDestroy(p->ev1);
         if (p->uploaded) cudaEventDestroy(p->uploaded);
@@ -1118,6 +1368,27 @@ int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
     const size_t eb = p->h.events.size() * sizeof(DtcEvent), lb = p->h.layers.size() * sizeof(DtcLayer);
     CUDA_TRY(table_upload((void**)&p->d_events, p->h.events.data(), eb, 16, device));
     CUDA_TRY(table_upload((void**)&p->d_layers, p->h.layers.data(), lb, 16, device));
+    if (engine == DTC_ENGINE_TILE && !p->h.spasses.empty() && n_local <= 22) {
+        bool ok = true;
+        for (DtcStreamPass& S : p->h.spasses) {
+            if (!S.mode) { ok = false; break; }
+            S.tmap_slot = 0;
+            if (S.contig) continue;
+            int slot = -1;
+            for (int i = 0; i < p->n_tmaps; ++i)
+                if (p->tmap_mode[i] == S.mode && p->tmap_g[i] == S.g) slot = i;
+            if (slot < 0) {
+                if (p->n_tmaps == 2) { ok = false; break; }
+                slot = p->n_tmaps++;
+                p->tmap_mode[slot] = S.mode;
+                p->tmap_g[slot] = S.g;
+            }
+            S.tmap_slot = slot;
+        }
+        p->resident_ok = ok;
+        if (ok)
+            CUDA_TRY(table_upload((void**)&p->d_spasses, p->h.spasses.data(), p->h.spasses.size() * sizeof(DtcStreamPass), 16, device));
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&p->uploaded, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->last_use, cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(p->uploaded, g_dev[device].upload));
@@ -1134,6 +1405,7 @@ int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
         CUDA_TRY(cudaFuncSetAttribute(k_tile_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
         CUDA_TRY(cudaFuncSetAttribute(k_tile_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
         CUDA_TRY(cudaFuncSetAttribute(k_tile_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
         CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms[device], cudaDevAttrMultiProcessorCount, device));
         attr_set[device] = true;
     }
@@ -1200,6 +1472,8 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     }
     p->last_gen_first = gen_first;
     p->last_fused = fused && h.engine == DTC_ENGINE_TILE;
+    p->last_resident = false;
+    p->last_kernel_launches = 1 + ((h.engine == DTC_ENGINE_TILE) ? (int)h.passes.size() : (int)h.gsteps.size());
     if (p->profiling) CUDA_TRY(cudaEventRecord(p->ev0, s));
     p->last_launches = (h.engine == DTC_ENGINE_TILE) ? (int)h.passes.size() : (int)h.gsteps.size();
     if (h.engine == DTC_ENGINE_TILE) {
@@ -1272,6 +1546,118 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(p->last_use, s));
     p->used = true;
+    return DTC_OK;
+}
+
+
+// ---- resident execution (k_tile_resident): read-out-only runs of programs whose passes all stream
+static size_t g_resident_bytes = 64ull << 20;      // dtc_set_resident_bytes(): state bytes kept in flight (L2 is 126 MB)
+
+static int resident_group(const dtc_program* p, int64_t n_traj) {
+    const size_t sb = sizeof(double2) << p->h.n_local;
+    long long G = (long long)(g_resident_bytes / sb);
+    if (G < 1) G = 1;
+    if (G > 64) G = 64;
+    if (G > n_traj) G = n_traj;
+    return (int)G;
+}
+
+int dtc_set_resident_bytes(size_t bytes) {
+    if (bytes < (1u << 20)) return fail(DTC_ERR_INVALID, "resident bytes must be at least 1 MiB");
+    g_resident_bytes = bytes;
+    return DTC_OK;
+}
+
+int dtc_program_resident_info(const dtc_program* p, int64_t n_traj, int* eligible, int* group, size_t* scratch_bytes) {
+    if (!p || !p->h.finalized || n_traj < 1 || !eligible || !group || !scratch_bytes) return fail(DTC_ERR_INVALID, "bad argument");
+    const int G = resident_group(p, n_traj);
+    const long long n_groups = (n_traj + G - 1) / G;
+    const bool small = n_groups * (long long)p->h.passes.size() * G < (1ll << 30);
+    *eligible = (p->resident_ok && p->fuse_rdm && p->fused_local_bit >= 0 && stream_enabled() && small) ? 1 : 0;
+    *group = G;
+    *scratch_bytes = ((size_t)G << p->h.n_local) * sizeof(double2);
+    return DTC_OK;
+}
+
+int dtc_program_run_resident(dtc_program* p, void* scratch, size_t scratch_bytes, int64_t n_traj, int64_t traj_offset,
+                             uint64_t seed, uint64_t init_index, uint64_t rank_bits, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+    if (!p || !p->h.finalized) return fail(DTC_ERR_INVALID, "program not finalized");
+    if (!scratch || !workspace || n_traj < 1) return fail(DTC_ERR_INVALID, "bad argument");
+    int eligible = 0, G = 0;
+    size_t need = 0;
+    if (dtc_program_resident_info(p, n_traj, &eligible, &G, &need) != DTC_OK) return DTC_ERR_INVALID;
+    if (!eligible) return fail(DTC_ERR_UNSUPPORTED, "program is not eligible for resident execution (needs the fused read-out and streaming passes only)");
+    if (scratch_bytes < need) return fail(DTC_ERR_INVALID, "scratch buffer too small");
+    const DtcProgramHost& h = p->h;
+    if (workspace_bytes < dtc_workspace_bytes(h, n_traj)) return fail(DTC_ERR_INVALID, "workspace too small");
+    if (init_index == DTC_INIT_KEEP) return fail(DTC_ERR_UNSUPPORTED, "resident execution starts from a basis state");
+    if (init_index != DTC_INIT_ZERO && (init_index >> h.n_local)) return fail(DTC_ERR_INVALID, "init_index out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    DeviceGuard guard(h.device);
+    CUDA_TRY(guard.err);
+    CUDA_TRY(cudaStreamWaitEvent(s, p->uploaded, 0));
+    u64 *masks, *fx, *fz;
+    int* ph;
+    ws_pointers(h, workspace, n_traj, &masks, &fx, &fz, &ph);
+    CUDA_TRY(cudaMemsetAsync(masks, 0, (size_t)h.n_layers * 4 * n_traj * sizeof(u64), s));
+    const int fb = 128;
+    k_frames<<<(unsigned)((n_traj + fb - 1) / fb), fb, 0, s>>>(p->d_events, (long long)h.events.size(), masks,
+                                                              n_traj, traj_offset, seed, fx, fz, ph);
+    ResidentPlan R;
+    memset(&R, 0, sizeof(R));
+    R.n_local = h.n_local;
+    R.n_passes = (int)h.passes.size();
+    R.G = G;
+    R.n_traj = n_traj;
+    R.n_groups = (n_traj + G - 1) / G;
+    R.last_G = (int)(n_traj - (R.n_groups - 1) * G);
+    R.nt_bits = h.n_local - DTC_TILE_BITS;
+    R.gen_first = 1;
+    R.fused_last = 1;
+    R.rdm_local_bit = p->fused_local_bit;
+    R.items_per_group = (long long)R.n_passes * G << R.nt_bits;
+    R.total_items = (R.n_groups - 1) * R.items_per_group + ((long long)R.n_passes * R.last_G << R.nt_bits);
+    R.init_index = init_index;
+    R.rank_bits = rank_bits;
+    double2* rdm_out = (double2*)((char*)workspace + dtc_workspace_rdm_offset(h, n_traj));
+    int* cnt = (int*)((char*)workspace + dtc_workspace_cnt_offset(h, n_traj));
+    CUDA_TRY(cudaMemsetAsync(rdm_out, 0, sizeof(double2) * 4 * (size_t)n_traj, s));
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(R.n_groups * R.n_passes * G), s));
+    alignas(64) CUtensorMap tm[2];
+    memset(tm, 0, sizeof(tm));
+    for (int i = 0; i < p->n_tmaps; ++i) {
+        const int rc = stream_tensor_map(&tm[i], scratch, h.n_local, p->tmap_g[i], G, p->tmap_mode[i]);
+        if (rc != DTC_OK) return rc;
+    }
+    const int n_sms = (h.device >= 0 && h.device < 16 && g_num_sms[h.device] > 0) ? g_num_sms[h.device] : 148;
+    const int max_ctas = (g_stream_ctas > 0 && g_stream_ctas < n_sms) ? g_stream_ctas : n_sms;
+    const unsigned grid = (unsigned)(R.total_items < max_ctas ? R.total_items : max_ctas);
+    if (p->profiling) CUDA_TRY(cudaEventRecord(p->ev0, s));
+    double2* st = (double2*)scratch;
+    const DtcStreamPass* dsp = p->d_spasses;
+    const DtcLayer* dl = p->d_layers;
+    const u64* dm = masks;
+    void* args[] = {&st, &tm[0], &tm[1], &R, &dsp, &dl, &dm, &cnt, &rdm_out};
+    // cooperative launch: all CTAs are co-resident by construction (they wait on one another's progress)
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_tile_resident, dim3(grid), dim3(DTC_STREAM_THREADS), args,
+                                         sizeof(StreamSmem) + 128, s));
+    if (p->profiling) CUDA_TRY(cudaEventRecord(p->ev1, s));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(p->last_use, s));
+    p->used = true;
+    p->last_gen_first = true;
+    p->last_fused = true;
+    p->last_resident = true;
+    p->last_launches = R.n_passes;
+    p->last_kernel_launches = 2;
+    return DTC_OK;
+}
+
+int dtc_program_last_run_info(const dtc_program* p, int* resident, int* kernel_launches) {
+    if (!p || !resident || !kernel_launches) return fail(DTC_ERR_INVALID, "bad argument");
+    *resident = p->last_resident ? 1 : 0;
+    *kernel_launches = p->last_kernel_launches;
     return DTC_OK;
 }
 

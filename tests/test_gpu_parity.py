@@ -701,3 +701,47 @@ def test_sharded_engine_vs_oracle(world, L, high_bit):
         assert np.abs(np.array(r["expect_z"]) - want).max() < AMP_TOL
         if world > 1:
             assert stats["exchanges"] == n_sliced > 0 and stats["exchanges"] <= stats["layers"]
+
+
+# ---- resident execution (k_tile_resident): all sweeps of a circuit in one persistent launch over L2-resident groups
+@pytest.mark.parametrize("L,t,echo,ntraj,resident_mb,high_bit", [
+    (12, 3, True, 37, 64, 15),        # one tile per state, everything in one group
+    (14, 2, False, 11, 1, 15),        # 4 tiles per state, groups of 4 slots, ragged last group
+    (16, 3, True, 9, 1, 15),          # groups of ONE slot: every item waits for the previous pass of its own slot
+    (16, 2, True, 7, 2, 9),           # high-stride groups: 2 KB-run tiles (second tensor map) in the same launch
+    (20, 2, True, 6, 64, 15),         # the C2 register: groups of 4 states of 16 MiB
+    (20, 3, False, 3, 16, 15),        # ... and of one state
+])
+def test_resident_execution_equals_streamed(ctx, disorder, L, t, echo, ntraj, resident_mb, high_bit):
+    """Fused read-out density matrices and frames of a resident run == those of the sweep-per-launch run (same kernels'
+    phases, different control structure: work order, completion counters, state slots reused by consecutive groups)."""
+    from dtcsim import backend, capi
+    hs, phis = disorder[20][0][1][:L], disorder[20][1][1][:L - 1]
+    circ = RC.transpiled(RC.qc_body("vacuum", L, 0.97, hs, phis, t, L // 2, echo))
+    capi.set_high_stride_bit(high_bit)
+    try:
+        prog = compile_circuit(circ, RC.noise_model(0.1), optimize=True)
+        assert prog.small is not None and prog.n_main == L
+        capi.RESIDENT = False
+        ref = backend.evolve(ctx, prog, ntraj, 5, 99, fused_rdm=True)
+        assert not ref.resident
+        rdm_ref = ref.readout_rdm().clone()
+        probs_ref = ref.outcome_probs().clone()
+        capi.RESIDENT = True
+        capi.set_resident_bytes(resident_mb << 20)
+        h = capi.ProgramHandle(prog, 0)
+        got = backend.evolve(ctx, prog, ntraj, 5, 99, handle=h, fused_rdm=True)
+        if ref.fused_rdm is None:
+            pytest.skip("last pass of this schedule is not fusable: resident execution does not apply")
+        assert got.resident and h.last_run_info() == (True, 2)
+        assert float((got.readout_rdm() - rdm_ref).abs().max()) < 1e-12
+        assert float((got.outcome_probs() - probs_ref).abs().max()) < 1e-12
+        assert all(np.array_equal(a, b) for a, b in zip(got.frames_host(), ref.frames_host()))
+        # a second run on the same handle and scratch (counters and slots are reset per run)
+        got2 = backend.evolve(ctx, prog, ntraj, 5, 99, handle=h, state=got.state, fused_rdm=True)
+        assert float((got2.readout_rdm() - rdm_ref).abs().max()) < 1e-12
+        h.close()
+    finally:
+        capi.RESIDENT = True
+        capi.set_resident_bytes(64 << 20)
+        capi.set_high_stride_bit(15)
