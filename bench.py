@@ -466,8 +466,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = backend.DeviceContext(local)
-    if args.no_resident:
-        capi.RESIDENT = False
+    capi.RESIDENT = bool(args.resident)
     if args.resident_mb:
         capi.set_resident_bytes(args.resident_mb << 20)
     hs, phis = load_disorder(rank)                      # weak scaling: one disorder instance per rank (C4)
@@ -663,7 +662,7 @@ def main():
     ap.add_argument("--config", default="C2", choices=["C2", "C3"], help="C2 (default, the headline) or C3 (exact density matrix)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-resident", action="store_true", help="one launch per sweep, batch streamed through HBM (round-1 execution)")
+    ap.add_argument("--resident", action="store_true", help="resident execution: all sweeps of a circuit in one persistent launch over L2-resident trajectory groups")
     ap.add_argument("--resident-mb", type=int, default=0, help="state MiB kept in flight per group in resident execution (default 64)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-record")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded-statevector (C5) sub-record")

@@ -109,7 +109,12 @@ def set_resident_bytes(nbytes=64 << 20):
     check(load().dtc_set_resident_bytes(int(nbytes)))
 
 
-RESIDENT = True          # module switch: evolve() uses resident execution for read-out-only runs when the program is eligible
+# Module switch: evolve() uses resident execution (k_tile_resident: every sweep of a circuit in one persistent launch over
+# groups of trajectories whose states stay in L2) for read-out-only runs of eligible programs.  Off by default: on B200 it is
+# 15-20 % slower than one launch per sweep on config C2 (profiles/experiments_r2.md) -- it draws 800 W instead of 990 W and
+# keeps the maximum SM clock, but a group small enough for L2 (4 states of 16 MiB) leaves too little distance between a tile
+# and the tiles it depends on.  Environment DTCSIM_RESIDENT=1 turns it on.
+RESIDENT = os.environ.get("DTCSIM_RESIDENT", "0") == "1"
 
 
 def set_stream_engine(enable):

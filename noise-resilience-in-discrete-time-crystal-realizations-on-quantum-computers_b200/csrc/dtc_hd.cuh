@@ -48,12 +48,14 @@ struct DtcLayer {
     double s1[2][DTC_MAXQ];        // sin(a/2)                         (0 if absent)
     double tc[DTC_MAXT], ts[DTC_MAXT];   // cos(b/2), sin(b/2) of D2 term k
     int ti[DTC_MAXT], tj[DTC_MAXT];      // its qubits
-    double rtan[DTC_MAXQ];         // tan(theta'/2) of the rotation on q in R_j (0 if none)
     u64 d1_any[2];                 // qubits with a non-trivial slot-s coefficient
-    u64 rot_any;                   // qubits rotated in R_j
     int n_terms;
     int pad_;
+    // ---- everything above is what the device-side table builders read (DTC_LAYER_PREFIX bytes); below: host / frames only
+    u64 rot_any;                   // qubits rotated in R_j
+    double rtan[DTC_MAXQ];         // tan(theta'/2) of the rotation on q in R_j (0 if none)
 };
+#define DTC_LAYER_PREFIX (16 + 4 * 8 * DTC_MAXQ + 2 * 8 * DTC_MAXT + 2 * 4 * DTC_MAXT + 16 + 8)
 
 struct DtcEvent {
     int type, layer, q0, q1, slot, k;    // k: ROT quarter turns (theta = theta' + k pi)
@@ -344,7 +346,8 @@ DTC_HD void tile_tables_thread(int tid, TileSmem& sm, const DtcTilePass& P) {
 }
 
 // resolve the trajectory's signs for the five register bits starting at local bit lo
-DTC_HD void tile_signed_t(const double* tbase, const int* tb, int lo, u64 rmask, double out[5]) {
+template <class TB>
+DTC_HD void tile_signed_t(const double* tbase, const TB* tb, int lo, u64 rmask, double out[5]) {
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         const double t = tbase[lo + k];

@@ -49,6 +49,17 @@ struct DtcStreamPass {
     unsigned char Fk[DTC_MAXT], Fa[DTC_MAXT], Fb[DTC_MAXT];
     unsigned char Ck[DTC_MAXT], Ca[DTC_MAXT], Cb[DTC_MAXT];      // local a, outer qubit b
     unsigned char Ok[DTC_MAXT], Oa[DTC_MAXT], Ob[DTC_MAXT];      // outer, outer
+} __attribute__((aligned(16)));
+
+// What the TMA driver and the compute warps of k_tile_resident need of a pass: small enough for an array of these to travel
+// in the kernel's parameter space (read through the constant cache, like the single grid-constant pass of k_tile_stream).
+#define DTC_RESIDENT_MAX_PASSES 128
+struct DtcResidentPass {
+    unsigned char mode, contig, g, tmap_slot;
+    short layerA, layerD, layerB, n_local;
+    unsigned char tb[DTC_TILE_BITS];
+    double t1[DTC_TILE_BITS], t2[DTC_TILE_BITS];
+    u64 tile_mask;
 };
 
 // per-stage phase tables of the tile in that stage, written by the stage's table-builder warp.
@@ -70,7 +81,8 @@ struct StreamBuild {
 };
 
 // ---- tile geometry
-DTC_HD u64 stream_tile_base(u64 tile_in_traj, const DtcStreamPass& P) {
+template <class PassT>
+DTC_HD u64 stream_tile_base(u64 tile_in_traj, const PassT& P) {
     if (P.contig) return tile_in_traj << DTC_TILE_BITS;
     if (P.mode == 3) {
         const int lb = P.g - 7;
@@ -105,8 +117,8 @@ DTC_HD int stream_s1_bit(int j) {
     return j == 0 ? 2 : j + 7;
 }
 
-template <int MODE>
-DTC_HD void stream_signed_s1(const double* tbase, const int* tb, u64 rmask, double out[5]) {
+template <int MODE, class TB>
+DTC_HD void stream_signed_s1(const double* tbase, const TB* tb, u64 rmask, double out[5]) {
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int l = stream_s1_bit<MODE>(j);
@@ -138,7 +150,8 @@ DTC_HD void stream_phase13(int t, double2* tile, const double* tbase, const int*
     stream_phase13_signed<MODE>(t, tile, tt);
 }
 
-DTC_HD void stream_phase2(int t, double2* tile, const StreamSlot& tab, const DtcStreamPass& P, u64 rmA, u64 rmB) {
+template <class PassT>
+DTC_HD void stream_phase2(int t, double2* tile, const StreamSlot& tab, const PassT& P, u64 rmA, u64 rmB) {
     double tA[5], tB[5];
     tile_signed_t(P.t1, P.tb, 3, rmA, tA);
     tile_signed_t(P.t2, P.tb, 3, rmB, tB);
@@ -172,7 +185,8 @@ DTC_HD void stream_phase2(int t, double2* tile, const StreamSlot& tab, const Dtc
 // Phase 2 of a pass that lacks one of its three parts (first / last pass of a circuit, rotation-only sweeps of large
 // registers): the absent parts are skipped instead of being executed with zero angles / identity tables.  Kept out of
 // stream_phase2 so that the register allocation of the hot path (all three parts present) is not disturbed.
-DTC_HD void stream_phase2_partial(int t, double2* tile, const StreamSlot& tab, const DtcStreamPass& P, u64 rmA, u64 rmB) {
+template <class PassT>
+DTC_HD void stream_phase2_partial(int t, double2* tile, const StreamSlot& tab, const PassT& P, u64 rmA, u64 rmB) {
     double2 a[DTC_NREG];
     double2* p = tile + stream_chunk2(t, 0);
 #pragma unroll
@@ -203,7 +217,8 @@ DTC_HD void stream_phase2_partial(int t, double2* tile, const StreamSlot& tab, c
 }
 
 // mode C: the only phase.  Thread t <-> passive local bits 0..6, registers <-> local bits 7..11; phase = T1c[r] * T2[t].
-DTC_HD void stream_phaseC(int t, double2* tile, const StreamSlot& tab, const DtcStreamPass& P, u64 rmA, u64 rmB) {
+template <class PassT>
+DTC_HD void stream_phaseC(int t, double2* tile, const StreamSlot& tab, const PassT& P, u64 rmA, u64 rmB) {
     double tA[5], tB[5];
     tile_signed_t(P.t1, P.tb, 7, rmA, tA);
     tile_signed_t(P.t2, P.tb, 7, rmB, tB);

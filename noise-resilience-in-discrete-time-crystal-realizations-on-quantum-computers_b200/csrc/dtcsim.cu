@@ -244,7 +244,8 @@ __device__ __forceinline__ void wg_barrier(int wg) {
     else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
 
-__device__ __forceinline__ void stream_tma_load(const DtcStreamPass& P, const CUtensorMap* tmap, const double2* state,
+template <class PassT>
+__device__ __forceinline__ void stream_tma_load(const PassT& P, const CUtensorMap* tmap, const double2* state,
                                                 u64 T, uint32_t dst, uint32_t bar) {
     mbar_expect_tx(bar, DTC_TILE * 16);
     if (P.contig) {
@@ -264,7 +265,8 @@ __device__ __forceinline__ void stream_tma_load(const DtcStreamPass& P, const CU
             : "memory");
     }
 }
-__device__ __forceinline__ void stream_tma_store(const DtcStreamPass& P, const CUtensorMap* tmap, double2* state, u64 T,
+template <class PassT>
+__device__ __forceinline__ void stream_tma_store(const PassT& P, const CUtensorMap* tmap, double2* state, u64 T,
                                                  uint32_t src) {
     if (P.contig) {
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -303,7 +305,8 @@ __device__ __noinline__ void stream_phase13_call(int t, double2* tile, double t0
     stream_phase13_signed<MODE>(t, tile, tt);
 }
 
-__device__ __noinline__ void stream_phase2_partial_call(int t, double2* tile, const StreamSlot* tab, const DtcStreamPass* P,
+template <class PassT>
+__device__ __noinline__ void stream_phase2_partial_call(int t, double2* tile, const StreamSlot* tab, const PassT* P,
                                                          u64 rmA, u64 rmB) {
     stream_phase2_partial(t, tile, *tab, *P, rmA, rmB);
 }
@@ -519,158 +522,289 @@ struct ResidentItem {
     u64 T, traj;                            // tile within the state, trajectory within the batch
     long long seq;                          // group * n_passes + pass
 };
-__device__ __forceinline__ ResidentItem resident_decode(long long w, const ResidentPlan& R) {
-    ResidentItem it;
-    const long long gi = w / R.items_per_group;
-    const int Gi = (gi == R.n_groups - 1) ? R.last_G : R.G;
-    const long long r = w - gi * R.items_per_group;
-    const long long per_pass = (long long)Gi << R.nt_bits;
-    it.p = (int)(r / per_pass);
-    const long long rr = r - (long long)it.p * per_pass;
-    it.j = (int)(rr >> R.nt_bits);
-    it.T = (u64)(rr & ((1ll << R.nt_bits) - 1));
-    it.traj = (u64)(gi * R.G + it.j);
-    it.seq = gi * R.n_passes + it.p;
-    return it;
-}
+// Iterator over the work items w0, w0 + step, w0 + 2 step, ... of one role: (group, offset in group) advanced without divisions
+struct ResidentIter {
+    long long gi;                           // group
+    unsigned r;                             // offset inside the group
+    unsigned step;
+    __device__ __forceinline__ void init(long long w0, unsigned step_, const ResidentPlan& R) {
+        gi = w0 / R.items_per_group;
+        r = (unsigned)(w0 - gi * R.items_per_group);
+        step = step_;
+    }
+    __device__ __forceinline__ void next(const ResidentPlan& R) {
+        r += step;
+        const unsigned ipg = (unsigned)R.items_per_group;
+        while (r >= ipg && gi < R.n_groups - 1) { r -= ipg; ++gi; }
+    }
+    __device__ __forceinline__ ResidentItem item(const ResidentPlan& R) const {
+        ResidentItem it;
+        const int Gi = (gi == R.n_groups - 1) ? R.last_G : R.G;
+        const unsigned per_pass = (unsigned)Gi << R.nt_bits;
+        it.p = (int)(r / per_pass);
+        const unsigned rr = r - (unsigned)it.p * per_pass;
+        it.j = (int)(rr >> R.nt_bits);
+        it.T = (u64)(rr & ((1u << R.nt_bits) - 1));
+        it.traj = (u64)(gi * R.G + it.j);
+        it.seq = gi * R.n_passes + it.p;
+        return it;
+    }
+};
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
 }
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+// Completion counters live in L2 (the point of coherence of the TMA loads and stores they order): a relaxed gpu-scope load
+// observes them there, and the writer counts an item with a RED only after its bulk stores have completed.
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// Issued only after cp.async.bulk.wait_group has reported the item's bulk stores complete, i.e. landed in L2.
+__device__ __forceinline__ void red_relaxed_gpu(int* p) {
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+
+struct ResidentPasses {
+    DtcResidentPass p[DTC_RESIDENT_MAX_PASSES];
+};
+static_assert(sizeof(ResidentPasses) + sizeof(ResidentPlan) + 2 * sizeof(CUtensorMap) + 64 <= 32764, "kernel parameter space");
+static_assert(offsetof(DtcLayer, rot_any) == DTC_LAYER_PREFIX, "DTC_LAYER_PREFIX must cover what the table builders read");
+
+// what the TMA driver needs of a pass
+struct ResidentTma {
+    int contig, mode, g;
+};
+struct ResidentPost {
+    u64 tile;                               // tile coordinate in the slot buffer: (slot << nt_bits) | tile in state
+    int counter;                            // index of the item's completion counter
+    unsigned char contig, mode, g, tmap;    // of its pass
+    unsigned char gen, readonly, pad0, pad1;   // first pass generates the state (no load); fused last pass (no store)
+};
+
+struct ResidentSmem {
+    double2 stage[DTC_STREAM_STAGES][DTC_TILE];
+    StreamSlot slot[DTC_STREAM_STAGES];
+    StreamBuild build[DTC_STREAM_STAGES];
+    // private to the stage's table-builder warp: the full descriptor and the layer tables of the pass it is building for,
+    // refreshed when the pass changes (global reads would miss the few KB of L1 left beside 217 KB of shared memory)
+    DtcStreamPass bpass[DTC_STREAM_STAGES];
+    unsigned long long blayer[DTC_STREAM_STAGES][DTC_LAYER_PREFIX / 8];
+    unsigned long long full[DTC_STREAM_STAGES], done[DTC_STREAM_STAGES];
+    long long dep_ok[DTC_STREAM_STAGES];
+    ResidentPlan plan;                                 // copy of the launch plan for the out-of-line roles
+    unsigned char pinfo[DTC_RESIDENT_MAX_PASSES][4];   // per pass: contig, mode, g, tensor-map slot (TMA driver)
+    // what the TMA driver needs of an item, posted by the stage's builder (the driver lane is a single thread on the critical
+    // path of every tile: it does no index arithmetic of its own).  Three deep per stage: an entry is overwritten only
+    // after two later items of the stage have been loaded, i.e. long after its own store was issued.
+    ResidentPost post[DTC_STREAM_STAGES][3];
+    int pend[4];
+};
+static_assert(sizeof(ResidentSmem) + 128 <= 227 * 1024, "stage buffers + tables must fit one CTA's shared memory");
+
+// ---- TMA driver (one lane).  Out of line: the role gets a register allocation of its own -- inlined into the kernel its loop
+// state is spilled to local memory (the compute warps need every register), and with 217 KB of shared memory per CTA there is
+// next to no L1 to catch those spills.
+// An event loop that never blocks on another CTA while it has a store to issue.  Per item it issues the store, waits until the
+// TMA engine has read the stage (the one long wait, as in k_tile_stream) and reloads the stage.  Whether the reload's
+// dependency is met it reads from shared memory: the stage's table-builder warp, which runs ahead and has slack, polls the
+// completion counter in global memory and posts the result.  Finished stores are counted when the loop is idle.
+__device__ __noinline__ void resident_driver(ResidentSmem* smp, double2* state, const CUtensorMap* tmap0, const CUtensorMap* tmap1,
+                                             int* cnt, long long K) {
+    ResidentSmem& sm = *smp;
+    long long load_k = 0, store_k = 0;
+    int ls = 0, lu = 0, ss = 0, su = 0;               // stage and use count (mod 3) of the load / store candidate
+    uint32_t spar = 0;                                // parity of done[ss] for the store candidate
+    int* pend = sm.pend;                              // counters of items stored but not yet counted
+    int n_pend = 0;
+    PROF_DECL;
+    while (store_k < K) {
+        bool progressed = false;
+        PROF_LAP(0);
+        if (store_k < load_k && mbar_test(smem_u32(&sm.done[ss]), spar)) {
+            const ResidentPost it = sm.post[ss][su];
+            if (it.readonly) {
+                red_relaxed_gpu(cnt + it.counter);    // read-only item: complete as soon as the stage has been consumed
+            } else {
+                if (n_pend == 4) {
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    for (int i = 0; i < n_pend; ++i) red_relaxed_gpu(cnt + pend[i]);
+                    n_pend = 0;
+                }
+                const ResidentTma P = {it.contig, it.mode, it.g};
+                stream_tma_store(P, it.tmap ? tmap1 : tmap0, state, it.tile, smem_u32(sm.stage[ss]));
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the stage may be reloaded
+                pend[n_pend++] = it.counter;
+            }
+            ++store_k;
+            if (++ss == DTC_STREAM_STAGES) { ss = 0; spar ^= 1u; if (++su == 3) su = 0; }
+            progressed = true;
+            PROF_LAP(1);
+        }
+        if (load_k < K && load_k < store_k + DTC_STREAM_STAGES) {
+            // dep_ok[s] = 1 + (index of the newest item of stage s whose dependency the builder has seen met and whose
+            // description it has posted)
+            if (*(volatile long long*)&sm.dep_ok[ls] > load_k) {
+                const ResidentPost it = sm.post[ls][lu];
+                if (it.gen) {
+                    mbar_arrive(smem_u32(&sm.full[ls]));
+                } else {
+                    // (no proxy fence: the load is issued only after the counter value has been observed -- a control
+                    //  dependency -- and it reads L2, where the producers' bulk stores had landed before they counted)
+                    const ResidentTma P = {it.contig, it.mode, it.g};
+                    stream_tma_load(P, it.tmap ? tmap1 : tmap0, state, it.tile, smem_u32(sm.stage[ls]), smem_u32(&sm.full[ls]));
+                }
+                ++load_k;
+                if (++ls == DTC_STREAM_STAGES) { ls = 0; if (++lu == 3) lu = 0; }
+                progressed = true;
+                PROF_LAP(2);
+            }
+        }
+        if (!progressed) {
+            if (n_pend) {                              // idle: count what has been stored (bounded wait on the TMA engine only)
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                for (int i = 0; i < n_pend; ++i) red_relaxed_gpu(cnt + pend[i]);
+                n_pend = 0;
+            } else if (load_k == K || load_k == store_k + DTC_STREAM_STAGES) {
+                // every stage is occupied: the only thing that can happen next is the oldest tile being finished --
+                // a hardware-assisted wait on its barrier
+                mbar_wait(smem_u32(&sm.done[ss]), spar);
+            }
+            // else: a free stage waits for its dependency (posted by the builder): poll again at once
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    for (int i = 0; i < n_pend; ++i) red_relaxed_gpu(cnt + pend[i]);
+    PROF_LAP(3);
+    PROF_FLUSH(0, true);
+}
+
+// ---- table builder of stage s (one warp), out of line for the same reason
+__device__ __noinline__ void resident_builder(ResidentSmem* smp, int s, int lane, const DtcStreamPass* __restrict__ passes,
+                                              const DtcLayer* __restrict__ layers, const u64* __restrict__ masks,
+                                              const int* cnt, long long K) {
+    ResidentSmem& sm = *smp;
+    const ResidentPlan& R = sm.plan;
+    StreamBuild& bl = sm.build[s];
+    StreamSlot& slot = sm.slot[s];
+    const int nt = 1 << R.nt_bits;
+    uint32_t par = 1;
+    ResidentIter bi;
+    bi.init((long long)blockIdx.x + (long long)s * gridDim.x, DTC_STREAM_STAGES * gridDim.x, R);
+    PROF_DECL;
+    DtcStreamPass& P = sm.bpass[s];
+    const DtcLayer& L = *reinterpret_cast<const DtcLayer*>(sm.blayer[s]);
+    int cached_p = -1;
+    for (long long k = s; k < K; k += DTC_STREAM_STAGES, bi.next(R)) {
+        const ResidentItem it = bi.item(R);
+        if (it.p != cached_p) {                       // new pass: stage its descriptor and layer tables (warp-private)
+            const uint4* src = reinterpret_cast<const uint4*>(passes + it.p);
+            uint4* dst = reinterpret_cast<uint4*>(&sm.bpass[s]);
+            for (int i = lane; i < (int)(sizeof(DtcStreamPass) / 16); i += 32) dst[i] = src[i];
+            __syncwarp();
+            if (P.layerD >= 0) {
+                const uint2* ls = reinterpret_cast<const uint2*>(layers + P.layerD);
+                uint2* ld = reinterpret_cast<uint2*>(sm.blayer[s]);
+                for (int i = lane; i < DTC_LAYER_PREFIX / 8; i += 32) ld[i] = ls[i];
+            }
+            __syncwarp();
+            cached_p = it.p;
+        }
+        const StreamMasks M = stream_load_masks(P, masks, R.n_traj, it.traj);
+        const u64 base = stream_tile_base(it.T, P);
+        if (P.layerD >= 0) {
+            stream_build1(lane, bl, P, L, base | (R.rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
+            __syncwarp();
+            stream_build2(lane, bl, P, L);
+            __syncwarp();
+        }
+        PROF_LAP(0);
+        if (lane == 0) {
+            ResidentPost po;
+            po.tile = ((u64)it.j << R.nt_bits) | it.T;
+            po.counter = (int)(it.seq * R.G + it.j);
+            po.contig = (unsigned char)P.contig; po.mode = (unsigned char)P.mode; po.g = (unsigned char)P.g;
+            po.tmap = (unsigned char)P.tmap_slot;
+            po.gen = (it.p == 0 && R.gen_first) ? 1 : 0;
+            po.readonly = (R.fused_last && it.p == R.n_passes - 1) ? 1 : 0;
+            po.pad0 = po.pad1 = 0;
+            sm.post[s][(k / DTC_STREAM_STAGES) % 3] = po;
+            // the item's dependency: every tile of its state slot in the previous pass (previous group's last pass for
+            // pass 0) has been stored.  Polled here, ahead of time and off the TMA driver's critical path; the driver
+            // reads the outcome from shared memory.
+            if (it.seq > 0) {
+                const int* c = cnt + (it.seq - 1) * R.G + it.j;
+                while (ld_relaxed_gpu(c) < nt) __nanosleep(64);
+            }
+            __threadfence_block();
+            *(volatile long long*)&sm.dep_ok[s] = k + 1;
+        }
+        PROF_LAP(3);
+        if (k >= DTC_STREAM_STAGES) mbar_wait(smem_u32(&sm.done[s]), par);      // slot s is free again
+        PROF_LAP(1);
+        stream_build3(lane, bl, slot, P);
+        if (lane == 0) { slot.rmA = M.rmA; slot.rmB = M.rmB; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.full[s]));
+        par ^= 1u;
+        PROF_LAP(2);
+    }
+    PROF_FLUSH(4, lane == 0 && s == 0);
 }
 
 __global__ void __launch_bounds__(DTC_STREAM_THREADS, 1)
 k_tile_resident(double2* __restrict__ state, const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
-                const __grid_constant__ ResidentPlan R, const DtcStreamPass* __restrict__ passes,
-                const DtcLayer* __restrict__ layers, const u64* __restrict__ masks, int* __restrict__ cnt,
-                double2* __restrict__ rdm_out) {
+                const __grid_constant__ ResidentPlan R, const __grid_constant__ ResidentPasses RP,
+                const DtcStreamPass* __restrict__ passes, const DtcLayer* __restrict__ layers,
+                const u64* __restrict__ masks, int* __restrict__ cnt, double2* __restrict__ rdm_out) {
     extern __shared__ unsigned char smraw[];
-    StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smraw + ((128u - (smem_u32(smraw) & 127u)) & 127u));
+    ResidentSmem& sm = *reinterpret_cast<ResidentSmem*>(smraw + ((128u - (smem_u32(smraw) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long K = (R.total_items - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x;
-    const int nt = 1 << R.nt_bits;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < DTC_STREAM_STAGES; ++s) {
             mbar_init(smem_u32(&sm.full[s]), 2);
             mbar_init(smem_u32(&sm.done[s]), 128);
+            sm.dep_ok[s] = 0;
         }
+        sm.plan = R;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < R.n_passes) {
+        sm.pinfo[tid][0] = RP.p[tid].contig;
+        sm.pinfo[tid][1] = RP.p[tid].mode;
+        sm.pinfo[tid][2] = RP.p[tid].g;
+        sm.pinfo[tid][3] = RP.p[tid].tmap_slot;
     }
     __syncthreads();
     if (warp == 4 * DTC_STREAM_WG) {
-        // ---- TMA driver: an event loop that never blocks on another CTA while it has a store to issue
-        if ((tid & 31) != 0) return;
-        long long load_k = 0, store_k = 0;
-        int pend[4], n_pend = 0;                          // counters of items stored but not yet signalled
-        while (store_k < K) {
-            bool progressed = false;
-            if (load_k < K && load_k < store_k + DTC_STREAM_STAGES) {
-                const ResidentItem it = resident_decode((long long)blockIdx.x + load_k * gridDim.x, R);
-                bool ok = true;
-                if (it.seq > 0) ok = ld_acquire_gpu(cnt + (it.seq - 1) * R.G + it.j) >= nt;
-                if (ok) {
-                    const int s = (int)(load_k % DTC_STREAM_STAGES);
-                    if (it.p == 0 && R.gen_first) {
-                        mbar_arrive(smem_u32(&sm.full[s]));
-                    } else {
-                        asm volatile("fence.proxy.async;" ::: "memory");       // acquired generic-proxy view -> TMA read
-                        const DtcStreamPass& P = passes[it.p];
-                        stream_tma_load(P, P.tmap_slot ? &tmap1 : &tmap0, state, ((u64)it.j << R.nt_bits) | it.T,
-                                        smem_u32(sm.stage[s]), smem_u32(&sm.full[s]));
-                    }
-                    ++load_k;
-                    progressed = true;
-                }
-            }
-            if (store_k < load_k) {
-                const int s = (int)(store_k % DTC_STREAM_STAGES);
-                if (mbar_test(smem_u32(&sm.done[s]), (uint32_t)((store_k / DTC_STREAM_STAGES) & 1))) {
-                    const ResidentItem it = resident_decode((long long)blockIdx.x + store_k * gridDim.x, R);
-                    const int ci = (int)(it.seq * R.G + it.j);
-                    if (R.fused_last && it.p == R.n_passes - 1) {
-                        atomicAdd(cnt + ci, 1);               // read-only item: complete as soon as the stage has been consumed
-                    } else {
-                        const DtcStreamPass& P = passes[it.p];
-                        stream_tma_store(P, P.tmap_slot ? &tmap1 : &tmap0, state, ((u64)it.j << R.nt_bits) | it.T, smem_u32(sm.stage[s]));
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the stage may be reloaded
-                        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");           // all earlier stores have landed
-                        if (n_pend) {
-                            asm volatile("fence.proxy.async;" ::: "memory");
-                            __threadfence();
-                            for (int i = 0; i < n_pend; ++i) atomicAdd(cnt + pend[i], 1);
-                            n_pend = 0;
-                        }
-                        pend[n_pend++] = ci;
-                    }
-                    ++store_k;
-                    progressed = true;
-                }
-            }
-            if (!progressed) {
-                if (n_pend) {                              // idle: publish what has been stored (bounded wait on the TMA engine only)
-                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    __threadfence();
-                    for (int i = 0; i < n_pend; ++i) atomicAdd(cnt + pend[i], 1);
-                    n_pend = 0;
-                } else {
-                    __nanosleep(64);
-                }
-            }
-        }
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        if (n_pend) {
-            asm volatile("fence.proxy.async;" ::: "memory");
-            __threadfence();
-            for (int i = 0; i < n_pend; ++i) atomicAdd(cnt + pend[i], 1);
-        }
+        if ((tid & 31) == 0) resident_driver(&sm, state, &tmap0, &tmap1, cnt, K);
         return;
     }
     if (warp > 4 * DTC_STREAM_WG) {
-        // ---- table builder of stage s
-        const int lane = tid & 31, s = warp - (4 * DTC_STREAM_WG + 1);
-        StreamBuild& bl = sm.build[s];
-        StreamSlot& slot = sm.slot[s];
-        uint32_t par = 1;
-        for (long long k = s; k < K; k += DTC_STREAM_STAGES) {
-            const ResidentItem it = resident_decode((long long)blockIdx.x + k * gridDim.x, R);
-            const DtcStreamPass& P = passes[it.p];
-            const StreamMasks M = stream_load_masks(P, masks, R.n_traj, it.traj);
-            const u64 base = stream_tile_base(it.T, P);
-            if (P.layerD >= 0) {
-                const DtcLayer& L = layers[P.layerD];
-                stream_build1(lane, bl, P, L, base | (R.rank_bits << P.n_local), M.m1a, M.m1b, M.m2);
-                __syncwarp();
-                stream_build2(lane, bl, P, L);
-                __syncwarp();
-            }
-            if (k >= DTC_STREAM_STAGES) mbar_wait(smem_u32(&sm.done[s]), par);      // slot s is free again
-            stream_build3(lane, bl, slot, P);
-            if (lane == 0) { slot.rmA = M.rmA; slot.rmB = M.rmB; }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&sm.full[s]));
-            par ^= 1u;
-        }
+        const int s = warp - (4 * DTC_STREAM_WG + 1);
+        if (s < K) resident_builder(&sm, s, tid & 31, passes, layers, masks, cnt, K);
         return;
     }
     // ---- compute warpgroups
     const int wg = warp >> 2, t = tid & 127;
-    for (long long k = wg; k < K; k += DTC_STREAM_WG) {
+    ResidentIter ci;
+    ci.init((long long)blockIdx.x + (long long)wg * gridDim.x, DTC_STREAM_WG * gridDim.x, R);
+    PROF_DECL;
+    for (long long k = wg; k < K; k += DTC_STREAM_WG, ci.next(R)) {
         const int s = (int)(k % DTC_STREAM_STAGES);
         const uint32_t u = (uint32_t)(k / DTC_STREAM_STAGES);
-        const ResidentItem it = resident_decode((long long)blockIdx.x + k * gridDim.x, R);
-        const DtcStreamPass& P = passes[it.p];
+        const ResidentItem it = ci.item(R);
+        const DtcResidentPass& P = RP.p[it.p];
         const int mode = P.mode;
         if (u > 0) mbar_wait(smem_u32(&sm.done[s]), (u - 1) & 1u);
         mbar_wait(smem_u32(&sm.full[s]), u & 1u);
         if (mode != 1) wg_barrier(wg);
+        PROF_LAP(0);
         double2* tile = sm.stage[s];
         const StreamSlot& slot = sm.slot[s];
         const u64 rmA = slot.rmA, rmB = slot.rmB;
@@ -706,9 +840,11 @@ k_tile_resident(double2* __restrict__ state, const __grid_constant__ CUtensorMap
                 }
             }
             if (mode == 1) __syncwarp(); else wg_barrier(wg);
+            PROF_LAP(1);
             if (P.layerA >= 0 && P.layerD >= 0 && P.layerB >= 0) stream_phase2(t, tile, slot, P, rmA, rmB);
             else stream_phase2_partial_call(t, tile, &slot, &P, rmA, rmB);
             if (mode == 1) __syncwarp(); else wg_barrier(wg);
+            PROF_LAP(2);
             if (P.layerB >= 0) {
                 if (mode == 1) {
                     stream_signed_s1<1>(P.t2, P.tb, rmB, tt);
@@ -738,7 +874,10 @@ k_tile_resident(double2* __restrict__ state, const __grid_constant__ CUtensorMap
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(smem_u32(&sm.done[s]));
+        PROF_LAP(3);
     }
+    PROF_FLUSH(8, t == 0 && wg == 0);
+    PROF_FLUSH(12, t == 0 && wg == 1);
 }
 
 // ---- generic engine
@@ -1368,7 +1507,8 @@ int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
     const size_t eb = p->h.events.size() * sizeof(DtcEvent), lb = p->h.layers.size() * sizeof(DtcLayer);
     CUDA_TRY(table_upload((void**)&p->d_events, p->h.events.data(), eb, 16, device));
     CUDA_TRY(table_upload((void**)&p->d_layers, p->h.layers.data(), lb, 16, device));
-    if (engine == DTC_ENGINE_TILE && !p->h.spasses.empty() && n_local <= 22) {
+    static_assert(sizeof(DtcStreamPass) % 16 == 0, "builder warps copy pass descriptors in 16 B pieces");
+    if (engine == DTC_ENGINE_TILE && !p->h.spasses.empty() && n_local <= 22 && p->h.spasses.size() <= DTC_RESIDENT_MAX_PASSES) {
         bool ok = true;
         for (DtcStreamPass& S : p->h.spasses) {
             if (!S.mode) { ok = false; break; }
@@ -1405,7 +1545,7 @@ int dtc_program_finalize(dtc_program* p, int device, int engine, int n_local) {
         CUDA_TRY(cudaFuncSetAttribute(k_tile_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
         CUDA_TRY(cudaFuncSetAttribute(k_tile_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
         CUDA_TRY(cudaFuncSetAttribute(k_tile_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
-        CUDA_TRY(cudaFuncSetAttribute(k_tile_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, ssb));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResidentSmem) + 128));
         CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms[device], cudaDevAttrMultiProcessorCount, device));
         attr_set[device] = true;
     }
@@ -1638,10 +1778,20 @@ int dtc_program_run_resident(dtc_program* p, void* scratch, size_t scratch_bytes
     const DtcStreamPass* dsp = p->d_spasses;
     const DtcLayer* dl = p->d_layers;
     const u64* dm = masks;
-    void* args[] = {&st, &tm[0], &tm[1], &R, &dsp, &dl, &dm, &cnt, &rdm_out};
+    static thread_local ResidentPasses RP;
+    for (size_t i = 0; i < h.spasses.size(); ++i) {
+        const DtcStreamPass& S = h.spasses[i];
+        DtcResidentPass& Q = RP.p[i];
+        Q.mode = (unsigned char)S.mode; Q.contig = (unsigned char)S.contig; Q.g = (unsigned char)S.g;
+        Q.tmap_slot = (unsigned char)S.tmap_slot;
+        Q.layerA = (short)S.layerA; Q.layerD = (short)S.layerD; Q.layerB = (short)S.layerB; Q.n_local = (short)S.n_local;
+        for (int l = 0; l < DTC_TILE_BITS; ++l) { Q.tb[l] = (unsigned char)S.tb[l]; Q.t1[l] = S.t1[l]; Q.t2[l] = S.t2[l]; }
+        Q.tile_mask = S.tile_mask;
+    }
+    void* args[] = {&st, &tm[0], &tm[1], &R, &RP, &dsp, &dl, &dm, &cnt, &rdm_out};
     // cooperative launch: all CTAs are co-resident by construction (they wait on one another's progress)
     CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_tile_resident, dim3(grid), dim3(DTC_STREAM_THREADS), args,
-                                         sizeof(StreamSmem) + 128, s));
+                                         sizeof(ResidentSmem) + 128, s));
     if (p->profiling) CUDA_TRY(cudaEventRecord(p->ev1, s));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(p->last_use, s));

@@ -742,6 +742,6 @@ def test_resident_execution_equals_streamed(ctx, disorder, L, t, echo, ntraj, re
         assert float((got2.readout_rdm() - rdm_ref).abs().max()) < 1e-12
         h.close()
     finally:
-        capi.RESIDENT = True
+        capi.RESIDENT = False
         capi.set_resident_bytes(64 << 20)
         capi.set_high_stride_bit(15)
