@@ -89,6 +89,21 @@ int dtc_program_workspace_bytes(const dtc_program *p, int64_t n_traj, size_t *by
 int dtc_program_run(dtc_program *p, void *state, int64_t n_traj, int64_t traj_offset, uint64_t seed,
                     uint64_t init_index, uint64_t rank_bits, void *workspace, size_t workspace_bytes,
                     void *stream);
+/* dtc_program_run in two steps, for callers that interleave the passes of a program with other work (sharded.py: a
+ * shard is swept slice by slice and each finished slice is sent while the next one is swept).
+ * prepare(): the frame walk only (sign masks + final frames into the workspace).  run_passes(): passes [pass_begin, pass_end)
+ * of the tile engine's schedule on `state`, using the masks prepare() left in the workspace; init_index other than
+ * DTC_INIT_KEEP is allowed when pass_begin == 0.  store_last_or_null: the LAST pass of the range stores its tiles to that
+ * buffer (same layout as `state`) instead of in place -- it may be a peer GPU's memory mapped into this process, so the
+ * sweep's TMA stores travel over NVLink straight into the receiver's buffer (the pass must be a streaming pass with
+ * contiguous tiles: dtc_program_pass_info).  n_ctas > 0 limits the persistent grid, leaving SMs to a kernel on another
+ * stream. */
+int dtc_program_prepare(dtc_program *p, int64_t n_traj, int64_t traj_offset, uint64_t seed, void *workspace,
+                        size_t workspace_bytes, void *stream);
+int dtc_program_run_passes(dtc_program *p, void *state, void *store_last_or_null, int pass_begin, int pass_end, int n_ctas,
+                           int64_t n_traj, uint64_t init_index, uint64_t rank_bits, void *workspace,
+                           size_t workspace_bytes, void *stream);
+int dtc_program_pass_info(const dtc_program *p, int pass, int *streaming, int *contiguous);
 /* Device pointers (inside the workspace) to the final frame of each trajectory:
  * fx, fz: uint64[n_traj] bit masks; ph: int32[n_traj] power of i.  psi_true = i^ph X^fx Z^fz psi'. */
 int dtc_program_frames(const dtc_program *p, void *workspace, int64_t n_traj,

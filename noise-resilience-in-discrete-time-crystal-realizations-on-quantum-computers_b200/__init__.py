@@ -10,6 +10,7 @@ from .lowering import generate_preset_pass_manager, lower_level0, SNAKE_LAYOUT  
 from .noise import NoiseModel, depolarizing_error, pauli_error, as_noise_model   # noqa: F401
 from .plan import compile_circuit, Program                                       # noqa: F401
 from .sweeps import autocorr_circuit, floquet_period, run_sweep, xy_cycle_schedule  # noqa: F401
+from .estimator import BackendEstimatorV2, dtc_hamiltonian                        # noqa: F401
 
 __version__ = "0.1.0"
 

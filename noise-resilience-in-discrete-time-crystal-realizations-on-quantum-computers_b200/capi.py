@@ -31,6 +31,10 @@ _SIGS = {
     "dtc_program_num_passes": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_workspace_bytes": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(ctypes.c_size_t)]),
     "dtc_program_run": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_u64, c_u64, c_u64, c_vp, ctypes.c_size_t, c_vp]),
+    "dtc_program_prepare": (ctypes.c_int, [c_vp, c_i64, c_i64, c_u64, c_vp, ctypes.c_size_t, c_vp]),
+    "dtc_program_run_passes": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64, c_u64, c_u64,
+                                              c_vp, ctypes.c_size_t, c_vp]),
+    "dtc_program_pass_info": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_frames": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
                                           ctypes.POINTER(c_vp)]),
     "dtc_program_set_readout": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, c_i32p, ctypes.c_int,
@@ -214,6 +218,22 @@ class ProgramHandle:
         r, k = ctypes.c_int(0), ctypes.c_int(0)
         check(load().dtc_program_last_run_info(self._h, ctypes.byref(r), ctypes.byref(k)))
         return bool(r.value), k.value
+
+    def prepare(self, n_traj, traj_offset, seed, ws_ptr, ws_bytes, stream):
+        """Frame walk only (sign masks into the workspace); run_passes() then executes pass ranges."""
+        check(load().dtc_program_prepare(self._h, int(n_traj), int(traj_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, ws_ptr,
+                                         ws_bytes, stream))
+
+    def run_passes(self, state_ptr, begin, end, n_traj, ws_ptr, ws_bytes, stream, store_last=None, n_ctas=0,
+                   init_index=INIT_KEEP, rank_bits=0):
+        check(load().dtc_program_run_passes(self._h, state_ptr, store_last, int(begin), int(end), int(n_ctas), int(n_traj),
+                                            int(init_index), int(rank_bits), ws_ptr, ws_bytes, stream))
+
+    def pass_info(self, i):
+        """(runs on the streaming engine, tiles contiguous in memory) of pass i."""
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        check(load().dtc_program_pass_info(self._h, int(i), ctypes.byref(a), ctypes.byref(b)))
+        return bool(a.value), bool(b.value)
 
     def set_fused_rdm(self, enable=True):
         """Let the last pass reduce the read-out qubit's density matrix instead of storing the state (factorised

@@ -327,7 +327,9 @@ template <int MODE>
 __global__ void __launch_bounds__(DTC_STREAM_THREADS, 1)
 k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DtcStreamPass P,
               const DtcLayer* __restrict__ layers, const u64* __restrict__ masks, long long n_traj, u64 rank_bits,
-              long long n_tiles, u64 init_index, double2* __restrict__ rdm_out, int rdm_local_bit) {
+              long long n_tiles, u64 init_index, double2* __restrict__ rdm_out, int rdm_local_bit, double2* store_base) {
+    // store_base != state (contiguous tiles only): the finished tiles are stored THERE instead of in place -- e.g. straight
+    // into a peer GPU's receive buffer over NVLink, fusing the last sweep before an exchange with the exchange itself.
     // rdm_out != nullptr (last pass of a factorised circuit): the tile is not stored; the reduced density matrix of the
     // tile-local bit rdm_local_bit of psi' is accumulated into rdm_out[trajectory][2][2] instead.
     // init_index != DTC_INIT_KEEP: the input is not read -- every trajectory starts in the basis state init_index
@@ -364,7 +366,7 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
         for (long long k = 0; k < K; ++k) {
             mbar_wait(smem_u32(&sm.done[s]), par);
             PROF_LAP(0);
-            if (!rdm_out) stream_tma_store(P, &tmap, state, (u64)blockIdx.x + (u64)k * gridDim.x, smem_u32(sm.stage[s]));
+            if (!rdm_out) stream_tma_store(P, &tmap, store_base, (u64)blockIdx.x + (u64)k * gridDim.x, smem_u32(sm.stage[s]));
             if (k + DTC_STREAM_STAGES < K) {
                 if (!rdm_out) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has read the stage
                 PROF_LAP(1);
@@ -1582,6 +1584,89 @@ int dtc_program_frames(const dtc_program* p, void* workspace, int64_t n_traj, ui
     return DTC_OK;
 }
 
+// frames of the batch: sign masks of every layer + final frames into the workspace
+static int run_frames(dtc_program* p, int64_t n_traj, int64_t traj_offset, uint64_t seed, void* workspace, cudaStream_t s) {
+    const DtcProgramHost& h = p->h;
+    u64 *masks, *fx, *fz;
+    int* ph;
+    ws_pointers(h, workspace, n_traj, &masks, &fx, &fz, &ph);
+    CUDA_TRY(cudaMemsetAsync(masks, 0, (size_t)h.n_layers * 4 * n_traj * sizeof(u64), s));
+    const int fb = 128;
+    k_frames<<<(unsigned)((n_traj + fb - 1) / fb), fb, 0, s>>>(p->d_events, (long long)h.events.size(), masks,
+                                                              n_traj, traj_offset, seed, fx, fz, ph);
+    return DTC_OK;
+}
+
+// passes [begin, end) of the tile engine's schedule.  store_last != nullptr: the last pass of the range stores its tiles there
+// instead of in place (that pass must run on k_tile_stream with contiguous tiles).  n_ctas > 0 limits the persistent grid.
+static int run_tile_passes(dtc_program* p, void* state, void* store_last, int begin, int end, int n_ctas, int64_t n_traj,
+                           uint64_t init_index, bool gen_first, bool fused, uint64_t rank_bits, void* workspace, cudaStream_t s) {
+    const DtcProgramHost& h = p->h;
+    u64 *masks, *fx, *fz;
+    int* ph;
+    ws_pointers(h, workspace, n_traj, &masks, &fx, &fz, &ph);
+    const long long grid = n_traj << (h.n_local - DTC_TILE_BITS);
+    if (grid > 0x7fffffffLL) return fail(DTC_ERR_INVALID, "batch too large for one launch");
+    static const int pf = []() {
+        const char* e = getenv("DTCSIM_PREFETCH_BLOCKS");      // tuning knob; default 148 CTAs ahead (measured best on B200)
+        return e ? atoi(e) : 148;
+    }();
+    const int n_sms = (h.device >= 0 && h.device < 16 && g_num_sms[h.device] > 0) ? g_num_sms[h.device] : 148;
+    for (int ip = begin; ip < end; ++ip) {
+        const DtcTilePass& T = h.passes[(size_t)ip];
+        const DtcStreamPass& S = h.spasses[(size_t)ip];
+        double2* out = (double2*)state;
+        if (store_last && ip + 1 == end) {
+            if (!(S.mode && S.contig && stream_enabled()))
+                return fail(DTC_ERR_UNSUPPORTED, "out-of-place store needs a streaming pass with contiguous tiles");
+            out = (double2*)store_last;
+        }
+        if (S.mode && stream_enabled()) {
+            // TMA-fed streaming engine: one persistent CTA per SM
+            alignas(64) CUtensorMap tm;
+            memset(&tm, 0, sizeof(tm));
+            if (!S.contig) {
+                const int rc = stream_tensor_map(&tm, state, h.n_local, S.g, n_traj, S.mode);
+                if (rc != DTC_OK) return rc;
+            }
+            int max_ctas = (g_stream_ctas > 0 && g_stream_ctas < n_sms) ? g_stream_ctas : n_sms;
+            if (n_ctas > 0 && n_ctas < max_ctas) max_ctas = n_ctas;
+            const unsigned sgrid = (unsigned)(grid < max_ctas ? grid : max_ctas);
+            const size_t ssb = sizeof(StreamSmem) + 128;
+            const u64 init = (ip == 0 && gen_first) ? (u64)init_index : (u64)DTC_INIT_KEEP;
+            double2* rdm_out = nullptr;
+            if (fused && ip + 1 == (int)h.passes.size()) {
+                rdm_out = (double2*)((char*)workspace + dtc_workspace_rdm_offset(h, n_traj));
+                CUDA_TRY(cudaMemsetAsync(rdm_out, 0, sizeof(double2) * 4 * (size_t)n_traj, s));
+            }
+            if (S.mode == 1)
+                k_tile_stream<1><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
+                                                                       rdm_out, p->fused_local_bit, out);
+            else if (S.mode == 2)
+                k_tile_stream<2><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
+                                                                       rdm_out, p->fused_local_bit, out);
+            else
+                k_tile_stream<3><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
+                                                                       rdm_out, p->fused_local_bit, out);
+            continue;
+        }
+        const bool hx = T.layerD >= 0 && T.nX > 0;
+#define DTC_LAUNCH(S, X)                                                                               \
+    k_tile_pass<S, X><<<(unsigned)grid, DTC_THREADS, sizeof(TileSmem), s>>>((double2*)state, T, p->d_layers, masks, \
+                                                                            n_traj, rank_bits, pf)
+        switch (T.s2_lo * 2 + (hx ? 1 : 0)) {
+            case 0: DTC_LAUNCH(0, false); break;
+            case 1: DTC_LAUNCH(0, true); break;
+            case 2: DTC_LAUNCH(1, false); break;
+            case 3: DTC_LAUNCH(1, true); break;
+            case 4: DTC_LAUNCH(2, false); break;
+            default: DTC_LAUNCH(2, true); break;
+        }
+#undef DTC_LAUNCH
+    }
+    return DTC_OK;
+}
+
 int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_offset, uint64_t seed,
                     uint64_t init_index, uint64_t rank_bits, void* workspace, size_t workspace_bytes, void* stream) {
     if (!p || !p->h.finalized) return fail(DTC_ERR_INVALID, "program not finalized");
@@ -1594,13 +1679,11 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     DeviceGuard guard(h.device);
     CUDA_TRY(guard.err);
     CUDA_TRY(cudaStreamWaitEvent(s, p->uploaded, 0));
+    int rc = run_frames(p, n_traj, traj_offset, seed, workspace, s);
+    if (rc != DTC_OK) return rc;
     u64 *masks, *fx, *fz;
     int* ph;
     ws_pointers(h, workspace, n_traj, &masks, &fx, &fz, &ph);
-    CUDA_TRY(cudaMemsetAsync(masks, 0, (size_t)h.n_layers * 4 * n_traj * sizeof(u64), s));
-    const int fb = 128;
-    k_frames<<<(unsigned)((n_traj + fb - 1) / fb), fb, 0, s>>>(p->d_events, (long long)h.events.size(), masks,
-                                                              n_traj, traj_offset, seed, fx, fz, ph);
     const bool fused = p->fuse_rdm && p->fused_local_bit >= 0 && stream_enabled();
     // the first pass can generate the initial state itself (no memset, no read) when it runs on k_tile_stream
     const bool gen_first = !keep && h.engine == DTC_ENGINE_TILE && !h.spasses.empty() && h.spasses[0].mode && stream_enabled();
@@ -1617,58 +1700,8 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     if (p->profiling) CUDA_TRY(cudaEventRecord(p->ev0, s));
     p->last_launches = (h.engine == DTC_ENGINE_TILE) ? (int)h.passes.size() : (int)h.gsteps.size();
     if (h.engine == DTC_ENGINE_TILE) {
-        const long long grid = n_traj << (h.n_local - DTC_TILE_BITS);
-        if (grid > 0x7fffffffLL) return fail(DTC_ERR_INVALID, "batch too large for one launch");
-        static const int pf = []() {
-            const char* e = getenv("DTCSIM_PREFETCH_BLOCKS");      // tuning knob; default 148 CTAs ahead (measured best on B200)
-            return e ? atoi(e) : 148;
-        }();
-        const int n_sms = (h.device >= 0 && h.device < 16 && g_num_sms[h.device] > 0) ? g_num_sms[h.device] : 148;
-        for (size_t ip = 0; ip < h.passes.size(); ++ip) {
-            const DtcTilePass& T = h.passes[ip];
-            const DtcStreamPass& S = h.spasses[ip];
-            if (S.mode && stream_enabled()) {
-                // TMA-fed streaming engine: one persistent CTA per SM
-                alignas(64) CUtensorMap tm;
-                memset(&tm, 0, sizeof(tm));
-                if (!S.contig) {
-                    const int rc = stream_tensor_map(&tm, state, h.n_local, S.g, n_traj, S.mode);
-                    if (rc != DTC_OK) return rc;
-                }
-                const int max_ctas = (g_stream_ctas > 0 && g_stream_ctas < n_sms) ? g_stream_ctas : n_sms;
-                const unsigned sgrid = (unsigned)(grid < max_ctas ? grid : max_ctas);
-                const size_t ssb = sizeof(StreamSmem) + 128;
-                const u64 init = (ip == 0 && gen_first) ? (u64)init_index : (u64)DTC_INIT_KEEP;
-                double2* rdm_out = nullptr;
-                if (fused && ip + 1 == h.passes.size()) {
-                    rdm_out = (double2*)((char*)workspace + dtc_workspace_rdm_offset(h, n_traj));
-                    CUDA_TRY(cudaMemsetAsync(rdm_out, 0, sizeof(double2) * 4 * (size_t)n_traj, s));
-                }
-                if (S.mode == 1)
-                    k_tile_stream<1><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
-                                                                           rdm_out, p->fused_local_bit);
-                else if (S.mode == 2)
-                    k_tile_stream<2><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
-                                                                           rdm_out, p->fused_local_bit);
-                else
-                    k_tile_stream<3><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
-                                                                           rdm_out, p->fused_local_bit);
-                continue;
-            }
-            const bool hx = T.layerD >= 0 && T.nX > 0;
-#define DTC_LAUNCH(S, X)                                                                               \
-    k_tile_pass<S, X><<<(unsigned)grid, DTC_THREADS, sizeof(TileSmem), s>>>((double2*)state, T, p->d_layers, masks, \
-                                                                            n_traj, rank_bits, pf)
-            switch (T.s2_lo * 2 + (hx ? 1 : 0)) {
-                case 0: DTC_LAUNCH(0, false); break;
-                case 1: DTC_LAUNCH(0, true); break;
-                case 2: DTC_LAUNCH(1, false); break;
-                case 3: DTC_LAUNCH(1, true); break;
-                case 4: DTC_LAUNCH(2, false); break;
-                default: DTC_LAUNCH(2, true); break;
-            }
-#undef DTC_LAUNCH
-        }
+        rc = run_tile_passes(p, state, nullptr, 0, (int)h.passes.size(), 0, n_traj, init_index, gen_first, fused, rank_bits, workspace, s);
+        if (rc != DTC_OK) return rc;
     } else {
         for (const DtcGenericStep& g : h.gsteps) {
             if (g.kind == 0) {
@@ -1686,6 +1719,62 @@ int dtc_program_run(dtc_program* p, void* state, int64_t n_traj, int64_t traj_of
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(p->last_use, s));
     p->used = true;
+    return DTC_OK;
+}
+
+int dtc_program_prepare(dtc_program* p, int64_t n_traj, int64_t traj_offset, uint64_t seed, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    if (!p || !p->h.finalized) return fail(DTC_ERR_INVALID, "program not finalized");
+    if (!workspace || n_traj < 1) return fail(DTC_ERR_INVALID, "bad argument");
+    if (workspace_bytes < dtc_workspace_bytes(p->h, n_traj)) return fail(DTC_ERR_INVALID, "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    DeviceGuard guard(p->h.device);
+    CUDA_TRY(guard.err);
+    CUDA_TRY(cudaStreamWaitEvent(s, p->uploaded, 0));
+    const int rc = run_frames(p, n_traj, traj_offset, seed, workspace, s);
+    if (rc != DTC_OK) return rc;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(p->last_use, s));
+    p->used = true;
+    return DTC_OK;
+}
+
+int dtc_program_run_passes(dtc_program* p, void* state, void* store_last, int pass_begin, int pass_end, int n_ctas,
+                           int64_t n_traj, uint64_t init_index, uint64_t rank_bits, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    if (!p || !p->h.finalized) return fail(DTC_ERR_INVALID, "program not finalized");
+    if (!state || !workspace || n_traj < 1) return fail(DTC_ERR_INVALID, "bad argument");
+    const DtcProgramHost& h = p->h;
+    if (h.engine != DTC_ENGINE_TILE) return fail(DTC_ERR_UNSUPPORTED, "pass ranges exist for the tile engine only");
+    if (pass_begin < 0 || pass_end > (int)h.passes.size() || pass_begin >= pass_end) return fail(DTC_ERR_INVALID, "bad pass range");
+    if (workspace_bytes < dtc_workspace_bytes(h, n_traj)) return fail(DTC_ERR_INVALID, "workspace too small");
+    const bool keep = init_index == DTC_INIT_KEEP, zero = init_index == DTC_INIT_ZERO;
+    if (!keep && !zero && (init_index >> h.n_local)) return fail(DTC_ERR_INVALID, "init_index out of range");
+    if (!keep && pass_begin != 0) return fail(DTC_ERR_INVALID, "only the first pass can start from a basis state");
+    cudaStream_t s = (cudaStream_t)stream;
+    DeviceGuard guard(h.device);
+    CUDA_TRY(guard.err);
+    CUDA_TRY(cudaStreamWaitEvent(s, p->uploaded, 0));
+    const bool gen_first = !keep && h.spasses[0].mode && stream_enabled();
+    if (!keep && !gen_first) {
+        CUDA_TRY(cudaMemsetAsync(state, 0, ((size_t)n_traj << h.n_local) * sizeof(double2), s));
+        if (!zero)
+            k_init_basis<<<(unsigned)((n_traj + 127) / 128), 128, 0, s>>>((double2*)state, h.n_local, n_traj, init_index);
+    }
+    const int rc = run_tile_passes(p, state, store_last, pass_begin, pass_end, n_ctas, n_traj, init_index, gen_first, false, rank_bits,
+                                   workspace, s);
+    if (rc != DTC_OK) return rc;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(p->last_use, s));
+    p->used = true;
+    return DTC_OK;
+}
+
+int dtc_program_pass_info(const dtc_program* p, int pass, int* streaming, int* contiguous) {
+    if (!p || !p->h.finalized || !streaming || !contiguous) return fail(DTC_ERR_INVALID, "bad argument");
+    if (p->h.engine != DTC_ENGINE_TILE || pass < 0 || pass >= (int)p->h.spasses.size()) return fail(DTC_ERR_INVALID, "no such pass");
+    *streaming = p->h.spasses[(size_t)pass].mode != 0 && stream_enabled();
+    *contiguous = p->h.spasses[(size_t)pass].contig;
     return DTC_OK;
 }
 

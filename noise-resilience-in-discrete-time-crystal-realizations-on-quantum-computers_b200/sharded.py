@@ -285,6 +285,7 @@ class CudaShardEngine:
        * `thread` ranks emulated by threads on one GPU (ThreadFabric; tests)."""
 
     NCCL_SMS = 20            # SMs left to the NCCL send/recv kernels while sweeps and exchange overlap (nccl mode)
+    REMOTE_CTAS = int(__import__("os").environ.get("DTCSIM_REMOTE_CTAS", "32"))   # persistent CTAs of a sweep that stores to a peer
 
     def __init__(self, n, n_local, rank, world, device_index, group=None, transport=None, overlap=True, fabric=None):
         import torch
@@ -321,6 +322,12 @@ class CudaShardEngine:
         if transport == "thread":
             fabric.register(rank, self.a, self.b)
         self.comm = torch.cuda.Stream(device=self.ctx.index) if world > 1 else None
+        # symm / thread transports: the LAST sweep of a slice program stores its tiles straight into the receiver's buffer
+        # (TMA stores to peer memory over NVLink) -- sweep and exchange are one kernel; it runs on the side stream with
+        # REMOTE_CTAS persistent CTAs while the other SMs already sweep the next slice
+        self.fuse_store = __import__("os").environ.get("DTCSIM_FUSE_STORE", "1") == "1"
+        self.fused_stores = 0
+        self.n_sms = torch.cuda.get_device_properties(self.ctx.index).multi_processor_count
         self._handles = {}
         self.passes = 0
         self.fast_exchanges = 0
@@ -337,6 +344,8 @@ class CudaShardEngine:
             h = capi.ProgramHandle(prog, self.ctx.index, capi.ENGINE_AUTO, n_local)
             wsb = h.workspace_bytes(1)
             hit = (h, self.ctx.empty(wsb, self.torch.uint8), wsb)
+            # segment programs are ideal (signs resolved on the host): their sign masks are all zero, written once
+            h.prepare(1, 0, 0, hit[1].data_ptr(), wsb, self.ctx.stream)
             if len(self._handles) >= 256:
                 old = self._handles.pop(next(iter(self._handles)))
                 old[0].close()                            # tables are freed in stream order after their last use
@@ -423,19 +432,46 @@ class CudaShardEngine:
             init = capi.INIT_KEEP if not first else (0 if (r == 0 and d == 0) else capi.INIT_ZERO)
             self._run(prog, a.data_ptr() + 16 * d * S, nls, init, (r << g) | d)
 
+        fuse = False
         if prog is not None:
-            self.passes += self._handle(prog, nls)[0].num_passes
+            h, ws, wsb = self._handle(prog, nls)
+            np_ = h.num_passes
+            self.passes += np_
+            fuse = self.fuse_store and not first and self.transport in ("symm", "thread") and self.overlap and nls >= 12
+            if fuse:
+                try:
+                    fuse = h.pass_info(np_ - 1) == (True, True)      # streaming pass with contiguous tiles
+                except ValueError:
+                    fuse = False
+
+        def sweep_and_send(d, dst_ptr, stream_last, ctas_main, ctas_last):
+            """Slice d: all sweeps but the last in place, the last one storing its tiles at dst_ptr (a peer's receive slot)."""
+            src = a.data_ptr() + 16 * d * S
+            if np_ > 1:
+                h.run_passes(src, 0, np_ - 1, 1, ws.data_ptr(), wsb, self.ctx.stream, n_ctas=ctas_main, rank_bits=(r << g) | d)
+            h.run_passes(src, np_ - 1, np_, 1, ws.data_ptr(), wsb, stream_last, store_last=dst_ptr, n_ctas=ctas_last,
+                         rank_bits=(r << g) | d)
+            self.passes_weighted += np_ * (1 << nls) / float(1 << self.n_local)
+            self.fused_stores += 1
 
         if self.transport == "thread":
-            # emulated ranks: all sweeps, barrier, every rank pulls its slices from the others' buffers, barrier
-            for d in range(P):
-                sweep(d)
+            # emulated ranks on one GPU: the "peer" buffers are the other threads' tensors
             torch.cuda.synchronize(self.ctx.index)
-            self.fabric.bar.wait()
-            for src in range(P):
-                b[src * S:(src + 1) * S].copy_(self.fabric.bufs[src]["a"][r * S:(r + 1) * S])
-            torch.cuda.synchronize(self.ctx.index)
-            self.fabric.bar.wait()
+            self.fabric.bar.wait()                     # every rank's receive buffer is free
+            if fuse:
+                for d in range(P):
+                    sweep_and_send(d, self.fabric.bufs[d]["b"].data_ptr() + 16 * r * S, self.ctx.stream, 0, 0)
+                torch.cuda.synchronize(self.ctx.index)
+                self.fabric.bar.wait()
+            else:
+                for d in range(P):
+                    sweep(d)
+                torch.cuda.synchronize(self.ctx.index)
+                self.fabric.bar.wait()
+                for src in range(P):
+                    b[src * S:(src + 1) * S].copy_(self.fabric.bufs[src]["a"][r * S:(r + 1) * S])
+                torch.cuda.synchronize(self.ctx.index)
+                self.fabric.bar.wait()
             self._swap()
             self.fabric.bufs[r] = {"a": self.a, "b": self.b}
             self.fabric.bar.wait()
@@ -453,6 +489,34 @@ class CudaShardEngine:
 
         order = [(r + s) % P for s in range(1, P)] + [r]
         comm = self.comm
+        if self.transport == "symm" and fuse:
+            # fused sweep + exchange: the last sweep of slice d writes rank d's receive slot directly (peer memory, NVLink);
+            # it runs on the side stream on REMOTE_CTAS SMs while the remaining SMs sweep the next slice
+            import ctypes
+            hb = self.hdl[b.data_ptr()]
+            peers = hb.buffer_ptrs
+            comm_ptr = ctypes.c_void_p(comm.cuda_stream)
+            n_last = max(1, min(self.REMOTE_CTAS, self.n_sms - 1))
+            n_main = self.n_sms - n_last
+            for d in order:
+                src = a.data_ptr() + 16 * d * S
+                rb = (r << g) | d
+                if np_ > 1:
+                    h.run_passes(src, 0, np_ - 1, 1, ws.data_ptr(), wsb, self.ctx.stream, n_ctas=n_main, rank_bits=rb)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                comm.wait_event(ev)
+                dst = (int(peers[d]) if d != r else b.data_ptr()) + 16 * r * S
+                h.run_passes(src, np_ - 1, np_, 1, ws.data_ptr(), wsb, comm_ptr, store_last=dst, n_ctas=n_last, rank_bits=rb)
+                self.passes_weighted += np_ * (1 << nls) / float(1 << self.n_local)
+                self.fused_stores += 1
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                hb.barrier(channel=0)            # every rank's stores into every receive buffer have completed
+            cur.wait_stream(comm)
+            self._swap()
+            return
+
         if self.transport == "symm":
             hb = self.hdl[b.data_ptr()]
             for d in order:

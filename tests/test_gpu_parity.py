@@ -675,7 +675,7 @@ def test_sharded_engine_vs_oracle(world, L, high_bit):
             allred = (lambda a: fabric.all_reduce(rank, a)) if fabric else None
             sv = sharded.ShardedStatevector(L, rank, world, eng, all_reduce=allred)
             r = sv.run(circ, noise, seed=11, trajectory=5)
-            results[rank] = (r, dict(sv.stats), eng.sliced_exchanges)
+            results[rank] = (r, dict(sv.stats), eng.sliced_exchanges, eng.fused_stores)
             eng.close()
         except Exception as exc:                      # surfaces in the main thread; peers fail on the broken barrier
             errors.append(exc)
@@ -696,11 +696,12 @@ def test_sharded_engine_vs_oracle(world, L, high_bit):
     psi = O.run_trajectories(oc, na, O.PauliNoise.depolarizing(0.2), 11, [5])[0]
     idx = np.arange(1 << L)
     want = np.array([np.sum(np.abs(psi) ** 2 * (1 - 2 * ((idx >> q) & 1))) for q in range(L)])
-    for r, stats, n_sliced in results:
+    for r, stats, n_sliced, n_fused in results:
         assert abs(r["norm"] - 1) < 1e-11
         assert np.abs(np.array(r["expect_z"]) - want).max() < AMP_TOL
         if world > 1:
             assert stats["exchanges"] == n_sliced > 0 and stats["exchanges"] <= stats["layers"]
+            assert n_fused > 0          # the last sweep of the slice programs stored straight into the receivers' buffers
 
 
 # ---- resident execution (k_tile_resident): all sweeps of a circuit in one persistent launch over L2-resident groups
