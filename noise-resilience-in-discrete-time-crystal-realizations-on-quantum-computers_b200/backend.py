@@ -581,7 +581,7 @@ class DTCSimulator:
         torch = self.ctx.torch
         ctx = self.ctx
         nm = as_noise_model(self.noise_model if noise_model is None else noise_model)
-        prog = compile_circuit(as_circuit(circuit), nm, optimize=self.optimize)
+        prog = self._compiled(as_circuit(circuit), nm)            # cached per (op list, noise model), like run()
         meas = prog.measures
         k = len(meas)
         if k == 0 or k > MAX_PROB_QUBITS:
@@ -591,11 +591,11 @@ class DTCSimulator:
         per = 16 << prog.n_main
         n = traj_end - traj_begin
         bt = max(1, min(n, (self.max_memory_bytes or int(0.7 * ctx.free_bytes())) // per))
-        state = ctx.empty(bt << prog.n_main, torch.complex128)
+        state = self._state_buffer(bt << prog.n_main)              # one buffer per simulator, reused by every call
         vals = np.zeros(n, dtype=np.int64)
         for a in range(0, n, bt):
             nt = min(bt, n - a)
-            batch = evolve(ctx, prog, nt, traj_begin + a, seed, handle=handle, state=state)
+            batch = evolve(ctx, prog, nt, traj_begin + a, seed, handle=handle, state=state, fused_rdm=True)
             cols = sample_rows(ctx, batch.outcome_probs(), 1, seed, traj_begin + a).cpu().numpy()[:, 0].astype(np.int64)
             v = np.zeros(nt, dtype=np.int64)
             for i in range(k):
