@@ -1262,36 +1262,54 @@ __global__ void k_dm_apply_table(double2* __restrict__ rho, int n, const double2
     rho[i] = cmul(rho[i], cmul(tr, make_double2(tc.x, -tc.y)));
 }
 
+// shared-memory position of tile element e: XOR swizzle of the low three bits, so that the stride-2 / stride-4 / stride-8
+// element patterns of a qubit whose row bit is one of the tile's lowest bits still hit eight different 16 B bank groups
+__device__ __forceinline__ int dm_phys(int e) { return e ^ ((e >> 3) & 7); }
+
 __global__ void __launch_bounds__(DTC_DM_THREADS)
 k_dm_tile(double2* __restrict__ rho, const __grid_constant__ DmTilePass P, const double2* __restrict__ T) {
     extern __shared__ __align__(16) double2 dm_tile[];
+    __shared__ u64 off_hi[16];
     const int tid = threadIdx.x, ne = 1 << P.tile_bits;
     u64 base = 0;
     for (int k = 0; k < P.seg_n; ++k)
         base |= (((u64)blockIdx.x >> P.seg_src[k]) & ((1ull << P.seg_len[k]) - 1)) << P.seg_dst[k];
-    const u64 rmask = (1ull << P.n) - 1;
-    for (int i = tid; i < ne; i += DTC_DM_THREADS) {
-        u64 g = base;
+    // element i = tid + 256 k of the tile: global offset = offset of tid's eight bits (per thread, once) | offset of k's bits
+    u64 off_lo = 0;
 #pragma unroll
-        for (int l = 0; l < 12; ++l)
-            if (l < P.tile_bits && ((i >> l) & 1)) g |= 1ull << P.tb[l];
+    for (int l = 0; l < 8; ++l)
+        if (l < P.tile_bits && ((tid >> l) & 1)) off_lo |= 1ull << P.tb[l];
+    if (tid < 16) {
+        u64 o = 0;
+        for (int l = 8; l < P.tile_bits; ++l)
+            if ((tid >> (l - 8)) & 1) o |= 1ull << P.tb[l];
+        off_hi[tid] = o;
+    }
+    __syncthreads();
+    const u64 rmask = (1ull << P.n) - 1;
+    const int nk = ne > DTC_DM_THREADS ? ne / DTC_DM_THREADS : 1;
+    for (int k = 0; k < nk; ++k) {
+        const int i = tid + DTC_DM_THREADS * k;
+        if (i >= ne) break;
+        const u64 g = base | off_lo | off_hi[k];
         double2 v = rho[g];
         if (P.has_diag) {
             const double2 tr = T[g & rmask], tc = T[g >> P.n];
             v = cmul(v, cmul(tr, make_double2(tc.x, -tc.y)));
         }
-        dm_tile[i] = v;
+        dm_tile[dm_phys(i)] = v;
     }
     __syncthreads();
     for (int k = 0; k < P.nq; ++k) {
         const DmQubitOp& Q = P.q[k];
         const int lowr = (1 << Q.lr) - 1, lowc = (1 << Q.lc) - 1;
+        const double c = Q.c, s = Q.s;
         for (int gidx = tid; gidx < (ne >> 2); gidx += DTC_DM_THREADS) {
             int x = ((gidx & ~lowr) << 1) | (gidx & lowr);          // zero at bit lr
             x = ((x & ~lowc) << 1) | (x & lowc);                    // zero at bit lc (lc > lr)
-            const int i00 = x, i10 = x | (1 << Q.lr), i01 = x | (1 << Q.lc), i11 = i10 | i01;   // i<row bit><column bit>
+            const int i00 = dm_phys(x), i10 = dm_phys(x | (1 << Q.lr)), i01 = dm_phys(x | (1 << Q.lc)),
+                      i11 = dm_phys(x | (1 << Q.lr) | (1 << Q.lc));  // i<row bit><column bit>
             double2 e00 = dm_tile[i00], e10 = dm_tile[i10], e01 = dm_tile[i01], e11 = dm_tile[i11];
-            const double c = Q.c, s = Q.s;
             // rows: [[c, -i s], [-i s, c]] on (r = 0, r = 1) for each column bit
             double2 a00 = make_double2(c * e00.x + s * e10.y, c * e00.y - s * e10.x);
             double2 a10 = make_double2(c * e10.x + s * e00.y, c * e10.y - s * e00.x);
@@ -1310,12 +1328,10 @@ k_dm_tile(double2* __restrict__ rho, const __grid_constant__ DmTilePass P, const
         }
         __syncthreads();
     }
-    for (int i = tid; i < ne; i += DTC_DM_THREADS) {
-        u64 g = base;
-#pragma unroll
-        for (int l = 0; l < 12; ++l)
-            if (l < P.tile_bits && ((i >> l) & 1)) g |= 1ull << P.tb[l];
-        rho[g] = dm_tile[i];
+    for (int k = 0; k < nk; ++k) {
+        const int i = tid + DTC_DM_THREADS * k;
+        if (i >= ne) break;
+        rho[base | off_lo | off_hi[k]] = dm_tile[dm_phys(i)];
     }
 }
 
