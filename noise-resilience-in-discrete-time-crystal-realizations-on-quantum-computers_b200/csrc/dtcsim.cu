@@ -1231,7 +1231,7 @@ struct DmQubitOp {
 };
 struct DmTilePass {
     int n, tile_bits, nq, has_diag;
-    int tb[12];                      // global bit of tile-local bit l
+    int tb[13];                      // global bit of tile-local bit l
     int seg_n, seg_src[8], seg_len[8], seg_dst[8];     // CTA index -> global base (bits outside the tile)
     DmQubitOp q[DTC_DM_MAXQ];
 };
@@ -1266,10 +1266,13 @@ __global__ void k_dm_apply_table(double2* __restrict__ rho, int n, const double2
 // element patterns of a qubit whose row bit is one of the tile's lowest bits still hit eight different 16 B bank groups
 __device__ __forceinline__ int dm_phys(int e) { return e ^ ((e >> 3) & 7); }
 
-__global__ void __launch_bounds__(DTC_DM_THREADS)
+// THREADS = 256 (tiles of <= 2^12 elements, three CTAs per SM) or 512 (2^13 elements = 128 KB, one CTA per SM)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1)
 k_dm_tile(double2* __restrict__ rho, const __grid_constant__ DmTilePass P, const double2* __restrict__ T) {
     extern __shared__ __align__(16) double2 dm_tile[];
-    __shared__ u64 off_hi[16];
+    __shared__ u64 off_hi[32];
+    constexpr int DTC_DM_THREADS_ = THREADS;
     const int tid = threadIdx.x, ne = 1 << P.tile_bits;
     u64 base = 0;
     for (int k = 0; k < P.seg_n; ++k)
@@ -1277,34 +1280,44 @@ k_dm_tile(double2* __restrict__ rho, const __grid_constant__ DmTilePass P, const
     // element i = tid + 256 k of the tile: global offset = offset of tid's eight bits (per thread, once) | offset of k's bits
     u64 off_lo = 0;
 #pragma unroll
-    for (int l = 0; l < 8; ++l)
+    for (int l = 0; l < 9; ++l)
         if (l < P.tile_bits && ((tid >> l) & 1)) off_lo |= 1ull << P.tb[l];
-    if (tid < 16) {
+    constexpr int LB = THREADS == 256 ? 8 : 9;            // element i = tid + THREADS k: tid carries LB bits, k the rest
+    if (tid < 32) {
         u64 o = 0;
-        for (int l = 8; l < P.tile_bits; ++l)
-            if ((tid >> (l - 8)) & 1) o |= 1ull << P.tb[l];
+        for (int l = LB; l < P.tile_bits; ++l)
+            if ((tid >> (l - LB)) & 1) o |= 1ull << P.tb[l];
         off_hi[tid] = o;
     }
     __syncthreads();
     const u64 rmask = (1ull << P.n) - 1;
-    const int nk = ne > DTC_DM_THREADS ? ne / DTC_DM_THREADS : 1;
-    for (int k = 0; k < nk; ++k) {
-        const int i = tid + DTC_DM_THREADS * k;
-        if (i >= ne) break;
-        const u64 g = base | off_lo | off_hi[k];
-        double2 v = rho[g];
+    const int nk = ne > DTC_DM_THREADS_ ? ne / DTC_DM_THREADS_ : 1;
+    {
+        // all of a thread's loads are issued before the first one is used (a rolled loop would pay one HBM latency per element)
+        double2 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < nk && tid + DTC_DM_THREADS_ * k < ne) v[k] = __ldcs(rho + (base | off_lo | off_hi[k]));
         if (P.has_diag) {
-            const double2 tr = T[g & rmask], tc = T[g >> P.n];
-            v = cmul(v, cmul(tr, make_double2(tc.x, -tc.y)));
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (k < nk && tid + DTC_DM_THREADS_ * k < ne) {
+                    const u64 g = base | off_lo | off_hi[k];
+                    const double2 tr = __ldg(T + (g & rmask)), tc = __ldg(T + (g >> P.n));
+                    v[k] = cmul(v[k], cmul(tr, make_double2(tc.x, -tc.y)));
+                }
         }
-        dm_tile[dm_phys(i)] = v;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < nk && tid + DTC_DM_THREADS_ * k < ne) dm_tile[dm_phys(tid + DTC_DM_THREADS_ * k)] = v[k];
     }
     __syncthreads();
     for (int k = 0; k < P.nq; ++k) {
         const DmQubitOp& Q = P.q[k];
         const int lowr = (1 << Q.lr) - 1, lowc = (1 << Q.lc) - 1;
         const double c = Q.c, s = Q.s;
-        for (int gidx = tid; gidx < (ne >> 2); gidx += DTC_DM_THREADS) {
+#pragma unroll 4
+        for (int gidx = tid; gidx < (ne >> 2); gidx += DTC_DM_THREADS_) {
             int x = ((gidx & ~lowr) << 1) | (gidx & lowr);          // zero at bit lr
             x = ((x & ~lowc) << 1) | (x & lowc);                    // zero at bit lc (lc > lr)
             const int i00 = dm_phys(x), i10 = dm_phys(x | (1 << Q.lr)), i01 = dm_phys(x | (1 << Q.lc)),
@@ -1328,11 +1341,9 @@ k_dm_tile(double2* __restrict__ rho, const __grid_constant__ DmTilePass P, const
         }
         __syncthreads();
     }
-    for (int k = 0; k < nk; ++k) {
-        const int i = tid + DTC_DM_THREADS * k;
-        if (i >= ne) break;
-        rho[base | off_lo | off_hi[k]] = dm_tile[dm_phys(i)];
-    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (k < nk && tid + DTC_DM_THREADS_ * k < ne) __stcs(rho + (base | off_lo | off_hi[k]), dm_tile[dm_phys(tid + DTC_DM_THREADS_ * k)]);
 }
 
 __global__ void k_dm_probs(const double2* __restrict__ rho, int n, int k, const int* __restrict__ qubits,
@@ -2236,7 +2247,8 @@ int dtc_dm_run(void* rho, int n, int n_seg, const int32_t* seg_type, const int32
         int dev = 0;
         CUDA_TRY(cudaGetDevice(&dev));
         if (dev >= 0 && dev < DTC_MAX_DEVICES && !attr_set[dev]) {
-            CUDA_TRY(cudaFuncSetAttribute(k_dm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
+            CUDA_TRY(cudaFuncSetAttribute(k_dm_tile<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
+            CUDA_TRY(cudaFuncSetAttribute(k_dm_tile<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 13));
             attr_set[dev] = true;
         }
     }
@@ -2307,33 +2319,31 @@ int dtc_dm_run(void* rho, int n, int n_seg, const int32_t* seg_type, const int32
             DmTilePass P;
             memset(&P, 0, sizeof(P));
             P.n = n;
-            P.tile_bits = TB;
-            const bool low_pair = (todo[pos] == 0 && pos + 1 < nt && todo[pos + 1] == 1) || 2 * n <= 12;
-            const int passive = low_pair ? 0 : (TB >= 4 ? 2 : 0);           // row bits {0,1}: 64 B runs
-            int cap = (TB - passive) / 2;
+            // a group that holds qubit 0 (or a register that fits one tile): up to six qubits in a 2^12 tile, row bit 0 among
+            // them; any other group: row bit 0 as a passive bit (32 B runs = whole sectors) + up to six qubits in a 2^13 tile
+            // (DTCSIM_DM_TILE13=0: 2^12 tiles without a passive bit for those groups -- 16 B runs, measured 9 % slower on C3)
+            static const bool wide13 = []() { const char* e = getenv("DTCSIM_DM_TILE13"); return !(e && atoi(e) == 0); }();
+            const bool low_group = todo[pos] == 0 || 2 * n <= 12 || !wide13;
+            const int passive = low_group ? 0 : 1;
+            const int TBg = low_group ? TB : ((2 * n < 13) ? 2 * n : 13);
+            P.tile_bits = TBg;
+            int cap = (TBg - passive) / 2;
             if (cap > DTC_DM_MAXQ) cap = DTC_DM_MAXQ;
             int grp[DTC_DM_MAXQ], ng = 0;
-            while (pos < nt && ng < cap) {
-                if (passive && todo[pos] < 2) {              // qubit 0 or 1 without its partner: it takes a pass of its own kind
-                    if (ng) break;
-                    grp[ng++] = todo[pos++];
-                    break;
-                }
-                grp[ng++] = todo[pos++];
-            }
+            while (pos < nt && ng < cap) grp[ng++] = todo[pos++];
             // tile bits: passive row bits (unless they belong to a qubit of the group), then row bits, then column bits, ascending;
             // spare positions are filled with the lowest unused row bits (they ride along untouched)
             u64 used = 0;
             for (int k = 0; k < ng; ++k) used |= (1ull << grp[k]) | (1ull << (grp[k] + n));
-            if (passive) used |= 3ull;
-            for (int b = 0; b < 2 * n && dtc_popc(used) < TB; ++b) used |= 1ull << b;
+            if (passive) used |= 1ull;
+            for (int b = 0; b < 2 * n && dtc_popc(used) < TBg; ++b) used |= 1ull << b;
             int l = 0;
             for (int b = 0; b < 2 * n; ++b)
                 if ((used >> b) & 1ull) P.tb[l++] = b;
             P.nq = ng;
             for (int k = 0; k < ng; ++k) {
                 DmQubitOp& Q = P.q[k];
-                for (int m = 0; m < TB; ++m) {
+                for (int m = 0; m < TBg; ++m) {
                     if (P.tb[m] == grp[k]) Q.lr = m;
                     if (P.tb[m] == grp[k] + n) Q.lc = m;
                 }
@@ -2353,7 +2363,8 @@ int dtc_dm_run(void* rho, int n, int n_seg, const int32_t* seg_type, const int32
             }
             P.has_diag = diag_pending ? 1 : 0;
             diag_pending = false;
-            k_dm_tile<<<1u << (2 * n - TB), DTC_DM_THREADS, sizeof(double2) << TB, s>>>((double2*)rho, P, T);
+            if (TBg <= 12) k_dm_tile<256><<<1u << (2 * n - TBg), 256, sizeof(double2) << TBg, s>>>((double2*)rho, P, T);
+            else k_dm_tile<512><<<1u << (2 * n - TBg), 512, sizeof(double2) << TBg, s>>>((double2*)rho, P, T);
             ++sweeps;
         }
     }
