@@ -233,11 +233,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef DTC_TRYWAIT_HINT
+#define DTC_TRYWAIT_HINT 0      // suspend-time hint (ns) of the try_wait loops; 0: the hardware default
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    while (!done)
+    while (!done) {
+#if DTC_TRYWAIT_HINT > 0
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"((uint32_t)DTC_TRYWAIT_HINT) : "memory");
+#else
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#endif
+    }
 }
 __device__ __forceinline__ void wg_barrier(int wg) {
     if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");

@@ -17,7 +17,7 @@ from .ir import QuantumCircuit
 from .lowering import SNAKE_LAYOUT, lower_level0
 
 PI = math.pi
-POLARIZATIONS = ("x", "y", "xy", "yx", "circular_left", "circular_right", "circular_static")
+POLARIZATIONS = ("x", "y", "xy", "yx", "circular_left", "circular_right", "circular_static", "xy_cycle")
 G_GRID = (0.5, 0.55, 0.6, 0.65, 0.7, 0.75, 0.8, 0.85, 0.9, 0.95, 1.0)      # generate_params.py:6
 
 
@@ -72,6 +72,9 @@ def autocorr_circuit(L, g, hs, phis, t, qubit=None, echo=False, polarization="x"
         raise ValueError(f"unknown initial state {initial_state!r}")
     circ.h(0)
     circ.cz(qubit + 1, 0)
+
+    if polarization == "xy_cycle" and pol_schedule is None:        # xy-cycle.py:144-156 as a named polarisation
+        pol_schedule = xy_cycle_schedule()
 
     def period(step):
         gg = g if g_values is None else g_values[step]
