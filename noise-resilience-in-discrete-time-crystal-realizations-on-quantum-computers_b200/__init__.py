@@ -7,7 +7,7 @@ the C ABI in ``include/dtcsim.h``; PyTorch only allocates device buffers and pro
 """
 from .ir import QuantumCircuit, Op, from_qasm2, from_qiskit, as_circuit          # noqa: F401
 from .lowering import generate_preset_pass_manager, lower_level0, SNAKE_LAYOUT   # noqa: F401
-from .noise import NoiseModel, depolarizing_error, pauli_error, as_noise_model   # noqa: F401
+from .noise import NoiseModel, ReadoutError, depolarizing_error, pauli_error, as_noise_model   # noqa: F401
 from .plan import compile_circuit, Program                                       # noqa: F401
 from .sweeps import autocorr_circuit, floquet_period, run_sweep, xy_cycle_schedule  # noqa: F401
 from .estimator import BackendEstimatorV2, dtc_hamiltonian                        # noqa: F401

@@ -24,6 +24,7 @@ from . import capi
 from .ir import as_circuit
 from .noise import as_noise_model
 from .plan import compile_circuit
+from . import philox_np
 
 MAX_DM_QUBITS = 13
 MAX_PROB_QUBITS = 12
@@ -413,9 +414,19 @@ class DTCSimulator:
         t0 = time.time()
         torch = self.ctx.torch
         ctx = self.ctx
+        full_nm = nm
+        if nm is not None and not nm.has_gate_noise():
+            nm = None                      # readout errors only: the evolution is ideal, the recorded bits are not
         prog0 = self._compiled(circ, nm)
         n = prog0.n
         method = self._choose_method(method, n, shots, nm)
+        # classical readout errors (device-calibrated noise, fast.py:77-78): assignment matrix per classical bit
+        readout = {}
+        if full_nm is not None and full_nm.has_readout_noise():
+            for c, q in prog0.measure_orig.items():
+                m = full_nm.lookup_readout(q)
+                if m is not None:
+                    readout[int(c)] = m
         meas = prog0.measures
         if not meas:
             raise ValueError("circuit has no measurements: nothing to count")
@@ -446,7 +457,7 @@ class DTCSimulator:
             cols = sample_rows(ctx, probs.view(1, -1), shots, seed, 0).cpu().numpy()[0]
             p_host = probs.cpu().numpy()
             data["probabilities"] = self._clbit_probs(p_host, to_clbits, prog0.n_clbits)
-            vals = to_clbits(cols)
+            vals = self._readout_flips(to_clbits(cols), readout, seed, np.arange(shots))
         elif nm is None:
             batch = evolve(ctx, prog0, 1, 0, seed, self.engine)
             data["num_passes"] = batch.handle.num_passes
@@ -463,7 +474,7 @@ class DTCSimulator:
                 probs = batch.outcome_probs()
                 cols = sample_rows(ctx, probs, shots, seed, 0).cpu().numpy()[0]
                 data["probabilities"] = self._clbit_probs(probs.cpu().numpy()[0], to_clbits, prog0.n_clbits)
-            vals = to_clbits(cols)
+            vals = self._readout_flips(to_clbits(cols), readout, seed, np.arange(shots))
         else:
             handle = capi.ProgramHandle(prog0, ctx.index, self.engine)
             handles.append(handle)
@@ -512,17 +523,17 @@ class DTCSimulator:
                             cols = np.zeros(nt, dtype=np.int64)
                             for i, q in enumerate(mq):
                                 cols |= ((idx >> q) & 1) << i
-                        vals[a:a + nt] = to_clbits(cols)
+                        vals[a:a + nt] = self._readout_flips(to_clbits(cols), readout, seed, np.arange(a, a + nt))
                 if psum is not None:
                     data["probabilities"] = self._clbit_probs(psum / shots, to_clbits, prog0.n_clbits)
                 if ez_sum is not None:
                     with torch.cuda.stream(side):
                         ez = ez_sum.cpu().numpy() / shots
                     data["expval_z_by_clbit"] = {int(c): float(ez[q]) for q, c in meas}
-                return self._experiment(vals, data, prog0, name or circ.name, shots, seed, t0)
+                return self._experiment(vals, data, prog0, name or circ.name, shots, seed, t0, readout)
 
             return finish
-        return self._experiment(vals, data, prog0, name or circ.name, shots, seed, t0)
+        return self._experiment(vals, data, prog0, name or circ.name, shots, seed, t0, readout)
 
     def _compiled(self, circ, nm, want_dm=False):
         """compile_circuit() with a small cache keyed by the circuit's op list and the noise model: sweeps that run the
@@ -558,11 +569,44 @@ class DTCSimulator:
         return self._side
 
     @staticmethod
-    def _experiment(vals, data, prog0, name, shots, seed, t0):
+    def _readout_flips(vals, readout, seed, shot_ids):
+        """Recorded classical-register values: bit c of shot s flips with P(recorded != true) of its assignment matrix;
+        u = philox(seed; index = c, stream 2, trajectory word = shot id) (the test-side restatement draws the same stream)."""
+        if not readout:
+            return vals
+        vals = np.array(vals, dtype=np.int64, copy=True)
+        for c, m in readout.items():
+            u = philox_np.uniform(seed, c, philox_np.STREAM_READOUT, np.asarray(shot_ids, dtype=np.uint64))
+            bit = (vals >> c) & 1
+            flip = np.where(bit == 0, u < m[0][1], u < m[1][0])
+            vals ^= flip.astype(np.int64) << c
+        return vals
+
+    @staticmethod
+    def _readout_probs(pr, readout):
+        """Exact distribution of the RECORDED register: every classical bit mixed by its assignment matrix."""
+        for c, m in readout.items():
+            new = {}
+            for v, p in pr.items():
+                b = (v >> c) & 1
+                new[v] = new.get(v, 0.0) + p * m[b][b]
+                new[v ^ (1 << c)] = new.get(v ^ (1 << c), 0.0) + p * m[b][1 - b]
+            pr = new
+        return pr
+
+    @staticmethod
+    def _experiment(vals, data, prog0, name, shots, seed, t0, readout=None):
         counts = {}
         uniq, cnt = np.unique(vals, return_counts=True)
         for v, c in zip(uniq, cnt):
             counts[format(int(v), f"0{prog0.n_clbits}b")] = int(c)
+        if readout and "probabilities" in data:
+            data["probabilities"] = DTCSimulator._readout_probs(data["probabilities"], readout)
+        if readout and "expval_z_by_clbit" in data:
+            for c, m in readout.items():
+                if c in data["expval_z_by_clbit"]:
+                    p0 = 0.5 * (1.0 + data["expval_z_by_clbit"][c])
+                    data["expval_z_by_clbit"][c] = (p0 * m[0][0] + (1 - p0) * m[1][0]) - (p0 * m[0][1] + (1 - p0) * m[1][1])
         if "probabilities" in data:
             pr = data["probabilities"]
             data["expval_z"] = [sum(p * (1 - 2 * ((v >> c) & 1)) for v, p in pr.items())
@@ -581,7 +625,13 @@ class DTCSimulator:
         torch = self.ctx.torch
         ctx = self.ctx
         nm = as_noise_model(self.noise_model if noise_model is None else noise_model)
+        full_nm = nm
+        if nm is not None and not nm.has_gate_noise():
+            nm = None
         prog = self._compiled(as_circuit(circuit), nm)            # cached per (op list, noise model), like run()
+        readout = {}
+        if full_nm is not None and full_nm.has_readout_noise():
+            readout = {int(c): m for c, m in ((c, full_nm.lookup_readout(q)) for c, q in prog.measure_orig.items()) if m is not None}
         meas = prog.measures
         k = len(meas)
         if k == 0 or k > MAX_PROB_QUBITS:
@@ -600,7 +650,7 @@ class DTCSimulator:
             v = np.zeros(nt, dtype=np.int64)
             for i in range(k):
                 v |= ((cols >> i) & 1) << cbits[i]
-            vals[a:a + nt] = v
+            vals[a:a + nt] = self._readout_flips(v, readout, seed, np.arange(traj_begin + a, traj_begin + a + nt))
         handle.close()
         return vals
 

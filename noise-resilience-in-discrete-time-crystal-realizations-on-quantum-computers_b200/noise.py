@@ -2,10 +2,10 @@
 
 Mirrors the two qiskit-aer entry points the reference uses -- ``depolarizing_error(p, 1)`` and
 ``NoiseModel().add_all_qubit_quantum_error(error, ["u1","u2","u3"])`` -- and adapts a *real*
-qiskit-aer ``NoiseModel`` through its ``to_dict()`` form.  Only single-qubit Pauli channels are
-representable (that is all the simulator path of the reference uses; device-calibrated noise from
-``NoiseModel.from_backend`` is SURVEY.md 8f-4 "next"); anything else raises ``ValueError`` -- there
-is no silent fallback.
+qiskit-aer ``NoiseModel`` through its ``to_dict()`` form.  Representable: single-qubit Pauli channels after
+gates (all the simulator path of the reference uses) and single-qubit readout errors (the classical part of
+device-calibrated noise, ``NoiseModel.from_backend``, fast.py:77-78 / SURVEY.md 8f-4); thermal-relaxation and other
+non-Pauli channels raise ``ValueError`` -- there is no silent fallback.
 """
 
 
@@ -39,6 +39,22 @@ class PauliError:
         return self.px == 0 and self.py == 0 and self.pz == 0
 
 
+class ReadoutError:
+    """qiskit_aer.noise.ReadoutError for one qubit: probabilities[i][j] = P(recorded j | true outcome i)."""
+
+    def __init__(self, probabilities):
+        m = [[float(x) for x in row] for row in probabilities]
+        if len(m) != 2 or any(len(r) != 2 for r in m):
+            raise ValueError("only single-qubit readout errors (2 x 2 assignment matrices) are supported")
+        for r in m:
+            if min(r) < 0 or abs(sum(r) - 1.0) > 1e-9:
+                raise ValueError("rows of a readout assignment matrix must be probability vectors")
+        self.probabilities = m
+
+    def is_ideal(self):
+        return self.probabilities[0][1] == 0.0 and self.probabilities[1][0] == 0.0
+
+
 def depolarizing_error(param, num_qubits=1):
     """qiskit_aer.noise.depolarizing_error: rho -> (1-p) rho + p I/2 (fast.py:85)."""
     if num_qubits != 1:
@@ -64,6 +80,8 @@ class NoiseModel:
     def __init__(self, basis_gates=None):
         self._all = {}        # gate name -> PauliError
         self._local = {}      # (gate name, qubit) -> PauliError
+        self._ro_all = None   # ReadoutError on every measured qubit
+        self._ro_local = {}   # qubit -> ReadoutError
         self.basis_gates = list(basis_gates or ["cx", "id", "rz", "sx"])
 
     def add_all_qubit_quantum_error(self, error, instructions, warnings=True):
@@ -83,9 +101,29 @@ class NoiseModel:
             key = (nm, int(q))
             self._local[key] = self._local[key].compose(error) if key in self._local else error
 
+    def add_all_qubit_readout_error(self, error, warnings=True):
+        self._ro_all = error if isinstance(error, ReadoutError) else ReadoutError(error)
+
+    def add_readout_error(self, error, qubits, warnings=True):
+        (q,) = tuple(qubits)
+        self._ro_local[int(q)] = error if isinstance(error, ReadoutError) else ReadoutError(error)
+
+    def has_gate_noise(self):
+        return not (all(e.is_ideal() for e in self._all.values()) and all(e.is_ideal() for e in self._local.values()))
+
+    def has_readout_noise(self):
+        return (self._ro_all is not None and not self._ro_all.is_ideal()) or \
+            any(not e.is_ideal() for e in self._ro_local.values())
+
     def is_ideal(self):
-        return all(e.is_ideal() for e in self._all.values()) and \
-            all(e.is_ideal() for e in self._local.values())
+        return not self.has_gate_noise() and not self.has_readout_noise()
+
+    def lookup_readout(self, qubit):
+        """2 x 2 assignment matrix P(recorded | true) of the measurement of `qubit`, or None."""
+        e = self._ro_local.get(int(qubit), self._ro_all)
+        if e is None or e.is_ideal():
+            return None
+        return e.probabilities
 
     def lookup(self, name, qubit):
         """Pauli probabilities (px,py,pz) applied after gate `name` on `qubit`, or None."""
@@ -107,8 +145,17 @@ _PAULI_NAMES = {"id": "I", "x": "X", "y": "Y", "z": "Z"}
 def _from_dict(d):
     nm = NoiseModel()
     for err in d.get("errors", []):
+        if err.get("type", "qerror") == "roerror":
+            ro = ReadoutError(err["probabilities"])
+            gate_qubits = err.get("gate_qubits")
+            if gate_qubits:
+                for gq in gate_qubits:
+                    nm.add_readout_error(ro, gq)
+            else:
+                nm.add_all_qubit_readout_error(ro)
+            continue
         if err.get("type", "qerror") != "qerror":
-            raise ValueError(f"unsupported noise entry type {err.get('type')!r} (readout errors are 8f-4)")
+            raise ValueError(f"unsupported noise entry type {err.get('type')!r}")
         acc = {"I": 0.0, "X": 0.0, "Y": 0.0, "Z": 0.0}
         for circ, p in zip(err["instructions"], err["probabilities"]):
             label = "I"

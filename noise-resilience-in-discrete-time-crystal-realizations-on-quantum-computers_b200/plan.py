@@ -79,6 +79,7 @@ class Program:
         self.ev_probs = []          # NOISE: (px, py, pz); zeros otherwise
         self.global_phase = 0.0     # psi_true carries e^{+i global_phase}
         self.measures = []          # (simulated qubit, clbit)
+        self.measure_orig = {}      # clbit -> index of the measured qubit in the (wide) input circuit: noise-model key
         self.n_sites = 0
         self.dm_segments = []       # ordered segments for the density-matrix engine
         self.rot_layers = 0         # number of non-empty rotation layers (for accounting)
@@ -577,6 +578,7 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True, opti
     prog.n_layers = prog.n_exec_layers + n_small_layers
     prog.rot_layers = len({prog.ev_layer[e] for e in main.events if prog.ev_type[e] == EV_ROT})
     prog.measures = sorted(((bit_of[q], c) for c, q in measured.items()), key=lambda qc: qc[1])
+    prog.measure_orig = {c: used[q] for c, q in measured.items()}
     if plan:
         prog.small = dict(events=sorted(small.events), elim_bits=sorted(bit_of[q] for q in elim),
                           reg_bits=sorted(bit_of[q] for q in plan[1]), first_layer=prog.n_exec_layers,

@@ -313,7 +313,19 @@ def counts_dict(values, n_clbits):
     return c
 
 
-def run_counts(ops, n_qubits, n_clbits, shots=1024, noise=None, seed=1234, method="automatic"):
+def apply_readout(vals, readout, seed, shot_ids):
+    """Classical readout errors (qiskit-aer ReadoutError semantics: readout[c][i][j] = P(recorded j | true i) for classical
+    bit c): bit c of shot s flips when u = philox.uniform(seed, c, STREAM_READOUT, s) falls below its flip probability."""
+    vals = np.array(vals, dtype=np.int64, copy=True)
+    for c, m in (readout or {}).items():
+        u = philox.uniform(seed, c, philox.STREAM_READOUT, np.asarray(shot_ids, dtype=np.uint64))
+        bit = (vals >> c) & 1
+        flip = np.where(bit == 0, u < m[0][1], u < m[1][0])
+        vals ^= flip.astype(np.int64) << c
+    return vals
+
+
+def run_counts(ops, n_qubits, n_clbits, shots=1024, noise=None, seed=1234, method="automatic", readout=None):
     """Full restatement of backend.run(circ, shots).result().get_counts() (fast.py:211-212).
 
     Returns (counts, info) with info = {method, probabilities (DM / noiseless) or per-trajectory p}.
@@ -329,13 +341,13 @@ def run_counts(ops, n_qubits, n_clbits, shots=1024, noise=None, seed=1234, metho
         rho = run_density_matrix(ops_c, n, noise if noisy else None)
         probs = outcome_probabilities(np.real(np.diag(rho)).copy(), n, meas, n_clbits)
         u = philox.uniform(seed, np.arange(shots), philox.STREAM_MEASURE, 0)
-        vals = sample_outcome(np.cumsum(probs), u)
+        vals = apply_readout(sample_outcome(np.cumsum(probs), u), readout, seed, np.arange(shots))
         return counts_dict(vals, n_clbits), {"method": method, "probabilities": probs}
     if not noisy:
         psi = run_statevector(ops_c, n)
         probs = outcome_probabilities(np.abs(psi) ** 2, n, meas, n_clbits)
         u = philox.uniform(seed, np.arange(shots), philox.STREAM_MEASURE, 0)
-        vals = sample_outcome(np.cumsum(probs), u)
+        vals = apply_readout(sample_outcome(np.cumsum(probs), u), readout, seed, np.arange(shots))
         return counts_dict(vals, n_clbits), {"method": method, "probabilities": probs}
     trajs = np.arange(shots, dtype=np.uint64)
     vals = np.zeros(shots, dtype=np.int64)
@@ -349,6 +361,7 @@ def run_counts(ops, n_qubits, n_clbits, shots=1024, noise=None, seed=1234, metho
         u = philox.uniform(seed, 0, philox.STREAM_MEASURE, tr)
         for r in range(len(tr)):
             vals[a + r] = sample_outcome(np.cumsum(probs[r]), u[r])
+    vals = apply_readout(vals, readout, seed, np.arange(shots))
     return counts_dict(vals, n_clbits), {"method": method, "trajectory_probabilities": ptraj}
 
 

@@ -26,6 +26,7 @@ _MASK = np.uint64(0xFFFFFFFF)
 
 STREAM_NOISE = 0
 STREAM_MEASURE = 1
+STREAM_READOUT = 2      # readout-error flip of classical bit `index` of shot `traj`
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

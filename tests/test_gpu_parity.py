@@ -769,3 +769,36 @@ def test_run_sweep_equals_per_point_oracle(disorder):
         want, _ = O.run_counts(C.lower_level0(ops, C.SNAKE_LAYOUT), 31, 1, shots=64, noise=onoise, seed=500 + k)
         assert abs(res["autocorr"][pts[k]] - O.compute_z_expectation(want, 1)[0]) < 1e-12, k
     assert np.allclose(res["mean"], res["autocorr"].mean(axis=3))
+
+
+def test_readout_errors_counts_vs_oracle(disorder):
+    """Classical readout errors (the part of device-calibrated noise, fast.py:77-78, that is not a channel on the state):
+    counts bit-identical to the oracle under the shared Philox contract on all three execution paths (density matrix,
+    trajectories, ideal multi-clbit), and the reported probabilities are the assignment matrix applied to the exact ones."""
+    M = [[0.97, 0.03], [0.08, 0.92]]
+    hs, phis = disorder[4][0][0], disorder[4][1][0]
+    nm = RC.noise_model(0.05)
+    nm.add_all_qubit_readout_error(dtcsim.ReadoutError(M))
+    sim = dtcsim.AerSimulator(noise_model=nm, device="GPU", cuStateVec_enable=True)
+    onoise = O.PauliNoise.depolarizing(0.05)
+    for t, echo, shots in ((2, False, 1024), (3, True, 24)):          # density matrix / trajectories
+        circ = RC.transpiled(RC.qc_body("vacuum", 4, 0.84, hs, phis, t, 2, echo), backend=sim)
+        res = sim.run(circ, shots=shots, seed_simulator=77).result()
+        want, info = O.run_counts(RC.ops_of(circ), 31, 1, shots=shots, noise=onoise, seed=77, readout={0: M})
+        assert res.get_counts() == want, (t, echo, res.get_counts(), want)
+        if "probabilities" in info:
+            p0, p1 = info["probabilities"]
+            assert abs(res.data()["probabilities"][0] - (p0 * M[0][0] + p1 * M[1][0])) < 1e-9
+    # readout error only (no gate noise): ideal evolution, flipped records; per-qubit matrices on a measure-all circuit
+    ops, n, nc = C.dtc_qasm_gates("1", 6, 0.94, disorder[20][0][0][:6], disorder[20][1][0][:5], 2)
+    circ = dtcsim.QuantumCircuit(6, 6)
+    for nm_, qs, ps, cs in ops:
+        circ._add(nm_, qs, ps, cs)
+    ro = dtcsim.NoiseModel()
+    ro.add_readout_error(M, [1])
+    ro.add_readout_error([[0.9, 0.1], [0.25, 0.75]], [4])
+    res = dtcsim.AerSimulator(noise_model=ro).run(circ, shots=2000, seed_simulator=5).result()
+    assert res.data()["method"] == "statevector"
+    want, _ = O.run_counts(ops, 6, 6, shots=2000, noise=None, seed=5, readout={1: M, 4: [[0.9, 0.1], [0.25, 0.75]]})
+    assert res.get_counts() == want
+    assert abs(sum(res.data()["probabilities"].values()) - 1) < 1e-12

@@ -192,8 +192,11 @@ def test_noise_model_from_qiskit_dict():
                       "probabilities": [0.3, 0.7]}]}
     nm2 = dtcsim.as_noise_model(d2)
     assert nm2.lookup("u3", 2) == (0.3, 0.0, 0.0) and nm2.lookup("u3", 1) is None
+    # an identity readout error is an ideal model; thermal-relaxation-like (non-Pauli) entries still raise
+    assert dtcsim.as_noise_model({"errors": [{"type": "roerror", "operations": ["measure"], "probabilities": [[1, 0], [0, 1]]}]}) is None
     with pytest.raises(ValueError):
-        dtcsim.as_noise_model({"errors": [{"type": "roerror", "operations": ["measure"], "probabilities": [[1, 0], [0, 1]]}]})
+        dtcsim.as_noise_model({"errors": [{"type": "qerror", "operations": ["u3"], "probabilities": [1.0],
+                                           "instructions": [[{"name": "kraus", "qubits": [0], "params": []}]]}]})
     assert dtcsim.as_noise_model(dtcsim.NoiseModel()) is None
     # composing errors on the same instruction (energy.py:214-218 loop)
     nm3 = dtcsim.NoiseModel()
@@ -283,3 +286,35 @@ def test_backend_program_cache(disorder):
     assert sim._compiled(dtcsim.as_circuit(c1), nm2) is not p1
     assert sim._compiled(dtcsim.as_circuit(c1), None) is not p1
     assert len(sim._prog_cache) == 4
+
+
+def test_readout_error_model_and_host_philox():
+    """Readout errors (fast.py:77-78 device-calibrated noise, classical part): parsing, lookup, host Philox == oracle Philox."""
+    import dtcsim
+    from dtcsim import noise as N
+    from dtcsim import philox_np
+    from oracle import philox
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_readout_error(dtcsim.ReadoutError([[0.97, 0.03], [0.08, 0.92]]))
+    nm.add_readout_error([[0.9, 0.1], [0.2, 0.8]], [5])
+    assert nm.has_readout_noise() and not nm.has_gate_noise() and not nm.is_ideal()
+    assert nm.lookup_readout(5) == [[0.9, 0.1], [0.2, 0.8]] and nm.lookup_readout(0)[1][0] == 0.08
+    d = {"errors": [{"type": "roerror", "operations": ["measure"], "probabilities": [[0.99, 0.01], [0.05, 0.95]],
+                     "gate_qubits": [[3]]},
+                    {"type": "qerror", "operations": ["u3"], "instructions": [[{"name": "x", "qubits": [0]}], [{"name": "id", "qubits": [0]}]],
+                     "probabilities": [0.1, 0.9]}]}
+    nm2 = N.as_noise_model(d)
+    assert nm2.lookup_readout(3) == [[0.99, 0.01], [0.05, 0.95]] and nm2.lookup_readout(2) is None and nm2.has_gate_noise()
+    with pytest.raises(ValueError):
+        dtcsim.ReadoutError([[0.5, 0.6], [0.1, 0.9]])
+    idx = np.array([0, 1, 7, 2 ** 31 + 5])
+    traj = np.array([0, 3, 2 ** 33 + 1, 9])
+    for seed in (0, 1234, 2 ** 40 + 3):
+        assert np.array_equal(philox_np.uniform(seed, idx, 2, traj), philox.uniform(seed, idx, 2, traj))
+    # flips: deterministic under the contract, and the recorded distribution is the assignment matrix applied to the true one
+    from dtcsim.backend import DTCSimulator
+    vals = np.zeros(200000, dtype=np.int64)
+    rec = DTCSimulator._readout_flips(vals, {0: [[0.97, 0.03], [0.08, 0.92]], 2: [[0.5, 0.5], [0.0, 1.0]]}, 9, np.arange(200000))
+    assert abs(((rec >> 0) & 1).mean() - 0.03) < 0.002 and abs(((rec >> 2) & 1).mean() - 0.5) < 0.005 and ((rec >> 1) & 1).sum() == 0
+    pr = DTCSimulator._readout_probs({0: 0.25, 1: 0.75}, {0: [[0.97, 0.03], [0.08, 0.92]]})
+    assert abs(pr[0] - (0.25 * 0.97 + 0.75 * 0.08)) < 1e-15 and abs(pr[0] + pr[1] - 1) < 1e-15
