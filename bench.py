@@ -525,6 +525,7 @@ def run_ours(args):
     launches[0] = 0
     resident[0] = 0
     pass_ms, pass_n, half_passes, n_timed_launches = 0.0, 0, 0, 0
+    by_mode = {}
     e0.record()
     for k in range(args.steps):
         step(1234 + k)
@@ -537,6 +538,13 @@ def run_ours(args):
             pass_ms += ms
             pass_n += n
             n_timed_launches += 1 if h.last_run_info()[0] else n
+            if not h.last_run_info()[0]:
+                pt = h.pass_times()
+                for j, (pms, mode) in enumerate(pt):
+                    if 0 < j < len(pt) - 1:                 # full-traffic sweeps only (not the generated first / fused last one)
+                        by_mode.setdefault(mode, [0.0, 0])
+                        by_mode[mode][0] += pms
+                        by_mode[mode][1] += 1
             half_passes += sum(h.last_run_flags())        # passes that only write (generated start) or only read (fused read-out)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
@@ -586,6 +594,10 @@ def run_ours(args):
                               "traffic for the DRAM bytes actually moved)") if is_resident else "one launch per sweep, batch streamed through HBM",
                 "algorithmic_bytes_timed": alg_bytes, "peak_source": peak_src,
                 "register_qubits": nmax, "traffic_source": traffic_src,
+                "by_tile_layout": {{1: "contiguous_64KB_tiles", 2: "runs_of_64B", 3: "runs_of_2KB", 0: "register_fed"}.get(m, str(m)):
+                                   {"launches": v[1], "avg_launch_ms": v[0] / v[1],
+                                    "gbs": bytes_per_launch / (v[0] / v[1] * 1e-3) / 1e9, "frac": bytes_per_launch / (v[0] / v[1] * 1e-3) / 1e9 / peak}
+                                   for m, v in sorted(by_mode.items()) if v[1]},
                 "periods_frac_actual_register": (value / world) * (2 * 16 * (1 << nmax)) / (peak * 1e9)}
 
     # ---- end to end through the public API (host circuits in, counts out)

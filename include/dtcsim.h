@@ -132,6 +132,9 @@ int dtc_program_set_profiling(dtc_program *p, int enable);
  * of storing (read the batch, wrote nothing). */
 int dtc_program_last_run_flags(const dtc_program *p, int *gen_first, int *fused_rdm);
 int dtc_program_pass_time(dtc_program *p, float *ms, int *n_launches);
+/* Per-pass durations of the last whole-program run with profiling on: ms[i], and modes[i] = tile layout of pass i
+ * (1 contiguous 64 KB tiles, 2 runs of 64 B, 3 runs of 2 KB, 0 register-fed kernel); *n_passes = passes in that run. */
+int dtc_program_pass_times(dtc_program *p, float *ms, int *modes, int cap, int *n_passes);
 
 /* Read-out of a factorised circuit (the Hadamard-test ancilla kept out of the register; replaces the measure
  * sampling input of AerSimulator.run(), fast.py:211).  set_readout() (once, after finalize): the indices of the

@@ -55,6 +55,8 @@ _SIGS = {
     "dtc_program_last_run_flags": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "dtc_program_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "dtc_program_pass_time": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
+    "dtc_program_pass_times": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                              ctypes.POINTER(ctypes.c_int)]),
     "dtc_materialize": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dtc_probs": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_i32p, c_vp, c_vp, c_vp]),
     "dtc_rdm": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_i32p, c_vp, c_vp]),
@@ -258,6 +260,15 @@ class ProgramHandle:
         ms, n = ctypes.c_float(0), ctypes.c_int(0)
         check(load().dtc_program_pass_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def pass_times(self):
+        """[(milliseconds, tile layout mode)] per pass of the last whole-program run (profiling on; waits for it)."""
+        cap = 4096
+        ms = (ctypes.c_float * cap)()
+        modes = (ctypes.c_int * cap)()
+        n = ctypes.c_int(0)
+        check(load().dtc_program_pass_times(self._h, ms, modes, cap, ctypes.byref(n)))
+        return [(ms[i], modes[i]) for i in range(min(n.value, cap))]
 
     def last_run_flags(self):
         """(first pass generated the state, last pass fused the read-out) of the last run()."""

@@ -18,6 +18,7 @@
 
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/dtcsim.h"
 #include "dtc_core.hpp"
@@ -117,6 +118,8 @@ struct dtc_program {
     int fused_local_bit = -1;            // tile-local position of the read-out qubit in the last pass (-1: not fusable)
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> pass_ev;    // profiling: one event after every pass of the last run (per-pass durations)
+    int pass_ev_n = 0;
     DtcStreamPass* d_spasses = nullptr;  // pass descriptors on the device (k_tile_resident looks them up per work item)
     bool resident_ok = false;            // every pass runs on the streaming engine and at most two tensor maps are needed
     int tmap_mode[2] = {0, 0}, tmap_g[2] = {0, 0}, n_tmaps = 0;
@@ -1486,6 +1489,7 @@ int dtc_program_destroy(dtc_program* p) {
         table_free(p->d_spasses, p->h.device);
         if (p->ev0) cudaEventDestroy(p->ev0);
         if (p->ev1) cudaEventDestroy(p->ev1);
+        for (cudaEvent_t e : p->pass_ev) cudaEventDestroy(e);
         if (p->uploaded) cudaEventDestroy(p->uploaded);
         if (p->last_use) cudaEventDestroy(p->last_use);
     }
@@ -1648,7 +1652,17 @@ static int run_tile_passes(dtc_program* p, void* state, void* store_last, int be
         return e ? atoi(e) : 148;
     }();
     const int n_sms = (h.device >= 0 && h.device < 16 && g_num_sms[h.device] > 0) ? g_num_sms[h.device] : 148;
+    const bool per_pass = p->profiling && begin == 0 && end == (int)h.passes.size();
+    if (per_pass) {
+        while ((int)p->pass_ev.size() < end) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreate(&e));
+            p->pass_ev.push_back(e);
+        }
+        p->pass_ev_n = end;
+    }
     for (int ip = begin; ip < end; ++ip) {
+        if (per_pass && ip > 0) CUDA_TRY(cudaEventRecord(p->pass_ev[(size_t)ip - 1], s));
         const DtcTilePass& T = h.passes[(size_t)ip];
         const DtcStreamPass& S = h.spasses[(size_t)ip];
         double2* out = (double2*)state;
@@ -2056,6 +2070,20 @@ int dtc_program_set_profiling(dtc_program* p, int enable) {
         CUDA_TRY(cudaEventCreate(&p->ev1));
     }
     p->profiling = enable != 0;
+    return DTC_OK;
+}
+
+int dtc_program_pass_times(dtc_program* p, float* ms, int* modes, int cap, int* n_passes) {
+    if (!p || !ms || !modes || !n_passes || !p->ev1) return fail(DTC_ERR_INVALID, "profiling not enabled");
+    CUDA_TRY(cudaEventSynchronize(p->ev1));
+    const int n = p->pass_ev_n;
+    *n_passes = n;
+    for (int i = 0; i < n && i < cap; ++i) {
+        cudaEvent_t a = i == 0 ? p->ev0 : p->pass_ev[(size_t)i - 1];
+        cudaEvent_t b = i + 1 == n ? p->ev1 : p->pass_ev[(size_t)i];
+        CUDA_TRY(cudaEventElapsedTime(&ms[i], a, b));
+        modes[i] = p->h.spasses[(size_t)i].mode;
+    }
     return DTC_OK;
 }
 
