@@ -339,9 +339,12 @@ template <int MODE>
 __global__ void __launch_bounds__(DTC_STREAM_THREADS, 1)
 k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DtcStreamPass P,
               const DtcLayer* __restrict__ layers, const u64* __restrict__ masks, long long n_traj, u64 rank_bits,
-              long long n_tiles, u64 init_index, double2* __restrict__ rdm_out, int rdm_local_bit, double2* store_base) {
+              long long n_tiles, u64 init_index, double2* __restrict__ rdm_out, int rdm_local_bit, double2* store_base,
+              int store_lag) {
     // store_base != state (contiguous tiles only): the finished tiles are stored THERE instead of in place -- e.g. straight
     // into a peer GPU's receive buffer over NVLink, fusing the last sweep before an exchange with the exchange itself.
+    // store_lag = 1 (for such slow stores): a stage is reloaded only after the NEXT tile's store has been issued, so two
+    // stores per SM are in flight instead of one (the loads run one tile later; a store-bound sweep does not care).
     // rdm_out != nullptr (last pass of a factorised circuit): the tile is not stored; the reduced density matrix of the
     // tile-local bit rdm_local_bit of psi' is accumulated into rdm_out[trajectory][2][2] instead.
     // init_index != DTC_INIT_KEEP: the input is not read -- every trajectory starts in the basis state init_index
@@ -379,7 +382,15 @@ k_tile_stream(double2* __restrict__ state, const __grid_constant__ CUtensorMap t
             mbar_wait(smem_u32(&sm.done[s]), par);
             PROF_LAP(0);
             if (!rdm_out) stream_tma_store(P, &tmap, store_base, (u64)blockIdx.x + (u64)k * gridDim.x, smem_u32(sm.stage[s]));
-            if (k + DTC_STREAM_STAGES < K) {
+            if (store_lag) {
+                // reload the stage of the PREVIOUS tile: all but the store just issued have read their stage
+                if (k >= 1 && k - 1 + DTC_STREAM_STAGES < K) {
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    const int sp = s == 0 ? DTC_STREAM_STAGES - 1 : s - 1;
+                    stream_tma_load(P, &tmap, state, (u64)blockIdx.x + (u64)(k - 1 + DTC_STREAM_STAGES) * gridDim.x,
+                                    smem_u32(sm.stage[sp]), smem_u32(&sm.full[sp]));
+                }
+            } else if (k + DTC_STREAM_STAGES < K) {
                 if (!rdm_out) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has read the stage
                 PROF_LAP(1);
                 if (gen) mbar_arrive(smem_u32(&sm.full[s]));
@@ -1442,6 +1453,7 @@ static int stream_tensor_map(CUtensorMap* tm, void* state, int n_local, int g, i
 
 static int g_stream_override = -1;      // dtc_set_stream_engine(); -1: environment / default
 static int g_stream_ctas = 0;           // dtc_set_stream_ctas(); 0: one persistent CTA per SM
+static int g_store_lag = []() { const char* e = getenv("DTCSIM_STORE_LAG"); return e ? atoi(e) : 1; }();   // out-of-place stores: two in flight per SM
 static bool stream_enabled() {
     if (g_stream_override >= 0) return g_stream_override != 0;
     static const bool on = []() {
@@ -1684,6 +1696,7 @@ static int run_tile_passes(dtc_program* p, void* state, void* store_last, int be
             const unsigned sgrid = (unsigned)(grid < max_ctas ? grid : max_ctas);
             const size_t ssb = sizeof(StreamSmem) + 128;
             const u64 init = (ip == 0 && gen_first) ? (u64)init_index : (u64)DTC_INIT_KEEP;
+            const int lag = (out != (double2*)state && g_store_lag && !(ip == 0 && gen_first)) ? 1 : 0;
             double2* rdm_out = nullptr;
             if (fused && ip + 1 == (int)h.passes.size()) {
                 rdm_out = (double2*)((char*)workspace + dtc_workspace_rdm_offset(h, n_traj));
@@ -1691,13 +1704,13 @@ static int run_tile_passes(dtc_program* p, void* state, void* store_last, int be
             }
             if (S.mode == 1)
                 k_tile_stream<1><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
-                                                                       rdm_out, p->fused_local_bit, out);
+                                                                       rdm_out, p->fused_local_bit, out, lag);
             else if (S.mode == 2)
                 k_tile_stream<2><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
-                                                                       rdm_out, p->fused_local_bit, out);
+                                                                       rdm_out, p->fused_local_bit, out, lag);
             else
                 k_tile_stream<3><<<sgrid, DTC_STREAM_THREADS, ssb, s>>>((double2*)state, tm, S, p->d_layers, masks, n_traj, rank_bits, grid, init,
-                                                                       rdm_out, p->fused_local_bit, out);
+                                                                       rdm_out, p->fused_local_bit, out, lag);
             continue;
         }
         const bool hx = T.layerD >= 0 && T.nX > 0;
