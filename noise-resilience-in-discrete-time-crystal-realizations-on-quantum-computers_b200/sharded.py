@@ -286,6 +286,7 @@ class CudaShardEngine:
 
     NCCL_SMS = 20            # SMs left to the NCCL send/recv kernels while sweeps and exchange overlap (nccl mode)
     REMOTE_CTAS = int(__import__("os").environ.get("DTCSIM_REMOTE_CTAS", "48"))   # persistent CTAs of a sweep that stores to a peer
+    CE_QUARTERS = int(__import__("os").environ.get("DTCSIM_CE_QUARTERS", "0"))    # quarters of a slice pushed by the copy engine instead
     # (L = 34 on 8 B200: 24 / 32 / 48 CTAs -> 12.8 / 14.2 / 14.5 periods/s; copy-engine pushes instead: 13.7)
 
     def __init__(self, n, n_local, rank, world, device_index, group=None, transport=None, overlap=True, fabric=None):
@@ -323,6 +324,7 @@ class CudaShardEngine:
         if transport == "thread":
             fabric.register(rank, self.a, self.b)
         self.comm = torch.cuda.Stream(device=self.ctx.index) if world > 1 else None
+        self.ce = torch.cuda.Stream(device=self.ctx.index) if world > 1 else None
         # symm / thread transports: the LAST sweep of a slice program stores its tiles straight into the receiver's buffer
         # (TMA stores to peer memory over NVLink) -- sweep and exchange are one kernel; it runs on the side stream with
         # REMOTE_CTAS persistent CTAs while the other SMs already sweep the next slice
@@ -336,17 +338,17 @@ class CudaShardEngine:
         self.timing = None          # set to {} to collect wall-clock seconds per component (synchronises after each)
 
     # ---- programs: one handle (+ workspace) per distinct segment, kept for the life of the engine
-    def _handle(self, prog, n_local):
+    def _handle(self, prog, n_local, n_traj=1):
         ev = prog.arrays()
-        key = (n_local, prog.n_layers) + tuple(ev[k].tobytes() for k in ("type", "layer", "q0", "q1", "slot", "val"))
+        key = (n_local, n_traj, prog.n_layers) + tuple(ev[k].tobytes() for k in ("type", "layer", "q0", "q1", "slot", "val"))
         hit = self._handles.get(key)
         if hit is None:
             capi = self.capi
             h = capi.ProgramHandle(prog, self.ctx.index, capi.ENGINE_AUTO, n_local)
-            wsb = h.workspace_bytes(1)
+            wsb = h.workspace_bytes(n_traj)
             hit = (h, self.ctx.empty(wsb, self.torch.uint8), wsb)
             # segment programs are ideal (signs resolved on the host): their sign masks are all zero, written once
-            h.prepare(1, 0, 0, hit[1].data_ptr(), wsb, self.ctx.stream)
+            h.prepare(n_traj, 0, 0, hit[1].data_ptr(), wsb, self.ctx.stream)
             if len(self._handles) >= 256:
                 old = self._handles.pop(next(iter(self._handles)))
                 old[0].close()                            # tables are freed in stream order after their last use
@@ -445,13 +447,26 @@ class CudaShardEngine:
                 except ValueError:
                     fuse = False
 
-        def sweep_and_send(d, dst_ptr, stream_last, ctas_main, ctas_last):
-            """Slice d: all sweeps but the last in place, the last one storing its tiles at dst_ptr (a peer's receive slot)."""
+        def sweep_and_send(d, dst_ptr, stream_last, ctas_main, ctas_last, dst_tensor=None):
+            """Slice d: all sweeps but the last in place, the last one storing its tiles at dst_ptr (a peer's receive slot);
+            with CE_QUARTERS = k the last k quarters of the slice are swept in place and copied instead (dst_tensor)."""
             src = a.data_ptr() + 16 * d * S
+            rb = (r << g) | d
             if np_ > 1:
-                h.run_passes(src, 0, np_ - 1, 1, ws.data_ptr(), wsb, self.ctx.stream, n_ctas=ctas_main, rank_bits=(r << g) | d)
-            h.run_passes(src, np_ - 1, np_, 1, ws.data_ptr(), wsb, stream_last, store_last=dst_ptr, n_ctas=ctas_last,
-                         rank_bits=(r << g) | d)
+                h.run_passes(src, 0, np_ - 1, 1, ws.data_ptr(), wsb, self.ctx.stream, n_ctas=ctas_main, rank_bits=rb)
+            kq = self.CE_QUARTERS if (dst_tensor is not None and nls - 2 >= 12 and max(prog.ev["q0"]) < nls - 2) else 0
+            if kq:
+                hq, wsq, wsqb = self._handle(prog, nls - 2, n_traj=4)
+                Q = S >> 2
+                hq.run_passes(src, np_ - 1, np_, 4 - kq, wsq.data_ptr(), wsqb, stream_last, store_last=dst_ptr, n_ctas=ctas_last,
+                              rank_bits=rb << 2)
+                lo = d * S + (4 - kq) * Q
+                hq.run_passes(a.data_ptr() + 16 * lo, np_ - 1, np_, kq, wsq.data_ptr(), wsqb, self.ctx.stream, n_ctas=ctas_main,
+                              rank_bits=rb << 2)
+                dst_tensor[r * S + (4 - kq) * Q:(r + 1) * S].copy_(a[lo:lo + kq * Q])
+            else:
+                h.run_passes(src, np_ - 1, np_, 1, ws.data_ptr(), wsb, stream_last, store_last=dst_ptr, n_ctas=ctas_last,
+                             rank_bits=rb)
             self.passes_weighted += np_ * (1 << nls) / float(1 << self.n_local)
             self.fused_stores += 1
 
@@ -461,7 +476,8 @@ class CudaShardEngine:
             self.fabric.bar.wait()                     # every rank's receive buffer is free
             if fuse:
                 for d in range(P):
-                    sweep_and_send(d, self.fabric.bufs[d]["b"].data_ptr() + 16 * r * S, self.ctx.stream, 0, 0)
+                    sweep_and_send(d, self.fabric.bufs[d]["b"].data_ptr() + 16 * r * S, self.ctx.stream, 0, 0,
+                                   dst_tensor=self.fabric.bufs[d]["b"])
                 torch.cuda.synchronize(self.ctx.index)
                 self.fabric.bar.wait()
             else:
@@ -499,6 +515,15 @@ class CudaShardEngine:
             comm_ptr = ctypes.c_void_p(comm.cuda_stream)
             n_last = max(1, min(self.REMOTE_CTAS, self.n_sms - 1))
             n_main = self.n_sms - n_last
+            # Hybrid (CE_QUARTERS = k > 0): the peer-storing sweep gets ~12 GB/s per SM out of the link, a copy engine 750 GB/s
+            # for no SM at all but one more read of the data from HBM.  The slice programs rotate only bits below
+            # n_local - g - 2, so the LAST sweep of a slice can run quarter by quarter: 4 - k quarters store into the peer
+            # (side stream, REMOTE_CTAS SMs), k quarters are swept in place by the main SMs and pushed by the copy engine.
+            kq = self.CE_QUARTERS if (nls - 2 >= 12 and max(prog.ev["q0"]) < nls - 2) else 0
+            if kq:
+                hq, wsq, wsqb = self._handle(prog, nls - 2, n_traj=4)
+                Q = S >> 2
+                ce = self.ce
             for d in order:
                 src = a.data_ptr() + 16 * d * S
                 rb = (r << g) | d
@@ -508,7 +533,19 @@ class CudaShardEngine:
                     ev = torch.cuda.Event()
                     ev.record(cur)
                     comm.wait_event(ev)
-                if d != r:
+                if d != r and kq:
+                    hq.run_passes(src, np_ - 1, np_, 4 - kq, wsq.data_ptr(), wsqb, comm_ptr,
+                                  store_last=int(peers[d]) + 16 * r * S, n_ctas=n_last, rank_bits=rb << 2)
+                    lo = d * S + (4 - kq) * Q                      # the last kq quarters: in place, then the copy engine
+                    hq.run_passes(a.data_ptr() + 16 * lo, np_ - 1, np_, kq, wsq.data_ptr(), wsqb, self.ctx.stream, n_ctas=n_main,
+                                  rank_bits=rb << 2)
+                    ev2 = torch.cuda.Event()
+                    ev2.record(cur)
+                    ce.wait_event(ev2)
+                    with torch.cuda.stream(ce):
+                        peer_b = hb.get_buffer(d, (2 * kq * Q,), torch.float64, 2 * (r * S + (4 - kq) * Q))
+                        peer_b.copy_(a[lo:lo + kq * Q].view(torch.float64), non_blocking=True)
+                elif d != r:
                     h.run_passes(src, np_ - 1, np_, 1, ws.data_ptr(), wsb, comm_ptr, store_last=int(peers[d]) + 16 * r * S,
                                  n_ctas=n_last, rank_bits=rb)
                 else:                            # the slice that stays: stored into this rank's own receive buffer, main stream
@@ -517,6 +554,8 @@ class CudaShardEngine:
                 self.passes_weighted += np_ * (1 << nls) / float(1 << self.n_local)
                 self.fused_stores += 1
             comm.wait_stream(cur)
+            if kq:
+                comm.wait_stream(ce)
             with torch.cuda.stream(comm):
                 hb.barrier(channel=0)            # every rank's stores into every receive buffer have completed
             cur.wait_stream(comm)

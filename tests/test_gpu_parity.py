@@ -655,8 +655,9 @@ def _dtc_chain_circuit(L, t, rng, echo=False):
     return circ, low
 
 
-@pytest.mark.parametrize("world,L,high_bit", [(1, 14, 15), (2, 16, 15), (4, 17, 9), (2, 18, 10)])
-def test_sharded_engine_vs_oracle(world, L, high_bit):
+@pytest.mark.parametrize("world,L,high_bit,ce_quarters", [(1, 14, 15, 0), (2, 16, 15, 0), (4, 17, 9, 0), (2, 18, 10, 0),
+                                                         (2, 18, 15, 2), (4, 19, 15, 1)])
+def test_sharded_engine_vs_oracle(world, L, high_bit, ce_quarters):
     """CudaShardEngine + ShardedStatevector (rank bits in the diagonal phases, one-sweep top-group segments, slice
     programs fused with the exchange, qubit permutation kept) against the oracle: a noisy trajectory of the dtc_qasm.py
     circuit shape.  world > 1: the ranks are emulated by threads on this one GPU (sharded.ThreadFabric)."""
@@ -683,6 +684,8 @@ def test_sharded_engine_vs_oracle(world, L, high_bit):
                 fabric.bar.abort()
 
     capi.set_high_stride_bit(high_bit)
+    saved = sharded.CudaShardEngine.CE_QUARTERS
+    sharded.CudaShardEngine.CE_QUARTERS = ce_quarters      # part of every slice copied instead of stored by the last sweep
     try:
         threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
         for th in threads:
@@ -691,6 +694,7 @@ def test_sharded_engine_vs_oracle(world, L, high_bit):
             th.join()
     finally:
         capi.set_high_stride_bit(15)
+        sharded.CudaShardEngine.CE_QUARTERS = saved
     assert not errors, errors
     oc, na, _ = O.compact_ops(low, L)
     psi = O.run_trajectories(oc, na, O.PauliNoise.depolarizing(0.2), 11, [5])[0]
