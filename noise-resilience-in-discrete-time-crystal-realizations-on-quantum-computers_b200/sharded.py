@@ -333,6 +333,7 @@ class CudaShardEngine:
         self.n_sms = torch.cuda.get_device_properties(self.ctx.index).multi_processor_count
         self._handles = {}
         self.passes = 0
+        self.passes_weighted = 0.0  # state sweeps in units of the whole shard (a slice sweep counts 1 / 2^g)
         self.fast_exchanges = 0
         self.sliced_exchanges = 0
         self.timing = None          # set to {} to collect wall-clock seconds per component (synchronises after each)
@@ -371,8 +372,6 @@ class CudaShardEngine:
         h.run(ptr, 1, 0, 0, ws.data_ptr(), wsb, self.ctx.stream, init_index=init, rank_bits=rank_bits)
         self.passes_weighted += h.num_passes * (1 << n_local) / float(1 << self.n_local)
         return h.num_passes
-
-    passes_weighted = 0.0           # state sweeps in units of the whole shard (a slice sweep counts 1 / 2^g)
 
     def run_segment(self, prog, first):
         import time

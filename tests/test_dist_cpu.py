@@ -89,3 +89,74 @@ def test_two_rank_gloo_counts_match_single_process():
     assert hist == single and sum(hist) == 101           # independent of the number of ranks
     assert sums == [float(i * i) for i in range(10)]
     assert counts == {"0": hist[0], "1": hist[1]}
+
+
+class _OracleSim:
+    """Stands in for DTCSimulator on the CPU: run(list, shots, seed list) -> counts from the oracle (same seeds, same contract)."""
+
+    class _Ctx:
+        device = None
+
+    ctx = _Ctx()
+
+    def run(self, circuits, shots=1024, seed_simulator=0, **_kw):
+        from oracle import oracle as O
+        noise = O.PauliNoise.depolarizing(0.05)
+        seeds = list(seed_simulator) if isinstance(seed_simulator, (list, tuple)) else [seed_simulator + i for i in range(len(circuits))]
+        outs = [O.run_counts([o.astuple() for o in c.ops], c.num_qubits, c.num_clbits, shots=shots, noise=noise, seed=s)[0]
+                for c, s in zip(circuits, seeds)]
+
+        class _R:
+            def get_counts(self, i):
+                return outs[i]
+
+        class _J:
+            def result(self):
+                return _R()
+        return _J()
+
+
+def _sweep_worker(rank, world, port, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import pandas as pd
+    import torch.distributed as dist
+    import dtcsim
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = os.path.join(root, "tests", "golden")
+    hs = pd.read_csv(os.path.join(g, "hs_L20.csv")).values[:2, :4]
+    phis = pd.read_csv(os.path.join(g, "phis_L20.csv")).values[:2, :3]
+    res = dtcsim.run_sweep(_OracleSim(), 4, [0.84, 0.97], hs, phis, [0, 1, 2], (False, True), ("x", "xy"), shots=32,
+                           seed_simulator=9, rank=rank, world=world, chunk=5)
+    if rank == 0:
+        out.put((res["autocorr"].tolist(), res["points"], res["periods"]))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_run_sweep_two_ranks_equal_one_rank():
+    """sweeps.run_sweep (the C4 front-end: g x polarisation x echo x instance x t) dealt over 2 gloo ranks == 1 rank:
+    per-point seeds are seed + GLOBAL point index, results are all-reduced."""
+    ctx = mp.get_context("spawn")
+    results = []
+    for world in (1, 2):
+        out = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_sweep_worker, args=(r, world, port, out)) for r in range(world)]
+        for p in procs:
+            p.start()
+        results.append(out.get(timeout=300))
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    (a1, n1, per1), (a2, n2, per2) = results
+    assert n1 == n2 == 2 * 2 * 2 * 2 * 3 and per1 == per2 == 32 * 2 * 2 * 2 * (3 + 6)
+    assert np.array_equal(np.array(a1), np.array(a2))
+    assert np.abs(np.array(a1)).max() <= 1.0 and np.abs(np.array(a1)[:, :, :, :, 0] - 0.735).max() < 0.4      # t = 0 rows ~ 0.95^6
