@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--periods", type=int, default=10)
-    ap.add_argument("--remote-ctas", type=int, default=0, help="persistent CTAs of the sweep that stores into the peer (default 48)")
+    ap.add_argument("--remote-ctas", type=int, default=0, help="persistent CTAs of the sweep that stores into the peer (default 64)")
     ap.add_argument("--ce-quarters", type=int, default=-1, help="quarters (0-3) of every slice pushed by the copy engine instead of stored by the sweep")
     ap.add_argument("--no-fuse", action="store_true", help="copy-engine pushes instead of storing the last sweep into the peer")
     ap.add_argument("--no-overlap", action="store_true", help="one all_to_all_single per exchange, no overlap (round-1 behaviour)")
@@ -51,7 +51,7 @@ def main():
     peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
     ns = argparse.Namespace(sharded_periods=args.periods)
     out = bench.sharded_leg(ns, dist, rank, world, local, peak)
-    out["options"] = {"remote_ctas": os.environ.get("DTCSIM_REMOTE_CTAS", "48"), "fuse_store": not args.no_fuse, "ce_quarters": os.environ.get("DTCSIM_CE_QUARTERS", "0"),
+    out["options"] = {"remote_ctas": os.environ.get("DTCSIM_REMOTE_CTAS", "64"), "fuse_store": not args.no_fuse, "ce_quarters": os.environ.get("DTCSIM_CE_QUARTERS", "0"),
                       "overlap": not args.no_overlap}
     if rank == 0:
         print(json.dumps(out), flush=True)

@@ -285,9 +285,10 @@ class CudaShardEngine:
        * `thread` ranks emulated by threads on one GPU (ThreadFabric; tests)."""
 
     NCCL_SMS = 20            # SMs left to the NCCL send/recv kernels while sweeps and exchange overlap (nccl mode)
-    REMOTE_CTAS = int(__import__("os").environ.get("DTCSIM_REMOTE_CTAS", "48"))   # persistent CTAs of a sweep that stores to a peer
+    REMOTE_CTAS = int(__import__("os").environ.get("DTCSIM_REMOTE_CTAS", "64"))   # persistent CTAs of a sweep that stores to a peer
     CE_QUARTERS = int(__import__("os").environ.get("DTCSIM_CE_QUARTERS", "0"))    # quarters of a slice pushed by the copy engine instead
-    # (L = 34 on 8 B200: 24 / 32 / 48 CTAs -> 12.8 / 14.2 / 14.5 periods/s; copy-engine pushes instead: 13.7)
+    # (L = 34 on 8 B200, two stores per SM in flight: 24 / 32 / 48 / 56 / 64 CTAs -> 10.6 / 12.6 / 14.8 / 14.4 / 15.1 periods/s;
+    #  copy-engine pushes instead: 13.7; profiles/sharded_L34_P8_r2_variants.jsonl)
 
     def __init__(self, n, n_local, rank, world, device_index, group=None, transport=None, overlap=True, fabric=None):
         import torch
