@@ -513,7 +513,10 @@ class CudaShardEngine:
             hb = self.hdl[b.data_ptr()]
             peers = hb.buffer_ptrs
             comm_ptr = ctypes.c_void_p(comm.cuda_stream)
-            n_last = max(1, min(self.REMOTE_CTAS, self.n_sms - 1))
+            remote = self.REMOTE_CTAS
+            if P == 2 and "DTCSIM_REMOTE_CTAS" not in __import__("os").environ:
+                remote = 32                  # one remote slice only: measured 61 ms per period at L = 32 (CE pushes: 73 ms)
+            n_last = max(1, min(remote, self.n_sms - 1))
             n_main = self.n_sms - n_last
             # Hybrid (CE_QUARTERS = k > 0): the peer-storing sweep gets ~12 GB/s per SM out of the link, a copy engine 750 GB/s
             # for no SM at all but one more read of the data from HBM.  The slice programs rotate only bits below
