@@ -149,3 +149,18 @@ def test_estimator_on_gpu_vs_exact(disorder, L, noisy):
                 exact += c * float(np.dot(p, z))
     tol = family_z(3) * float(pub.data.stds) + (0.0 if L <= 6 else 0.15)   # + Monte-Carlo error of the 600-trajectory reference
     assert abs(float(pub.data.evs) - exact) < tol, (float(pub.data.evs), exact, float(pub.data.stds))
+
+
+def test_estimator_y_and_mixed_terms(disorder):
+    """Basis changes for Y (sdg, h) and qubit-wise commuting groups of mixed X / Y / Z words, against exact values."""
+    L, g = 4, 0.6
+    hs, phis = disorder[20][0][1][:L], disorder[20][1][1][:L - 1]
+    circ = _energy_circuit(L, g, hs, phis, 2)
+    terms = [("IIYI", 0.7), ("XYIZ", -1.3), ("ZZII", 0.4), ("IYXI", 0.9), ("YIIY", 0.5), ("IIII", 0.25)]
+    groups = E.group_qubitwise_commuting([t for t in terms if set(t[0]) != {"I"}])
+    assert len(groups) <= 4
+    est = E.BackendEstimatorV2(_OracleBackend(None, seed=11), options={"default_precision": 1 / 128})
+    pub = est.run([(circ, terms)]).result()[0]
+    exact = _exact_energy([o.astuple() for o in circ.ops], L, terms)
+    assert pub.metadata["shots"] == 16384
+    assert abs(float(pub.data.evs) - exact) < 4.5 * float(pub.data.stds) + 1e-12, (float(pub.data.evs), exact)
