@@ -444,7 +444,7 @@ def run_c3(args):
             "config": {"workload": "C3: L=12 exact noisy density matrix (2^24 complex128 = 256 MiB), g=0.97, depolarizing p=0.05, "
                                    "20 periods, <Z_6>", "l2_policy": "rho (256 MiB) is larger than L2"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "kernel": "k_dm_tile", "sweeps_per_period": sweeps / T,
+                         "kernel": "k_dm_reg", "sweeps_per_period": sweeps / T,
                          "per_sweep_gbs": sweeps * b_alg / (ms * 1e-3) / 1e9,
                          "note": "achieved = periods/s x 2 x 16 B x 4^12 (SURVEY 8d byte model: ONE read + write of rho per period); "
                                  "per_sweep_gbs = what each of the sweeps_per_period passes over rho sustains"},

@@ -23,6 +23,7 @@
 #include "../../include/dtcsim.h"
 #include "dtc_core.hpp"
 #include "dtc_readout.cuh"
+#include "dtc_dm.cuh"
 
 // ------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -1245,27 +1246,6 @@ __global__ void k_dm_channel(double2* __restrict__ rho, int n, int q, double px,
 // conjugate on the column bit and the Pauli channel that follows (a 2 x 2 block of rho per qubit), with the diagonal layer
 // that precedes them folded into the load.  rho is a 2n-bit vector (index = row + 2^n col); a tile holds 2^TB elements:
 // optional passive row bits {0,1} (64 B runs) + the row and column bits of the pass's qubits.
-#define DTC_DM_MAXQ 6
-#define DTC_DM_THREADS 256
-struct DmQubitOp {
-    int lr, lc;                      // tile-local positions of the qubit's row / column bit (lr < lc)
-    double c, s;                     // cos, sin of theta/2 (row: RX(theta), column: its conjugate)
-    double dA, dB, oA, oB;           // channel: diagonal block mixing (r == c), off-diagonal block mixing (r != c)
-};
-struct DmTilePass {
-    int n, tile_bits, nq, has_diag;
-    int tb[13];                      // global bit of tile-local bit l
-    int seg_n, seg_src[8], seg_len[8], seg_dst[8];     // CTA index -> global base (bits outside the tile)
-    DmQubitOp q[DTC_DM_MAXQ];
-};
-struct DmDiagTerms {
-    int n1, n2;
-    int q1[16];
-    double a[16];
-    int qi[DTC_MAXT], qj[DTC_MAXT];
-    double b[DTC_MAXT];
-};
-
 // T[x] = exp(-i phi(x)), phi(x) = sum_k a_k z_k(x)/2 + sum_k b_k z_i z_j /2 : rho[r,c] *= T[r] conj(T[c])
 __global__ void k_dm_phase_table(double2* __restrict__ T, int n, const __grid_constant__ DmDiagTerms D) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1284,10 +1264,6 @@ __global__ void k_dm_apply_table(double2* __restrict__ rho, int n, const double2
     const double2 tr = T[(u64)i & ((1ull << n) - 1)], tc = T[(u64)i >> n];
     rho[i] = cmul(rho[i], cmul(tr, make_double2(tc.x, -tc.y)));
 }
-
-// shared-memory position of tile element e: XOR swizzle of the low three bits, so that the stride-2 / stride-4 / stride-8
-// element patterns of a qubit whose row bit is one of the tile's lowest bits still hit eight different 16 B bank groups
-__device__ __forceinline__ int dm_phys(int e) { return e ^ ((e >> 3) & 7); }
 
 // THREADS = 256 (tiles of <= 2^12 elements, three CTAs per SM) or 512 (2^13 elements = 128 KB, one CTA per SM)
 template <int THREADS>
@@ -1367,6 +1343,21 @@ k_dm_tile(double2* __restrict__ rho, const __grid_constant__ DmTilePass P, const
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         if (k < nk && tid + DTC_DM_THREADS_ * k < ne) __stcs(rho + (base | off_lo | off_hi[k]), dm_tile[dm_phys(tid + DTC_DM_THREADS_ * k)]);
+}
+
+// Register-resident sweep (csrc/dtc_dm.cuh): 16 elements = two qubits' (row, column) bits per thread; round 0 HBM -> registers
+// -> shared memory, middle round shared -> shared, last round shared -> registers -> HBM.  THREADS = 2^(tile_bits - 4).
+// Two CTAs per SM for the 2^12 tiles (126 registers; at 80 registers for three CTAs the 16 elements spill), one for 2^13.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
+k_dm_reg(double2* __restrict__ rho, const __grid_constant__ DmRegPass P, const double2* __restrict__ T) {
+    extern __shared__ __align__(16) double2 dm_tile[];
+    const unsigned base = (unsigned)dm_cta_base((u64)blockIdx.x, P.seg_n, P.seg_src, P.seg_len, P.seg_dst);
+    constexpr int LB = THREADS == 256 ? 8 : 9;
+    for (int r = 0; r < P.n_rounds; ++r) {
+        if (r) __syncthreads();
+        dmr_round<LB>(r, (int)threadIdx.x, P, rho, T, base, dm_tile);
+    }
 }
 
 __global__ void k_dm_probs(const double2* __restrict__ rho, int n, int k, const int* __restrict__ qubits,
@@ -2299,129 +2290,49 @@ int dtc_dm_run(void* rho, int n, int n_seg, const int32_t* seg_type, const int32
         if (dev >= 0 && dev < DTC_MAX_DEVICES && !attr_set[dev]) {
             CUDA_TRY(cudaFuncSetAttribute(k_dm_tile<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
             CUDA_TRY(cudaFuncSetAttribute(k_dm_tile<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 13));
+            CUDA_TRY(cudaFuncSetAttribute(k_dm_reg<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
+            CUDA_TRY(cudaFuncSetAttribute(k_dm_reg<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 13));
             attr_set[dev] = true;
         }
     }
+    // DTCSIM_DM_REG=0: element-per-thread tiles (k_dm_tile) everywhere; DTCSIM_DM_TILE13=0: 2^12 tiles without a passive bit
+    // for the groups that do not hold qubit 0 (16 B runs)
+    static const DmPlanOptions opt = []() {
+        DmPlanOptions o;
+        const char* e = getenv("DTCSIM_DM_REG");
+        o.reg_passes = !(e && atoi(e) == 0);
+        e = getenv("DTCSIM_DM_TILE13");
+        o.wide13 = !(e && atoi(e) == 0);
+        return o;
+    }();
+    std::vector<DmStep> steps;
+    {
+        std::string err;
+        if (!dm_plan(n, n_seg, seg_type, seg_off, q0, q1, val, probs, opt, steps, err)) return fail(DTC_ERR_INVALID, err.c_str());
+    }
     double2* T = nullptr;
     CUDA_TRY(cudaMallocAsync((void**)&T, sizeof(double2) << n, s));
-    bool diag_pending = false;
     int sweeps = 0;
-    const int TB = (2 * n < 12) ? 2 * n : 12;
-    struct QOp { bool used; double theta, px, py, pz; };
-    int i = 0;
-    while (i < n_seg) {
-        if (seg_type[i] == 1) {
-            if (diag_pending) {                          // two diagonal segments in a row: flush the first
-                const long long ne = 1ll << (2 * n);
-                k_dm_apply_table<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>((double2*)rho, n, T);
-                ++sweeps;
-            }
-            DmDiagTerms D;
-            memset(&D, 0, sizeof(D));
-            for (int k = seg_off[i]; k < seg_off[i + 1]; ++k) {
-                if (q0[k] < 0 || q0[k] >= n || q1[k] >= n) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "diagonal term: qubit out of range"); }
-                if (q1[k] < 0) {
-                    if (D.n1 >= 16) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "too many one-body terms"); }
-                    D.q1[D.n1] = q0[k]; D.a[D.n1] = val[k]; ++D.n1;
-                } else {
-                    if (D.n2 >= DTC_MAXT) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "too many two-body terms in one segment"); }
-                    D.qi[D.n2] = q0[k]; D.qj[D.n2] = q1[k]; D.b[D.n2] = val[k]; ++D.n2;
-                }
-            }
-            k_dm_phase_table<<<((1 << n) + 127) / 128, 128, 0, s>>>(T, n, D);
-            diag_pending = true;
-            ++i;
-            continue;
-        }
-        // a layer of qubit operations: [rotations] [channels]
-        QOp ops[16];
-        for (int q = 0; q < 16; ++q) ops[q] = QOp{false, 0.0, 0.0, 0.0, 0.0};
-        int j = i;
-        if (seg_type[j] == 0) {
-            for (int k = seg_off[j]; k < seg_off[j + 1]; ++k) {
-                if (q0[k] < 0 || q0[k] >= n || ops[q0[k]].used) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "rotation segment: bad or repeated qubit"); }
-                ops[q0[k]].used = true;
-                ops[q0[k]].theta = val[k];
-            }
-            ++j;
-        }
-        if (j < n_seg && seg_type[j] == 2) {
-            bool seen[16] = {false};
-            for (int k = seg_off[j]; k < seg_off[j + 1]; ++k) {
-                if (q0[k] < 0 || q0[k] >= n || seen[q0[k]]) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "channel segment: bad or repeated qubit"); }
-                seen[q0[k]] = true;
-                QOp& o = ops[q0[k]];
-                o.used = true;
-                o.px = probs[3 * k]; o.py = probs[3 * k + 1]; o.pz = probs[3 * k + 2];
-            }
-            ++j;
-        } else if (j == i) {
-            cudaFreeAsync(T, s);
-            return fail(DTC_ERR_INVALID, "unknown segment type");
-        }
-        i = j;
-        // groups of qubits per sweep
-        int todo[16], nt = 0;
-        for (int q = 0; q < n; ++q)
-            if (ops[q].used) todo[nt++] = q;
-        int pos = 0;
-        while (pos < nt) {
-            DmTilePass P;
-            memset(&P, 0, sizeof(P));
-            P.n = n;
-            // a group that holds qubit 0 (or a register that fits one tile): up to six qubits in a 2^12 tile, row bit 0 among
-            // them; any other group: row bit 0 as a passive bit (32 B runs = whole sectors) + up to six qubits in a 2^13 tile
-            // (DTCSIM_DM_TILE13=0: 2^12 tiles without a passive bit for those groups -- 16 B runs, measured 9 % slower on C3)
-            static const bool wide13 = []() { const char* e = getenv("DTCSIM_DM_TILE13"); return !(e && atoi(e) == 0); }();
-            const bool low_group = todo[pos] == 0 || 2 * n <= 12 || !wide13;
-            const int passive = low_group ? 0 : 1;
-            const int TBg = low_group ? TB : ((2 * n < 13) ? 2 * n : 13);
-            P.tile_bits = TBg;
-            int cap = (TBg - passive) / 2;
-            if (cap > DTC_DM_MAXQ) cap = DTC_DM_MAXQ;
-            int grp[DTC_DM_MAXQ], ng = 0;
-            while (pos < nt && ng < cap) grp[ng++] = todo[pos++];
-            // tile bits: passive row bits (unless they belong to a qubit of the group), then row bits, then column bits, ascending;
-            // spare positions are filled with the lowest unused row bits (they ride along untouched)
-            u64 used = 0;
-            for (int k = 0; k < ng; ++k) used |= (1ull << grp[k]) | (1ull << (grp[k] + n));
-            if (passive) used |= 1ull;
-            for (int b = 0; b < 2 * n && dtc_popc(used) < TBg; ++b) used |= 1ull << b;
-            int l = 0;
-            for (int b = 0; b < 2 * n; ++b)
-                if ((used >> b) & 1ull) P.tb[l++] = b;
-            P.nq = ng;
-            for (int k = 0; k < ng; ++k) {
-                DmQubitOp& Q = P.q[k];
-                for (int m = 0; m < TBg; ++m) {
-                    if (P.tb[m] == grp[k]) Q.lr = m;
-                    if (P.tb[m] == grp[k] + n) Q.lc = m;
-                }
-                const QOp& o = ops[grp[k]];
-                Q.c = cos(0.5 * o.theta); Q.s = sin(0.5 * o.theta);
-                Q.dA = 1.0 - o.px - o.py; Q.dB = o.px + o.py;
-                Q.oA = 1.0 - o.px - o.py - 2.0 * o.pz; Q.oB = o.px - o.py;
-            }
-            int src = 0, p2 = 0;
-            while (p2 < 2 * n) {
-                if ((used >> p2) & 1ull) { ++p2; continue; }
-                int len = 0;
-                while (p2 + len < 2 * n && !((used >> (p2 + len)) & 1ull)) ++len;
-                if (P.seg_n >= 8) { cudaFreeAsync(T, s); return fail(DTC_ERR_INVALID, "internal: too many index segments"); }
-                P.seg_src[P.seg_n] = src; P.seg_len[P.seg_n] = len; P.seg_dst[P.seg_n] = p2; ++P.seg_n;
-                src += len; p2 += len;
-            }
-            P.has_diag = diag_pending ? 1 : 0;
-            diag_pending = false;
-            if (TBg <= 12) k_dm_tile<256><<<1u << (2 * n - TBg), 256, sizeof(double2) << TBg, s>>>((double2*)rho, P, T);
-            else k_dm_tile<512><<<1u << (2 * n - TBg), 512, sizeof(double2) << TBg, s>>>((double2*)rho, P, T);
+    for (const DmStep& S : steps) {
+        if (S.kind == 0) {
+            k_dm_phase_table<<<((1 << n) + 127) / 128, 128, 0, s>>>(T, n, S.D);
+        } else if (S.kind == 1) {
+            const long long ne = 1ll << (2 * n);
+            k_dm_apply_table<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>((double2*)rho, n, T);
+            ++sweeps;
+        } else if (S.kind == 2) {
+            const int TBg = S.P.tile_bits;
+            if (TBg <= 12) k_dm_tile<256><<<1u << (2 * n - TBg), 256, sizeof(double2) << TBg, s>>>((double2*)rho, S.P, T);
+            else k_dm_tile<512><<<1u << (2 * n - TBg), 512, sizeof(double2) << TBg, s>>>((double2*)rho, S.P, T);
+            ++sweeps;
+        } else {
+            const int TBg = S.R.tile_bits;
+            const size_t smem = S.R.n_rounds > 1 ? sizeof(double2) << TBg : 0;
+            const unsigned grid = 1u << (2 * n - TBg);
+            if (TBg == 12) k_dm_reg<256><<<grid, 256, smem, s>>>((double2*)rho, S.R, T);
+            else k_dm_reg<512><<<grid, 512, smem, s>>>((double2*)rho, S.R, T);
             ++sweeps;
         }
-    }
-    if (diag_pending) {
-        const long long ne = 1ll << (2 * n);
-        k_dm_apply_table<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>((double2*)rho, n, T);
-        ++sweeps;
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaFreeAsync(T, s));

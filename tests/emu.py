@@ -13,7 +13,7 @@ CSRC = os.path.join(os.path.dirname(HERE),
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("dtc_hd.cuh", "dtc_core.hpp", "dtc_stream.cuh", "dtc_readout.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("dtc_hd.cuh", "dtc_core.hpp", "dtc_stream.cuh", "dtc_readout.cuh", "dtc_dm.cuh")]
     if force or not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", OUT, SRC])
@@ -106,3 +106,25 @@ def readout_small(prog, rdm, masks, fx):
 
 def set_high_stride_bit(bit=15):
     lib().emu_set_high_stride_bit(ctypes.c_int(bit))
+
+
+def dm_run(n, flat_segments, rho0=None, reg_passes=True, wide13=True):
+    """dtc_dm_run on the CPU (planner + per-thread code of csrc/dtc_dm.cuh).  flat_segments = backend.flatten_dm_segments(...).
+    Returns (rho [2^n cols, 2^n rows], info dict)."""
+    st, so, q0, q1, val, pr = flat_segments
+    rho = np.zeros(1 << (2 * n), dtype=np.complex128)
+    if rho0 is None:
+        rho[0] = 1.0
+    else:
+        rho[:] = np.asarray(rho0, dtype=np.complex128).reshape(-1)
+    pr = np.ascontiguousarray(pr, dtype=np.float64)
+    info = np.zeros(4, dtype=np.int32)
+    err = ctypes.create_string_buffer(512)
+    rc = lib().emu_dm_run(
+        ctypes.c_int(n), ctypes.c_int(len(st)), _p(st, ctypes.c_int32), _p(so, ctypes.c_int32), _p(q0, ctypes.c_int32),
+        _p(q1, ctypes.c_int32), _p(val, ctypes.c_double), pr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+        ctypes.c_int(int(reg_passes)), ctypes.c_int(int(wide13)), rho.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+        _p(info, ctypes.c_int32), err, ctypes.c_int(512))
+    if rc != 0:
+        raise ValueError(err.value.decode())
+    return rho.reshape(1 << n, 1 << n), {"sweeps": int(info[0]), "reg_passes": int(info[1]), "worst_conflict": int(info[2])}

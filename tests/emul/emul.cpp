@@ -11,6 +11,7 @@
 
 #include "../../noise-resilience-in-discrete-time-crystal-realizations-on-quantum-computers_b200/csrc/dtc_core.hpp"
 #include "../../noise-resilience-in-discrete-time-crystal-realizations-on-quantum-computers_b200/csrc/dtc_readout.cuh"
+#include "../../noise-resilience-in-discrete-time-crystal-realizations-on-quantum-computers_b200/csrc/dtc_dm.cuh"
 
 template <int S2_LO>
 static void emu_tile_pass(double2* state, const DtcTilePass& P, const DtcLayer* layers, const u64* masks,
@@ -255,3 +256,136 @@ extern "C" int emu_readout_small(int n_qubits, int n_layers, int64_t n_events, c
 }
 
 extern "C" void emu_set_high_stride_bit(int bit) { g_dtc_high_stride_bit = bit; }
+
+// dtc_dm_run on the CPU: the planner of csrc/dtc_dm.cuh, then every step executed CTA by CTA.  Register passes (k_dm_reg) run
+// the kernel's own per-thread function round by round (a round ends where the kernel has its __syncthreads); element-per-thread
+// tile passes (k_dm_tile) are replayed from their pass descriptor.  info[0] = sweeps over rho, info[1] = register passes,
+// info[2] = worst shared-memory conflict degree of a quarter warp over all register-pass rounds (1 = conflict free).
+extern "C" int emu_dm_run(int n, int n_seg, const int32_t* seg_type, const int32_t* seg_off, const int32_t* q0, const int32_t* q1,
+                          const double* val, const double* probs, int reg_passes, int wide13, double* rho_io, int32_t* info,
+                          char* errbuf, int errlen) {
+    DmPlanOptions opt;
+    opt.reg_passes = reg_passes != 0;
+    opt.wide13 = wide13 != 0;
+    std::vector<DmStep> steps;
+    std::string err;
+    if (!dm_plan(n, n_seg, seg_type, seg_off, q0, q1, val, probs, opt, steps, err)) {
+        snprintf(errbuf, errlen, "%s", err.c_str());
+        return -1;
+    }
+    double2* rho = reinterpret_cast<double2*>(rho_io);
+    const u64 ne = 1ull << (2 * n), rmask = (1ull << n) - 1;
+    std::vector<double2> T((size_t)1 << n);
+    int sweeps = 0, nreg = 0, worst = 1;
+    for (const DmStep& S : steps) {
+        if (S.kind == 0) {
+            for (u64 x = 0; x < (1ull << n); ++x) {
+                double ang = 0.0;
+                for (int k = 0; k < S.D.n1; ++k) ang += 0.5 * S.D.a[k] * (double)(1 - 2 * (int)((x >> S.D.q1[k]) & 1));
+                for (int k = 0; k < S.D.n2; ++k) ang += 0.5 * S.D.b[k] * (double)(1 - 2 * (int)(((x >> S.D.qi[k]) ^ (x >> S.D.qj[k])) & 1));
+                T[x] = make_double2(cos(ang), -sin(ang));
+            }
+        } else if (S.kind == 1) {
+            for (u64 i = 0; i < ne; ++i) {
+                const double2 tc = T[i >> n];
+                rho[i] = cmul(rho[i], cmul(T[i & rmask], make_double2(tc.x, -tc.y)));
+            }
+            ++sweeps;
+        } else if (S.kind == 2) {
+            const DmTilePass& P = S.P;
+            const int te = 1 << P.tile_bits;
+            std::vector<double2> tile(te);
+            std::vector<u64> off(te);
+            for (int e = 0; e < te; ++e) {
+                u64 o = 0;
+                for (int l = 0; l < P.tile_bits; ++l)
+                    if ((e >> l) & 1) o |= 1ull << P.tb[l];
+                off[e] = o;
+            }
+            for (u64 cta = 0; cta < (ne >> P.tile_bits); ++cta) {
+                const u64 base = dm_cta_base(cta, P.seg_n, P.seg_src, P.seg_len, P.seg_dst);
+                for (int e = 0; e < te; ++e) {
+                    const u64 g = base | off[e];
+                    double2 v = rho[g];
+                    if (P.has_diag) {
+                        const double2 tc = T[g >> n];
+                        v = cmul(v, cmul(T[g & rmask], make_double2(tc.x, -tc.y)));
+                    }
+                    tile[e] = v;
+                }
+                for (int k = 0; k < P.nq; ++k) {
+                    const DmQubitOp& Q = P.q[k];
+                    const double c = Q.c, s = Q.s;
+                    for (int x = 0; x < te; ++x) {
+                        if (x & ((1 << Q.lr) | (1 << Q.lc))) continue;
+                        const int i00 = x, i10 = x | (1 << Q.lr), i01 = x | (1 << Q.lc), i11 = i10 | i01;
+                        double2 e00 = tile[i00], e10 = tile[i10], e01 = tile[i01], e11 = tile[i11];
+                        const double2 a00 = make_double2(c * e00.x + s * e10.y, c * e00.y - s * e10.x);
+                        const double2 a10 = make_double2(c * e10.x + s * e00.y, c * e10.y - s * e00.x);
+                        const double2 a01 = make_double2(c * e01.x + s * e11.y, c * e01.y - s * e11.x);
+                        const double2 a11 = make_double2(c * e11.x + s * e01.y, c * e11.y - s * e01.x);
+                        e00 = make_double2(c * a00.x - s * a01.y, c * a00.y + s * a01.x);
+                        e01 = make_double2(c * a01.x - s * a00.y, c * a01.y + s * a00.x);
+                        e10 = make_double2(c * a10.x - s * a11.y, c * a10.y + s * a11.x);
+                        e11 = make_double2(c * a11.x - s * a10.y, c * a11.y + s * a10.x);
+                        tile[i00] = make_double2(Q.dA * e00.x + Q.dB * e11.x, Q.dA * e00.y + Q.dB * e11.y);
+                        tile[i11] = make_double2(Q.dA * e11.x + Q.dB * e00.x, Q.dA * e11.y + Q.dB * e00.y);
+                        tile[i10] = make_double2(Q.oA * e10.x + Q.oB * e01.x, Q.oA * e10.y + Q.oB * e01.y);
+                        tile[i01] = make_double2(Q.oA * e01.x + Q.oB * e10.x, Q.oA * e01.y + Q.oB * e10.y);
+                    }
+                }
+                for (int e = 0; e < te; ++e) rho[base | off[e]] = tile[e];
+            }
+            ++sweeps;
+        } else {
+            const DmRegPass& P = S.R;
+            const int threads = 1 << (P.tile_bits - 4);
+            std::vector<double2> tile((size_t)1 << P.tile_bits);
+            // every element of the tile must belong to exactly one (thread, register) of every round
+            for (int r = 0; r < P.n_rounds; ++r) {
+                std::vector<int> seen((size_t)1 << P.tile_bits, 0);
+                for (int tid = 0; tid < threads; ++tid) {
+                    int e = 0;
+                    for (int k = 0; k < P.tile_bits - 4; ++k)
+                        if ((tid >> k) & 1) e |= 1 << P.r[r].tbit[k];
+                    for (int j = 0; j < 16; ++j) {
+                        int ej = e;
+                        for (int k = 0; k < 4; ++k)
+                            if ((j >> k) & 1) ej |= 1 << P.r[r].hb[k];
+                        ++seen[ej];
+                    }
+                }
+                for (int x : seen)
+                    if (x != 1) {
+                        snprintf(errbuf, errlen, "register pass: round %d does not cover the tile exactly once", r);
+                        return -1;
+                    }
+                // conflict degree of the 16 B accesses of each quarter warp (same register j, eight consecutive lanes)
+                for (int q8 = 0; q8 < threads / 8; ++q8) {
+                    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int lane = 0; lane < 8; ++lane) {
+                        const int tid = q8 * 8 + lane;
+                        int e = 0;
+                        for (int k = 0; k < P.tile_bits - 4; ++k)
+                            if ((tid >> k) & 1) e |= 1 << P.r[r].tbit[k];
+                        ++cnt[dm_phys(e) & 7];
+                    }
+                    for (int b = 0; b < 8; ++b)
+                        if (cnt[b] > worst) worst = cnt[b];
+                }
+            }
+            for (u64 cta = 0; cta < (ne >> P.tile_bits); ++cta) {
+                const u64 base = dm_cta_base(cta, P.seg_n, P.seg_src, P.seg_len, P.seg_dst);
+                for (int r = 0; r < P.n_rounds; ++r)
+                    for (int tid = 0; tid < threads; ++tid) {
+                        if (P.tile_bits == 12) dmr_round<8>(r, tid, P, rho, T.data(), (unsigned)base, tile.data());
+                        else dmr_round<9>(r, tid, P, rho, T.data(), (unsigned)base, tile.data());
+                    }
+            }
+            ++sweeps;
+            ++nreg;
+        }
+    }
+    info[0] = sweeps; info[1] = nreg; info[2] = worst;
+    return 0;
+}

@@ -250,3 +250,84 @@ def test_schedule_large_register_uses_2kb_run_tiles_for_high_groups():
     for g in (20, 25, 26):
         assert tiles[tuple(range(7)) + tuple(range(g, g + 5))] == 3
     assert len(tiles) == 5
+
+
+# ----------------------------------------------------------------------------------- density matrix (csrc/dtc_dm.cuh)
+def _dm_check(circ, nm, tol=1e-13, **opts):
+    from dtcsim.backend import flatten_dm_segments
+    prog = compile_circuit(circ, nm, want_dm=True, optimize=False)
+    rho, info = emu.dm_run(prog.n, flatten_dm_segments(prog.dm_segments), **opts)
+    want = PI.run_dm(prog, prog.n)                       # [row, col]
+    assert np.abs(rho.T - want).max() < tol
+    return prog, info
+
+
+@pytest.mark.parametrize("L,t,echo,pol,reg,wide13", [
+    (5, 2, True, "x", True, True),       # n = 6: one 2^12 tile, three rounds
+    (6, 2, False, "xy", True, True),     # n = 7: low group of six + a 2^13 tile with a single qubit (one round, spare bits)
+    (7, 1, True, "y", True, True),       # n = 8: 2^13 tile with two qubits
+    (7, 1, True, "y", True, False),      # ... 2^12 tiles without a passive bit
+    (8, 1, False, "x", True, True),      # n = 9: 2^13 tile with three qubits (two rounds, the last one with spare bits)
+    (6, 2, False, "xy", False, True),    # element-per-thread tiles (the emulator's replay of k_dm_tile)
+    (4, 3, True, "x", True, True),       # n = 5 (reference config C1): tile smaller than 2^12 -> k_dm_tile
+])
+def test_dm_passes_reference_circuits(disorder, L, t, echo, pol, reg, wide13):
+    """Planner + per-thread code of the density-matrix sweeps == numpy execution of the same segments."""
+    hs, phis = disorder[20][0][1][:L], disorder[20][1][1][:L - 1]
+    circ = RC.transpiled(RC.qc_body("neel", L, 0.97, hs, phis, t, L // 2, echo, pol))
+    _prog, info = _dm_check(circ, RC.noise_model(0.05), reg_passes=reg, wide13=wide13)
+    assert (info["reg_passes"] > 0) == (reg and L + 1 >= 6)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_dm_passes_random_circuits_asymmetric_channels(seed):
+    """General rotations (quarter turns -> swap form, angles beyond pi) and channels with pX != pY != pZ."""
+    rng = np.random.default_rng(300 + seed)
+    n = 6 + seed
+    c = dtcsim.QuantumCircuit(n, 1)
+    for _layer in range(3):
+        for q in range(n):
+            kind = rng.integers(0, 4)
+            if kind == 0:
+                c.rx(float(rng.uniform(-2 * np.pi, 2 * np.pi)), q)
+            elif kind == 1:
+                c.rx(float(np.pi * rng.integers(-2, 3)), q)             # exact multiples of pi
+            elif kind == 2:
+                c.ry(float(rng.uniform(-np.pi, np.pi)), q)
+            else:
+                c.h(q)
+        for q in range(0, n - 1, 2):
+            c.rzz(float(rng.uniform(-np.pi, np.pi)), q, q + 1)
+        for q in range(1, n - 1, 2):
+            c.cz(q, q + 1)
+    c.measure(0, 0)
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_quantum_error(dtcsim.pauli_error([("X", 0.07), ("Y", 0.02), ("Z", 0.11), ("I", 0.80)]), ["rx", "ry", "h"])
+    _dm_check(c, nm, tol=1e-12)
+
+
+def test_dm_register_passes_c3_geometry(disorder):
+    """BASELINE config C3 (L = 12 ancilla-free chain, rho = 2^24 entries) on the emulator: two register passes per period,
+    conflict-free shared-memory accesses, <Z_6> equals the exact light-cone value."""
+    from dtcsim.backend import flatten_dm_segments
+    hs, phis = disorder[20][0][0][:12], disorder[20][1][0][:11]
+    t = 2
+    c = dtcsim.QuantumCircuit(12, 1)
+    for _ in range(t):
+        for i in range(12):
+            c.rx(np.pi * 0.97, i)
+        for i in range(0, 11, 2):
+            c.rzz(phis[i], i, i + 1)
+        for i in range(1, 11, 2):
+            c.rzz(phis[i], i, i + 1)
+        for i in range(12):
+            c.rz(hs[i], i)
+    c.measure(6, 0)
+    prog = compile_circuit(dtcsim.lower_level0(c), RC.noise_model(0.05), want_dm=True, optimize=False)
+    rho, info = emu.dm_run(prog.n, flatten_dm_segments(prog.dm_segments))
+    assert info["reg_passes"] == 2 * t and info["sweeps"] <= 2 * t + 1 and info["worst_conflict"] == 1
+    diag = np.real(np.diagonal(rho))
+    assert abs(diag.sum() - 1) < 1e-12
+    bit = prog.bit_of[6] if hasattr(prog, "bit_of") else 6
+    z = 1.0 - 2.0 * ((np.arange(1 << 12) >> bit) & 1)
+    assert abs(float((diag * z).sum()) - O.lightcone_zq(12, 0.97, hs, phis, t, 6, 0.05)) < 1e-10
