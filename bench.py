@@ -390,9 +390,10 @@ def sweep_leg(args, ctx, dist, rank, world, noise):
 
 
 # ------------------------------------------------------------------------------------------ config C3 (exact density matrix)
-def run_c3(args):
+def c3_record(args, device=0):
     """BASELINE config C3: L = 12 exact noisy density-matrix evolution (rho = 2^24 complex128 = 256 MiB), 20 periods,
-    hs_L20/phis_L20 row 0 entries 0..11, g = 0.97, p = 0.05, observable <Z_6>.  One step = the 20-period evolution."""
+    hs_L20/phis_L20 row 0 entries 0..11, g = 0.97, p = 0.05, observable <Z_6>.  One step = the 20-period evolution.
+    Returns the JSON record (`bench.py --config C3` prints it; the default C2 run carries it as the `c3` sub-record)."""
     import torch
     import dtcsim
     from dtcsim import backend
@@ -413,12 +414,12 @@ def run_c3(args):
     noise = dtcsim.NoiseModel()
     noise.add_all_qubit_quantum_error(dtcsim.depolarizing_error(P_NOISE, 1), ["u1", "u2", "u3"], warnings=False)
     prog = dtcsim.compile_circuit(dtcsim.lower_level0(c), dtcsim.as_noise_model(noise), want_dm=True)
-    ctx = backend.DeviceContext(0)
+    ctx = backend.DeviceContext(device)
     stats = {}
     for _ in range(max(args.warmup, 3)):
         rho = backend.run_density_matrix(ctx, prog, stats)
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(device)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     steps = max(args.steps, 20)
@@ -449,7 +450,12 @@ def run_c3(args):
                          "note": "achieved = periods/s x 2 x 16 B x 4^12 (SURVEY 8d byte model: ONE read + write of rho per period); "
                                  "per_sweep_gbs = what each of the sweeps_per_period passes over rho sustains"},
             "expect_z6_after_20_periods": ez, "trace": float(diag.sum()), "gpu_launches": steps * (2 * sweeps + 2), "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    return line
+
+
+def run_c3(args):
+    print(json.dumps(c3_record(args)), flush=True)
+
 
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
@@ -645,6 +651,14 @@ def run_ours(args):
             extra["sharded"] = sharded_leg(args, dist, rank, world, local, peak)
         except Exception as exc:                      # the headline line must still be printed
             extra["sharded"] = {"error": repr(exc)[:400]}
+    if rank == 0 and not args.no_c3:
+        # config C3 (exact density matrix, one GPU) rides along as a sub-record: ~0.3 s of device time
+        try:
+            c3 = c3_record(args, local)
+            extra["c3"] = {k: c3[k] for k in ("value", "unit", "steps", "ms_per_step", "config", "roofline",
+                                              "expect_z6_after_20_periods", "trace", "gpu_launches")}
+        except Exception as exc:
+            extra["c3"] = {"error": repr(exc)[:400]}
     if rank == 0:
         cpu = None
         if not args.no_cpu:
@@ -676,6 +690,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--resident", action="store_true", help="resident execution: all sweeps of a circuit in one persistent launch over L2-resident trajectory groups")
     ap.add_argument("--resident-mb", type=int, default=0, help="state MiB kept in flight per group in resident execution (default 64)")
+    ap.add_argument("--no-c3", action="store_true", help="skip the C3 (exact density matrix) sub-record")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-record")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded-statevector (C5) sub-record")
     ap.add_argument("--sharded-periods", type=int, default=10, help="C5: periods forward (+ the same number inverse)")
