@@ -149,3 +149,118 @@ def run_sweep(sim, L, g_list, hs, phis, t_values, echoes=(False, True), polariza
     tot = D.all_reduce_sum(tot, group, sim.ctx.device if world > 1 else None)
     out = tot[:-1].reshape(shape)
     return {"autocorr": out, "mean": out.mean(axis=3), "points": len(pts), "periods": int(round(tot[-1]))}
+
+
+# ----------------------------------------------------------------------------------- real-time adaptive g (ctrl-g.py, g-opt.py)
+def feedback_g(echo_val, target_echo, current_g, time_step, feedback_gain, g_min, g_max, exponential=True,
+               decay_compensation=0.1):
+    """Next-step g from the echo just measured: `calculate_exponential_g_adjustment` (ctrl-g.py:352-398, g-opt.py:429-474).
+
+    linear:       g + gain * (target - echo)
+    exponential:  [gain * error * exp(c t) + log term] * (1 + c t) added to g, the log term being gain * 0.1 * ln(target / echo)
+                  for 0.01 < echo < target, 0 for echo >= target and 2 * gain for echo <= 0.01;  clipped to [g_min, g_max]."""
+    err = target_echo - echo_val
+    if exponential:
+        adj = feedback_gain * err * math.exp(decay_compensation * time_step)
+        if echo_val > 0.01:
+            adj += feedback_gain * (math.log(target_echo / echo_val) if echo_val < target_echo else 0.0) * 0.1
+        else:
+            adj += feedback_gain * 2.0
+        new_g = current_g + adj * (1.0 + decay_compensation * time_step)
+    else:
+        new_g = current_g + feedback_gain * err
+    return float(min(max(new_g, g_min), g_max))
+
+
+def optimize_g(echo_of, target_echo, g_min, g_max, method="bounded", grid_points=10, xatol=1e-5, maxiter=500):
+    """g in [g_min, g_max] minimising (echo(g) - target)^2: `optimize_g_for_target_echo` (g-opt.py:354-393).
+
+    echo_of(list of g) -> list of echo values (one circuit per candidate; a list lets the grid go through ONE run(list)).
+    method "bounded": Brent's bounded scalar minimiser as the reference calls it (scipy `minimize_scalar(method='bounded')`,
+    one candidate per call -- sequential by construction); "grid": the reference's fallback `grid_search_g_optimization`
+    (g-opt.py:395-428: `grid_points` equidistant candidates, smallest |echo - target| wins, first one on ties)."""
+    if method == "bounded":
+        from scipy.optimize import minimize_scalar
+        res = minimize_scalar(lambda g: (echo_of([float(g)])[0] - target_echo) ** 2, bounds=(g_min, g_max), method="bounded",
+                              options={"xatol": xatol, "maxiter": maxiter})
+        if res.success:
+            return float(res.x)
+    elif method != "grid":
+        raise ValueError(f"unknown optimiser {method!r}")
+    cands = [float(x) for x in np.linspace(g_min, g_max, grid_points)]
+    dist = [abs(e - target_echo) for e in echo_of(cands)]
+    return cands[int(np.argmin(dist))]
+
+
+def run_adaptive(sim, L, hs, phis, T, g_initial=0.84, target_echo=1.0, feedback_gain=0.01, exponential_feedback=True,
+                 decay_compensation=0.1, g_min=0.84, g_max=1.0, use_optimization=False, optimizer="bounded", grid_points=10,
+                 qubit=None, initial_state="vacuum", shots=1024, seed_simulator=1234, rank=0, world=1, group=None,
+                 parallel="instances"):
+    """Real-time adaptive control of the kick strength: `get_instances_adaptive_realtime` (ctrl-g.py:443-490; with
+    use_optimization g-opt.py:500-556).
+
+    Per disorder instance, for t = 0..T-1: the circuits of step t use g_history + [g_t] (time-dependent g, ctrl-g.py:196-241)
+    for t+1 periods; forward and echo are evaluated (one pipelined run([forward, echo])), and g_{t+1} follows from the echo by
+    `feedback_g`, or -- use_optimization -- from `optimize_g` over the g of step t (the reference hands the optimiser the
+    history WITHOUT step t and t+1 periods, and uses the optimum as the next step's g; kept as is).
+
+    The steps of one instance depend on each other; what runs in parallel is (a) forward / echo / grid candidates of a step in
+    one run(list), (b) parallel="instances": instances dealt over the ranks, one all-reduce at the end, or
+    parallel="trajectories": every rank walks the same loop and each circuit's shots are split over the ranks
+    (dist.ShardedSampler; counts identical to one GPU).  Seeds are `seed + 1000003 * instance + 4099 * step + evaluation index`,
+    so the result does not depend on the number of ranks.
+
+    Returns {"forward", "echo", "g_history": float64 [n_inst, T]; "mean_forward", "mean_echo", "mean_g": [T];
+             "circuits": circuits evaluated over all ranks}."""
+    from . import dist as D
+    from .backend import compute_z_expectation
+    if parallel not in ("instances", "trajectories"):
+        raise ValueError("parallel must be 'instances' or 'trajectories'")
+    hs = np.atleast_2d(np.asarray(hs, dtype=np.float64))
+    phis = np.atleast_2d(np.asarray(phis, dtype=np.float64))
+    n_inst = hs.shape[0]
+    split_shots = parallel == "trajectories" and world > 1
+    sampler = D.ShardedSampler(sim, rank, world, group) if split_shots else None
+    mine = list(range(n_inst)) if (split_shots or world == 1) else D.deal_units(n_inst, rank, world)
+    out = np.zeros((3, n_inst, T), dtype=np.float64)
+    n_circ = 0
+
+    def expvals(circs, seeds):
+        if sampler is not None:
+            return [compute_z_expectation(sampler.run_counts(c, shots, s), 1)[0] for c, s in zip(circs, seeds)]
+        res = sim.run(circs, shots=shots, seed_simulator=[int(s) for s in seeds]).result()
+        return [compute_z_expectation(res.get_counts(j), 1)[0] for j in range(len(circs))]
+
+    for i in mine:
+        g_hist = []
+        g = float(g_initial)
+        for t in range(T):
+            gv = g_hist + [g]
+            g_hist.append(g)
+            base = int(seed_simulator) + 1000003 * i + 4099 * t
+            circs = [autocorr_circuit(L, g, hs[i], phis[i], t + 1, qubit, echo, "x", initial_state, g_values=gv)
+                     for echo in (False, True)]
+            fwd, ech = expvals(circs, [base, base + 1])
+            n_circ += 2
+            out[0, i, t], out[1, i, t], out[2, i, t] = fwd, ech, g
+            if t == T - 1:
+                break
+            if use_optimization:
+                evals = [0]
+
+                def echo_of(cands, _i=i, _t=t, _prev=g_hist[:-1], _base=base):
+                    cs = [autocorr_circuit(L, c, hs[_i], phis[_i], _t + 1, qubit, True, "x", initial_state, g_values=_prev + [c])
+                          for c in cands]
+                    seeds = [_base + 2 + evals[0] + k for k in range(len(cs))]
+                    evals[0] += len(cs)
+                    return expvals(cs, seeds)
+
+                g = optimize_g(echo_of, target_echo, g_min, g_max, optimizer, grid_points)
+                n_circ += evals[0]
+            else:
+                g = feedback_g(ech, target_echo, g, t, feedback_gain, g_min, g_max, bool(exponential_feedback), decay_compensation)
+    if not split_shots and world > 1:
+        tot = D.all_reduce_sum(np.concatenate([out.reshape(-1), [float(n_circ)]]), group, sim.ctx.device)
+        out, n_circ = tot[:-1].reshape(out.shape), int(round(tot[-1]))
+    return {"forward": out[0], "echo": out[1], "g_history": out[2], "mean_forward": out[0].mean(axis=0),
+            "mean_echo": out[1].mean(axis=0), "mean_g": out[2].mean(axis=0), "circuits": n_circ}

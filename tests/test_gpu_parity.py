@@ -775,6 +775,24 @@ def test_run_sweep_equals_per_point_oracle(disorder):
     assert np.allclose(res["mean"], res["autocorr"].mean(axis=3))
 
 
+def test_run_adaptive_equals_oracle_backed_loop(disorder):
+    """sweeps.run_adaptive (real-time adaptive g: ctrl-g.py:443-490 feedback, g-opt.py:354-428 grid optimiser) through the
+    device simulator == the same control loop on the oracle-backed stand-in simulator: every forward / echo value and the
+    whole g history are identical (counts are bit-identical under the shared Philox contract, the control law is
+    deterministic).  L = 6 runs the trajectory path (shots < 2^n), L = 4 the exact density-matrix path."""
+    from test_dist_cpu import _OracleSim
+    sim = dtcsim.AerSimulator(noise_model=RC.noise_model(0.05), device="GPU", cuStateVec_enable=True)
+    for L, shots, kw in ((6, 64, dict(feedback_gain=0.05, exponential_feedback=True)),
+                         (4, 256, dict(feedback_gain=0.05, exponential_feedback=False, g_max=0.95)),
+                         (4, 128, dict(use_optimization=True, optimizer="grid", grid_points=4))):
+        hs, phis = disorder[20][0][:2, :L], disorder[20][1][:2, :L - 1]
+        got = dtcsim.run_adaptive(sim, L, hs, phis, 4, shots=shots, seed_simulator=77, **kw)
+        want = dtcsim.run_adaptive(_OracleSim(), L, hs, phis, 4, shots=shots, seed_simulator=77, **kw)
+        for key in ("forward", "echo", "g_history"):
+            assert np.array_equal(got[key], want[key]), (L, key)
+        assert got["circuits"] == want["circuits"]
+
+
 def test_readout_errors_counts_vs_oracle(disorder):
     """Classical readout errors (the part of device-calibrated noise, fast.py:77-78, that is not a channel on the state):
     counts bit-identical to the oracle under the shared Philox contract on all three execution paths (density matrix,
