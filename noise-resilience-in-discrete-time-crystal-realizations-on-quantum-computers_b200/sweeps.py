@@ -264,3 +264,68 @@ def run_adaptive(sim, L, hs, phis, T, g_initial=0.84, target_echo=1.0, feedback_
         out, n_circ = tot[:-1].reshape(out.shape), int(round(tot[-1]))
     return {"forward": out[0], "echo": out[1], "g_history": out[2], "mean_forward": out[0].mean(axis=0),
             "mean_echo": out[1].mean(axis=0), "mean_g": out[2].mean(axis=0), "circuits": n_circ}
+
+
+# ----------------------------------------------------------------------------------- energy sweeps (energy.py)
+def energy_circuit(L, g, hs, phis, t, echo=False, initial_state="vacuum", transpile=True):
+    """The L-qubit circuit of the energy scripts (energy.py:111-135): no ancilla, t periods of U_F on qubits 0..L-1, then
+    -- echo -- t inverse periods.  ("neel" flips the qubits of even index >= 2 below L; the reference's own loop runs to
+    index L, which its L-qubit circuit does not have, so only "vacuum" ever ran there.)"""
+    circ = QuantumCircuit(L)
+    if initial_state == "neel":
+        for i in range(2, L, 2):
+            circ.x(i)
+    elif initial_state != "vacuum":
+        raise ValueError(f"unknown initial state {initial_state!r}")
+    sub = QuantumCircuit(L)
+    for i in range(L):
+        sub.rx(PI * g, i)
+    for i in range(0, L - 1, 2):
+        sub.rzz(float(phis[i]), i, i + 1)
+    for i in range(1, L - 1, 2):
+        sub.rzz(float(phis[i]), i, i + 1)
+    for i in range(L):
+        sub.rz(float(hs[i]), i)
+    for _ in range(t):
+        circ.append(sub, range(L))
+    if echo:
+        inv = sub.inverse()
+        for _ in range(t):
+            circ.append(inv, range(L))
+    return lower_level0(circ) if transpile else circ
+
+
+def run_energy_sweep(sim, L, g, hs, phis, t_values, echo=False, initial_state="vacuum", precision=None, seed_simulator=None,
+                     rank=0, world=1, group=None):
+    """<H>(t) / L of the kicked-Ising Hamiltonian along the Floquet evolution: the loops of the energy scripts
+    (`get_single_out` / `get_instances`, energy.py:173-195; per-site energy as written to the CSV, energy.py:218-231).
+
+    Every (instance, t) point is one estimator pub: `BackendEstimatorV2(sim).run([(energy_circuit, dtc_hamiltonian)])`
+    (energy.py:166-171; Z / ZZ terms share one measurement circuit, the X terms another; 4096 shots per circuit at the
+    default precision).  Points are dealt over the ranks, one all-reduce at the end.  The noise model is the simulator's; the
+    reference transpiles at the preset manager's default level (energy.py:152-158), which merges single-qubit gates and so moves
+    the noisy-gate sites -- no fixture pins that placement; circuits here are lowered at level 0 like the
+    autocorrelation scripts'.
+    Returns {"energy_per_site": float64 [n_inst, len(t_values)], "mean": [len(t_values)], "stds": same shape as
+    energy_per_site (standard error of <H>/L from the shot statistics), "points", "circuits"}."""
+    from . import dist as D
+    from .estimator import BackendEstimatorV2, dtc_hamiltonian
+    hs = np.atleast_2d(np.asarray(hs, dtype=np.float64))
+    phis = np.atleast_2d(np.asarray(phis, dtype=np.float64))
+    n_inst = hs.shape[0]
+    pts = [(i, k) for i in range(n_inst) for k in range(len(t_values))]
+    out = np.zeros((2, n_inst, len(t_values)), dtype=np.float64)
+    n_circ = 0
+    for p in D.deal_units(len(pts), rank, world):
+        i, k = pts[p]
+        opts = {} if seed_simulator is None else {"seed_simulator": int(seed_simulator) + 7919 * p}
+        est = BackendEstimatorV2(sim, options=opts)
+        circ = energy_circuit(L, g, hs[i], phis[i], int(t_values[k]), echo, initial_state)
+        res = est.run([(circ, dtc_hamiltonian(L, g, phis[i], hs[i]))], precision=precision).result()[0]
+        out[0, i, k] = float(res.data.evs) / L
+        out[1, i, k] = float(res.data.stds) / L
+        n_circ += res.metadata["circuits"]
+    if world > 1:
+        tot = D.all_reduce_sum(np.concatenate([out.reshape(-1), [float(n_circ)]]), group, sim.ctx.device)
+        out, n_circ = tot[:-1].reshape(out.shape), int(round(tot[-1]))
+    return {"energy_per_site": out[0], "mean": out[0].mean(axis=0), "stds": out[1], "points": len(pts), "circuits": n_circ}

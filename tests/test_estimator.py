@@ -164,3 +164,26 @@ def test_estimator_y_and_mixed_terms(disorder):
     exact = _exact_energy([o.astuple() for o in circ.ops], L, terms)
     assert pub.metadata["shots"] == 16384
     assert abs(float(pub.data.evs) - exact) < 4.5 * float(pub.data.stds) + 1e-12, (float(pub.data.evs), exact)
+
+
+def test_run_energy_sweep_vs_exact_energy(disorder):
+    """sweeps.run_energy_sweep (energy.py:173-195 loops: instance x t, <H>/L per point through the estimator) on the
+    oracle-backed stand-in simulator: every point within 5 standard errors of Tr(rho H)/L of the noisy density matrix, the
+    t = 0 Z-part exact, shape / bookkeeping as documented."""
+    from test_dist_cpu import _OracleSim
+    L, g = 4, 0.97
+    hs, phis = disorder[20][0][:2, :L], disorder[20][1][:2, :L - 1]
+    tv = [0, 1, 3]
+    res = dtcsim.run_energy_sweep(_OracleSim(), L, g, hs, phis, tv, precision=1 / 32, seed_simulator=3)
+    assert res["energy_per_site"].shape == (2, 3) and res["points"] == 6 and res["circuits"] == 12
+    assert np.allclose(res["mean"], res["energy_per_site"].mean(axis=0))
+    noise = O.PauliNoise.depolarizing(0.05)
+    for i in range(2):
+        ham = E.dtc_hamiltonian(L, g, phis[i], hs[i])
+        for k, t in enumerate(tv):
+            ops = [o.astuple() for o in dtcsim.energy_circuit(L, g, hs[i], phis[i], t, transpile=False).ops]
+            want = _exact_energy(ops, L, ham, noise) / L
+            assert abs(res["energy_per_site"][i, k] - want) < 5 * max(res["stds"][i, k], 1e-3), (i, t)
+    # echo circuits: t periods forward and t back
+    c = dtcsim.energy_circuit(L, g, hs[0], phis[0], 2, echo=True, transpile=False)
+    assert len(c.ops) == 4 * (L + (L - 1) + L)
