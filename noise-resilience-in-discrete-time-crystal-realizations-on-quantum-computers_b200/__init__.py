@@ -9,8 +9,8 @@ from .ir import QuantumCircuit, Op, from_qasm2, from_qiskit, as_circuit         
 from .lowering import generate_preset_pass_manager, lower_level0, SNAKE_LAYOUT   # noqa: F401
 from .noise import NoiseModel, ReadoutError, depolarizing_error, pauli_error, as_noise_model   # noqa: F401
 from .plan import compile_circuit, Program                                       # noqa: F401
-from .sweeps import (autocorr_circuit, energy_circuit, feedback_g, floquet_period, optimize_g, run_adaptive,   # noqa: F401
-                     run_energy_sweep, run_sweep, xy_cycle_schedule)
+from .sweeps import (autocorr_circuit, energy_circuit, expz_circuit, feedback_g, floquet_period, optimize_g,   # noqa: F401
+                     run_adaptive, run_energy_sweep, run_expz_sweep, run_sweep, xy_cycle_schedule)
 from .estimator import BackendEstimatorV2, dtc_hamiltonian                        # noqa: F401
 
 __version__ = "0.1.0"

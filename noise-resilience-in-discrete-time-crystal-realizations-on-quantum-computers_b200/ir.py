@@ -114,6 +114,21 @@ class QuantumCircuit:
 
     compose = append
 
+    def qasm(self):
+        """OpenQASM-2 text of the circuit (the form dtc_qasm.py:95-107 writes to disk and reads back with
+        `QuantumCircuit.from_qasm_str`); `from_qasm2(circ.qasm())` returns the same op list.  Parameters are written with
+        17 significant digits, so the round trip is exact."""
+        lines = ["OPENQASM 2.0;", 'include "qelib1.inc";', f"qreg q[{self.num_qubits}];"]
+        if self.num_clbits:
+            lines.append(f"creg c[{self.num_clbits}];")
+        for op in self.ops:
+            if op.name == "measure":
+                lines.append(f"measure q[{op.qubits[0]}] -> c[{op.clbits[0]}];")
+                continue
+            par = "(" + ",".join(repr(float(x)) for x in op.params) + ")" if op.params else ""
+            lines.append(f"{op.name}{par} " + ",".join(f"q[{q}]" for q in op.qubits) + ";")
+        return "\n".join(lines) + "\n"
+
     def inverse(self):
         """Reversed op order with inverted gates (fast.py:141 ``UF_subcircuit.inverse()``)."""
         inv = QuantumCircuit(self.num_qubits, self.num_clbits, self.name + "_dg")

@@ -329,3 +329,63 @@ def run_energy_sweep(sim, L, g, hs, phis, t_values, echo=False, initial_state="v
         tot = D.all_reduce_sum(np.concatenate([out.reshape(-1), [float(n_circ)]]), group, sim.ctx.device)
         out, n_circ = tot[:-1].reshape(out.shape), int(round(tot[-1]))
     return {"energy_per_site": out[0], "mean": out[0].mean(axis=0), "stds": out[1], "points": len(pts), "circuits": n_circ}
+
+
+# ----------------------------------------------------------------------------------- site-resolved <Z_i(t)> (dtc_qasm.py)
+def expz_circuit(L, g, hs, phis, t, state="0"):
+    """The circuit dtc_qasm.py sends through OpenQASM (dtc_qasm.py:70-91): L qubits, state "1" flips qubit L // 2, t periods
+    of U_F, every qubit measured into its own classical bit."""
+    circ = QuantumCircuit(L, L)
+    if state == "1":
+        circ.x(L // 2)
+    elif state != "0":
+        raise ValueError(f"unknown state {state!r}")
+    for _ in range(t):
+        for i in range(L):
+            circ.rx(PI * g, i)
+        for i in range(0, L - 1, 2):
+            circ.rzz(float(phis[i]), i, i + 1)
+        for i in range(1, L - 1, 2):
+            circ.rzz(float(phis[i]), i, i + 1)
+        for i in range(L):
+            circ.rz(float(hs[i]), i)
+    for i in range(L):
+        circ.measure(i, i)
+    return circ
+
+
+def run_expz_sweep(sim, L, g, hs, phis, T, state="0", shots=1024, seed_simulator=1234, via_qasm=True, exact=False,
+                   rank=0, world=1, group=None, chunk=32):
+    """<Z_site(t)> for t = 1..T-1 and every site: `get_single_out` / `get_instances` of dtc_qasm.py (:123-160).
+
+    Each point is one L-qubit circuit measured on all qubits; <Z_i> = (N0 - N1) / shots of classical bit i
+    (`compute_z_expectation`, dtc_qasm.py:105-121).  via_qasm=True hands the simulator the OpenQASM-2 text the script writes
+    (`expz_circuit(...).qasm()`, parsed by `ir.from_qasm2`), exactly the reference's hand-over format; exact=True returns the
+    simulated probabilities' <Z_i> instead of the shot estimate (`Result.expectation_z`).  Points (instance, t) are dealt over
+    the ranks, one all-reduce at the end; seeds are seed + global point index.
+    Returns {"expz": float64 [n_inst, L, T-1] (the layout `savecsv` writes: row = (instance, site), column = t),
+             "mean": [L, T-1], "points"}."""
+    from . import dist as D
+    from .backend import compute_z_expectation
+    hs = np.atleast_2d(np.asarray(hs, dtype=np.float64))
+    phis = np.atleast_2d(np.asarray(phis, dtype=np.float64))
+    n_inst = hs.shape[0]
+    pts = [(i, t) for i in range(n_inst) for t in range(1, T)]
+    mine = D.deal_units(len(pts), rank, world)
+    out = np.zeros((n_inst, L, max(T - 1, 0)), dtype=np.float64)
+    for a in range(0, len(mine), chunk):
+        idx = mine[a:a + chunk]
+        circs = []
+        for k in idx:
+            i, t = pts[k]
+            c = expz_circuit(L, g, hs[i], phis[i], t, state)
+            circs.append(c.qasm() if via_qasm else c)
+        if not circs:
+            continue
+        res = sim.run(circs, shots=shots, seed_simulator=[int(seed_simulator) + int(k) for k in idx]).result()
+        for j, k in enumerate(idx):
+            i, t = pts[k]
+            out[i, :, t - 1] = res.expectation_z(j)[:L] if exact else compute_z_expectation(res.get_counts(j), L)
+    if world > 1:
+        out = D.all_reduce_sum(out.reshape(-1), group, sim.ctx.device).reshape(out.shape)
+    return {"expz": out, "mean": out.mean(axis=0), "points": len(pts)}

@@ -147,3 +147,37 @@ def test_run_adaptive_two_ranks_equal_one_rank():
             p.join(timeout=60)
             assert p.exitcode == 0
     assert results[0] == results[1] and results[0][3] == 3 * 3 * 2
+
+
+# ----------------------------------------------------------------------------------- dtc_qasm.py driver
+def test_qasm_export_round_trip(disorder):
+    """QuantumCircuit.qasm() -> ir.from_qasm2 returns the same op list, parameters bit for bit (dtc_qasm.py:95-107 hand-over)."""
+    hs, phis = disorder[20][0][0][:6], disorder[20][1][0][:5]
+    c = dtcsim.expz_circuit(6, 0.94, hs, phis, 3, state="1")
+    back = dtcsim.from_qasm2(c.qasm())
+    assert back.num_qubits == 6 and back.num_clbits == 6
+    assert [o.astuple() for o in back.ops] == [o.astuple() for o in c.ops]
+    # the circuit is the oracle's restatement of dtc_qasm.py:70-91, gate for gate
+    from oracle import dtc_circuits as C
+    ops, n, nc = C.dtc_qasm_gates("1", 6, 0.94, hs, phis, 3)
+    assert [o.astuple() for o in c.ops] == [(a, tuple(b), tuple(p), tuple(d)) for a, b, p, d in ops]
+    t = dtcsim.autocorr_circuit(4, 0.97, hs, phis, 2, echo=True)          # a transpiled (u2 / u3 / cx / rz) circuit as well
+    assert [o.astuple() for o in dtcsim.from_qasm2(t.qasm()).ops] == [o.astuple() for o in t.ops]
+
+
+def test_run_expz_sweep_layout_and_values(disorder):
+    """run_expz_sweep: [instance, site, t-1] from L-bit counts; every entry = the oracle's counts of that point's circuit."""
+    from oracle import oracle as O
+    L, T = 4, 4
+    hs, phis = disorder[20][0][:2, :L], disorder[20][1][:2, :L - 1]
+    res = dtcsim.run_expz_sweep(_OracleSim(), L, 0.94, hs, phis, T, state="1", shots=128, seed_simulator=40, via_qasm=False)
+    assert res["expz"].shape == (2, L, T - 1) and res["points"] == 2 * (T - 1)
+    noise = O.PauliNoise.depolarizing(0.05)
+    k = 0
+    for i in range(2):
+        for t in range(1, T):
+            c = dtcsim.expz_circuit(L, 0.94, hs[i], phis[i], t, "1")
+            counts = O.run_counts([o.astuple() for o in c.ops], L, L, shots=128, noise=noise, seed=40 + k)[0]
+            assert np.array_equal(res["expz"][i, :, t - 1], O.compute_z_expectation(counts, L))
+            k += 1
+    assert np.allclose(res["mean"], res["expz"].mean(axis=0))

@@ -793,6 +793,28 @@ def test_run_adaptive_equals_oracle_backed_loop(disorder):
         assert got["circuits"] == want["circuits"]
 
 
+def test_run_expz_sweep_through_qasm_equals_oracle(disorder):
+    """sweeps.run_expz_sweep (dtc_qasm.py:123-160: every (instance, t) circuit handed over as OpenQASM-2 text, L-bit counts,
+    per-site <Z>) through the device simulator == the oracle's counts of the same circuits; exact=True agrees with the
+    shot estimate within the family-wise bound."""
+    L, T = 6, 4
+    hs, phis = disorder[20][0][:2, :L], disorder[20][1][:2, :L - 1]
+    sim = dtcsim.AerSimulator(noise_model=RC.noise_model(0.05), device="GPU", cuStateVec_enable=True)
+    # the untranspiled rx / rzz / rz circuit carries no u1/u2/u3, so the run is noise-free like the reference's ideal QPU-bound text
+    res = dtcsim.run_expz_sweep(sim, L, 0.94, hs, phis, T, state="1", shots=512, seed_simulator=40)
+    assert res["expz"].shape == (2, L, T - 1)
+    k = 0
+    for i in range(2):
+        for t in range(1, T):
+            c = dtcsim.expz_circuit(L, 0.94, hs[i], phis[i], t, "1")
+            counts = O.run_counts([o.astuple() for o in c.ops], L, L, shots=512, noise=None, seed=40 + k)[0]
+            assert np.array_equal(res["expz"][i, :, t - 1], O.compute_z_expectation(counts, L)), (i, t)
+            k += 1
+    ex = dtcsim.run_expz_sweep(sim, L, 0.94, hs, phis, T, state="1", shots=512, seed_simulator=40, exact=True)
+    z = np.abs(ex["expz"] - res["expz"]) / np.sqrt(np.maximum(1 - ex["expz"] ** 2, 1e-3) / 512)
+    assert z.max() < family_z(z.size)
+
+
 def test_readout_errors_counts_vs_oracle(disorder):
     """Classical readout errors (the part of device-calibrated noise, fast.py:77-78, that is not a channel on the state):
     counts bit-identical to the oracle under the shared Philox contract on all three execution paths (density matrix,
