@@ -651,8 +651,8 @@ def run_ours(args):
             extra["sharded"] = sharded_leg(args, dist, rank, world, local, peak)
         except Exception as exc:                      # the headline line must still be printed
             extra["sharded"] = {"error": repr(exc)[:400]}
-    if rank == 0 and not args.no_c3:
-        # config C3 (exact density matrix, one GPU) rides along as a sub-record: ~0.3 s of device time
+    if world == 1 and not args.no_c3:
+        # config C3 (exact density matrix, fits one GPU: replicas only) rides along as a sub-record of the 1-GPU run
         try:
             c3 = c3_record(args, local)
             extra["c3"] = {k: c3[k] for k in ("value", "unit", "steps", "ms_per_step", "config", "roofline",
