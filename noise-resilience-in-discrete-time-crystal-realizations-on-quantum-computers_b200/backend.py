@@ -27,6 +27,7 @@ from .plan import compile_circuit
 from . import philox_np
 
 MAX_DM_QUBITS = 13
+PIPELINE_DEPTH = 8        # circuits of a run(list) the host may enqueue ahead of the one whose results it fetches
 MAX_PROB_QUBITS = 12
 
 
@@ -377,23 +378,24 @@ class DTCSimulator:
             seeds = [int(seed) + i for i in range(len(circ_list))]
         nm = as_noise_model(self.noise_model if noise_model is None else noise_model)
         method = self.method if method is None else method
-        # A list of circuits is pipelined: circuit i+1 is compiled and enqueued while the GPU still works
-        # on circuit i, whose results are then fetched on a side stream.  Counts are identical to one-by-one calls.
+        # A list of circuits is pipelined: the host compiles and enqueues circuits ahead of the GPU -- up to
+        # PIPELINE_DEPTH circuits are in flight before the oldest one's results are fetched (on a side stream), so a slow
+        # compile or a host hiccup does not leave the GPU idle.  Counts are identical to one-by-one calls.
         exps = [None] * len(circ_list)
-        pending = None
+        pending = []
         handles = []
         try:
             for i, c in enumerate(circ_list):
                 r = self._run_one(as_circuit(c), shots, seeds[i], nm, method, getattr(c, "name", None), handles)
-                if pending is not None:
-                    exps[pending[0]] = pending[1]()
-                    pending = None
                 if callable(r):
-                    pending = (i, r)
+                    pending.append((i, r))
                 else:
                     exps[i] = r
-            if pending is not None:
-                exps[pending[0]] = pending[1]()
+                while len(pending) > PIPELINE_DEPTH:
+                    j, fetch = pending.pop(0)
+                    exps[j] = fetch()
+            for j, fetch in pending:
+                exps[j] = fetch()
         finally:
             for h in handles:
                 h.close()
