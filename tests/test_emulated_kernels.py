@@ -331,3 +331,40 @@ def test_dm_register_passes_c3_geometry(disorder):
     bit = prog.bit_of[6] if hasattr(prog, "bit_of") else 6
     z = 1.0 - 2.0 * ((np.arange(1 << 12) >> bit) & 1)
     assert abs(float((diag * z).sum()) - O.lightcone_zq(12, 0.97, hs, phis, t, 6, 0.05)) < 1e-10
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_dm_planner_fuzz_random_segments(seed):
+    """Random segment programs straight into the planner: arbitrary qubit subsets per layer (groups that start above qubit 0,
+    odd group sizes, single-qubit rounds with spare bits), repeated diagonal segments, channels without a rotation and
+    rotations without a channel, quarter / half / full turns.  Register passes and element-per-thread passes against numpy."""
+    from types import SimpleNamespace
+    from dtcsim.backend import flatten_dm_segments
+    rng = np.random.default_rng(900 + seed)
+    n = 6 + seed % 4
+    segs = []
+    for _ in range(6):
+        kind = rng.integers(0, 4)
+        qs = sorted(rng.choice(n, size=rng.integers(1, n + 1), replace=False).tolist())
+        if kind == 0:
+            angles = [float(rng.choice([rng.uniform(-7, 7), np.pi / 2, -np.pi / 2, np.pi, 2 * np.pi, 1e-9])) for _ in qs]
+            segs.append(("R", list(zip(qs, angles))))
+        elif kind == 1:
+            segs.append(("N", [(q, tuple(rng.dirichlet([8, 1, 1, 1])[1:])) for q in qs]))
+        elif kind == 2:
+            segs.append(("R", [(q, float(rng.uniform(-3, 3))) for q in qs]))
+            segs.append(("N", [(q, (0.0125, 0.0125, 0.0125)) for q in qs[::2]]))
+        else:
+            d1 = {int(q): float(rng.uniform(-3, 3)) for q in qs}
+            d2 = {(int(a), int(a) + 1): float(rng.uniform(-3, 3)) for a in range(0, n - 1, 2) if rng.random() < 0.7}
+            segs.append(("D", d1, d2))
+            if rng.random() < 0.3:
+                segs.append(("D", {0: 0.3}, {}))
+    # a non-trivial start: put every qubit into a superposition first
+    segs = [("R", [(q, 0.7 + 0.1 * q) for q in range(n)])] + segs
+    want = PI.run_dm(SimpleNamespace(dm_segments=segs), n)
+    flat = flatten_dm_segments(segs)
+    for reg, wide in ((True, True), (True, False), (False, True)):
+        rho, info = emu.dm_run(n, flat, reg_passes=reg, wide13=wide)
+        assert np.abs(rho.T - want).max() < 1e-12, (reg, wide)
+        assert (info["reg_passes"] > 0) == reg
