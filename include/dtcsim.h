@@ -211,6 +211,11 @@ int dtc_dm_rot(void *rho, int n, int qubit, double theta, void *stream);        
 int dtc_dm_diag(void *rho, int n, int n1, const int32_t *q1, const double *a,
                 int n2, const int32_t *qi, const int32_t *qj, const double *b, void *stream);
 int dtc_dm_pauli_channel(void *rho, int n, int qubit, double px, double py, double pz, void *stream);
+/* General single-qubit channel (thermal relaxation, amplitude damping, Kraus sets, reset: the non-Pauli part of a
+ * device-calibrated noise model, NoiseModel.from_backend, fast.py:77-78): superop = 4 x 4 complex matrix, row major, (re, im)
+ * pairs (32 doubles, host), acting on the (row bit, column bit) block of `qubit` with block index = row + 2 col:
+ * out[i] = sum_j superop[i][j] in[j].  One sweep of rho. */
+int dtc_dm_superop(void *rho, int n, int qubit, const double *superop, void *stream);
 int dtc_dm_probs(const void *rho, int n, int k, const int32_t *qubits, double *out, void *stream);
 /* A whole density-matrix program in one call (Aer method density_matrix inside run(), fast.py:211, for n <= 13).  Segments in
  * circuit order: seg_type[i] = 0 rotations RX(val) on q0, 1 diagonal terms exp(-i val Z_q0 / 2) (q1 < 0) or

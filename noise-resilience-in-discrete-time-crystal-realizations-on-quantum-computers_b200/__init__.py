@@ -7,7 +7,8 @@ the C ABI in ``include/dtcsim.h``; PyTorch only allocates device buffers and pro
 """
 from .ir import QuantumCircuit, Op, from_qasm2, from_qiskit, as_circuit          # noqa: F401
 from .lowering import generate_preset_pass_manager, lower_level0, SNAKE_LAYOUT   # noqa: F401
-from .noise import NoiseModel, ReadoutError, depolarizing_error, pauli_error, as_noise_model   # noqa: F401
+from .noise import (NoiseModel, ReadoutError, ChannelError, depolarizing_error, pauli_error, kraus_error,   # noqa: F401
+                    amplitude_damping_error, phase_damping_error, thermal_relaxation_error, as_noise_model)
 from .plan import compile_circuit, Program                                       # noqa: F401
 from .sweeps import (autocorr_circuit, energy_circuit, expz_circuit, feedback_g, floquet_period, optimize_g,   # noqa: F401
                      run_adaptive, run_energy_sweep, run_expz_sweep, run_sweep, xy_cycle_schedule)

@@ -213,7 +213,7 @@ def sample_rows(ctx, probs, n_samples, seed, traj_offset):
 
 
 def flatten_dm_segments(segments):
-    """prog.dm_segments -> the flat arrays of dtc_dm_run (seg_type, seg_off, q0, q1, val, probs)."""
+    """prog.dm_segments (R / D / N segments only) -> the flat arrays of dtc_dm_run (seg_type, seg_off, q0, q1, val, probs)."""
     seg_type, seg_off, q0, q1, val, probs = [], [0], [], [], [], []
     for seg in segments:
         if seg[0] == "R":
@@ -226,19 +226,39 @@ def flatten_dm_segments(segments):
                 q0.append(q); q1.append(-1); val.append(a); probs.append((0.0, 0.0, 0.0))
             for (i, j), b in seg[2].items():
                 q0.append(i); q1.append(j); val.append(b); probs.append((0.0, 0.0, 0.0))
-        else:
+        elif seg[0] == "N":
             seg_type.append(2)
             for q, pr in seg[1]:
                 q0.append(q); q1.append(-1); val.append(0.0); probs.append(tuple(pr))
+        else:
+            raise ValueError(f"segment type {seg[0]!r} does not go through dtc_dm_run")
         seg_off.append(len(q0))
     return (np.asarray(seg_type, dtype=np.int32), np.asarray(seg_off, dtype=np.int32), np.asarray(q0, dtype=np.int32),
             np.asarray(q1, dtype=np.int32), np.asarray(val, dtype=np.float64),
             np.asarray(probs, dtype=np.float64).reshape(-1, 3))
 
 
+def split_dm_segments(segments):
+    """Runs of R / D / N segments (one dtc_dm_run call each) separated by the "K" segments of non-Pauli channels
+    (one dtc_dm_superop call per channel): [("run", [segments]) | ("K", [(qubit, superoperator), ...]), ...]."""
+    out, cur = [], []
+    for seg in segments:
+        if seg[0] == "K":
+            if cur:
+                out.append(("run", cur))
+                cur = []
+            out.append(("K", list(seg[1])))
+        else:
+            cur.append(seg)
+    if cur:
+        out.append(("run", cur))
+    return out
+
+
 def run_density_matrix(ctx, prog, stats=None):
     """Exact noisy evolution of rho (Aer method density_matrix); returns the rho tensor (2^n x 2^n, [col,row]).
-    One C-ABI call for the whole program (dtc_dm_run); stats["sweeps"] = passes over rho it made."""
+    One C-ABI call for the whole program (dtc_dm_run) -- or one per stretch between non-Pauli channels, each of which is one
+    sweep of dtc_dm_superop; stats["sweeps"] = passes over rho made."""
     torch = ctx.torch
     lib = capi.load()
     n = prog.n
@@ -247,13 +267,22 @@ def run_density_matrix(ctx, prog, stats=None):
     rho = ctx.empty(1 << (2 * n), torch.complex128)
     s = ctx.stream
     capi.check(lib.dtc_dm_init(rho.data_ptr(), n, 0, s))
-    st, so, q0, q1, val, pr = flatten_dm_segments(prog.dm_segments)
-    sweeps = ctypes.c_int(0)
-    capi.check(lib.dtc_dm_run(rho.data_ptr(), n, len(st), st.ctypes.data_as(capi.c_i32p), so.ctypes.data_as(capi.c_i32p),
-                              q0.ctypes.data_as(capi.c_i32p), q1.ctypes.data_as(capi.c_i32p),
-                              val.ctypes.data_as(capi.c_f64p), pr.ctypes.data_as(capi.c_f64p), ctypes.byref(sweeps), s))
+    total = 0
+    for kind, payload in split_dm_segments(prog.dm_segments):
+        if kind == "K":
+            for q, S in payload:
+                Sf = np.ascontiguousarray(np.asarray(S, dtype=np.complex128).reshape(16)).view(np.float64)
+                capi.check(lib.dtc_dm_superop(rho.data_ptr(), n, int(q), Sf.ctypes.data_as(capi.c_f64p), s))
+                total += 1
+            continue
+        st, so, q0, q1, val, pr = flatten_dm_segments(payload)
+        sweeps = ctypes.c_int(0)
+        capi.check(lib.dtc_dm_run(rho.data_ptr(), n, len(st), st.ctypes.data_as(capi.c_i32p), so.ctypes.data_as(capi.c_i32p),
+                                  q0.ctypes.data_as(capi.c_i32p), q1.ctypes.data_as(capi.c_i32p),
+                                  val.ctypes.data_as(capi.c_f64p), pr.ctypes.data_as(capi.c_f64p), ctypes.byref(sweeps), s))
+        total += sweeps.value
     if stats is not None:
-        stats["sweeps"] = sweeps.value
+        stats["sweeps"] = total
     return rho
 
 
@@ -419,7 +448,19 @@ class DTCSimulator:
         full_nm = nm
         if nm is not None and not nm.has_gate_noise():
             nm = None                      # readout errors only: the evolution is ideal, the recorded bits are not
-        prog0 = self._compiled(circ, nm)
+        channels = nm is not None and nm.has_channel_noise()
+        if channels:
+            # non-Pauli channels (thermal relaxation, ...) exist only as density-matrix segments: exact rho whatever the
+            # shot count (Aer would sample Kraus trajectories for shots <= 2^n; the outcome distribution is the same)
+            if method not in ("automatic", None, "density_matrix"):
+                raise ValueError("non-Pauli noise channels need method='density_matrix' (or 'automatic')")
+            prog0 = self._compiled(circ, nm, want_dm=True)
+            if prog0.n > MAX_DM_QUBITS:
+                raise ValueError(f"non-Pauli noise channels run on the density-matrix method only: at most {MAX_DM_QUBITS} "
+                                 f"active qubits (got {prog0.n})")
+            method = "density_matrix"
+        else:
+            prog0 = self._compiled(circ, nm)
         n = prog0.n
         method = self._choose_method(method, n, shots, nm)
         # classical readout errors (device-calibrated noise, fast.py:77-78): assignment matrix per classical bit

@@ -70,6 +70,7 @@ _SIGS = {
                                    c_f64p, c_vp]),
     "dtc_dm_pauli_channel": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                             ctypes.c_double, c_vp]),
+    "dtc_dm_superop": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_f64p, c_vp]),
     "dtc_dm_probs": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_i32p, c_vp, c_vp]),
     "dtc_dm_run": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_i32p, c_i32p, c_i32p, c_i32p, c_f64p, c_f64p,
                                   ctypes.POINTER(ctypes.c_int), c_vp]),

@@ -40,6 +40,33 @@ struct DmDiagTerms {
     double b[DTC_MAXT];
 };
 
+// ---- general single-qubit channel (non-Pauli part of a device noise model): 4 x 4 complex superoperator on the block
+// (row bit q, column bit q) with block index = row + 2 col; thread i handles the i-th block
+struct DmSuperop { double re[16], im[16]; };
+DTC_HD void dm_superop_thread(double2* rho, int n, int q, const DmSuperop& S, long long i) {
+    const int b0 = q, b1 = q + n;
+    u64 x = (u64)i;
+    const u64 low0 = (1ull << b0) - 1;
+    x = ((x & ~low0) << 1) | (x & low0);
+    const u64 low1 = (1ull << b1) - 1;
+    x = ((x & ~low1) << 1) | (x & low1);
+    const u64 idx[4] = {x, x | (1ull << b0), x | (1ull << b1), x | (1ull << b0) | (1ull << b1)};
+    double2 e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e[k] = rho[idx[k]];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const double sr = S.re[4 * r + c], si = S.im[4 * r + c];
+            acc.x = fma(sr, e[c].x, fma(-si, e[c].y, acc.x));
+            acc.y = fma(sr, e[c].y, fma(si, e[c].x, acc.y));
+        }
+        rho[idx[r]] = acc;
+    }
+}
+
 // ---- register-resident passes
 struct DmRegOp {
     double t;                        // tan form of the rotation (0: none)

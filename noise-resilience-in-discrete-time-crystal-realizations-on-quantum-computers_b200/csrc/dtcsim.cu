@@ -1242,6 +1242,13 @@ __global__ void k_dm_channel(double2* __restrict__ rho, int n, int q, double px,
 }
 
 
+// general single-qubit channel: 4 x 4 complex superoperator on the (row bit q, column bit q) block (csrc/dtc_dm.cuh)
+__global__ void k_dm_superop(double2* __restrict__ rho, int n, int q, const __grid_constant__ DmSuperop S) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1ll << (2 * n - 2))) return;
+    dm_superop_thread(rho, n, q, S, i);
+}
+
 // ---- density matrix, fused: one sweep of rho applies, to up to six qubits at once, the rotation on the row bit, its
 // conjugate on the column bit and the Pauli channel that follows (a 2 x 2 block of rho per qubit), with the diagonal layer
 // that precedes them folded into the load.  rho is a 2n-bit vector (index = row + 2^n col); a tile holds 2^TB elements:
@@ -2271,6 +2278,21 @@ int dtc_dm_pauli_channel(void* rho, int n, int qubit, double px, double py, doub
     return DTC_OK;
 }
 
+
+int dtc_dm_superop(void* rho, int n, int qubit, const double* superop, void* stream) {
+    if (!rho || !superop || n < 1 || n > 13 || qubit < 0 || qubit >= n) return fail(DTC_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device_of(rho));
+    CUDA_TRY(guard.err);
+    DmSuperop S;
+    for (int k = 0; k < 16; ++k) {
+        S.re[k] = superop[2 * k];
+        S.im[k] = superop[2 * k + 1];
+    }
+    const long long ng = 1ll << (2 * n - 2);
+    k_dm_superop<<<(unsigned)((ng + 255) / 256), 256, 0, (cudaStream_t)stream>>>((double2*)rho, n, qubit, S);
+    CUDA_TRY(cudaGetLastError());
+    return DTC_OK;
+}
 
 // Whole density-matrix program in one call (replaces a per-gate launch loop on the host side): segments of rotations (type 0),
 // diagonal terms (1) and Pauli channels (2) in circuit order.  Rotation + channel segments that follow each other are fused

@@ -3,10 +3,16 @@
 Mirrors the two qiskit-aer entry points the reference uses -- ``depolarizing_error(p, 1)`` and
 ``NoiseModel().add_all_qubit_quantum_error(error, ["u1","u2","u3"])`` -- and adapts a *real*
 qiskit-aer ``NoiseModel`` through its ``to_dict()`` form.  Representable: single-qubit Pauli channels after
-gates (all the simulator path of the reference uses) and single-qubit readout errors (the classical part of
-device-calibrated noise, ``NoiseModel.from_backend``, fast.py:77-78 / SURVEY.md 8f-4); thermal-relaxation and other
-non-Pauli channels raise ``ValueError`` -- there is no silent fallback.
+gates (all the simulator path of the reference uses), single-qubit readout errors (the classical part of
+device-calibrated noise, ``NoiseModel.from_backend``, fast.py:77-78 / SURVEY.md 8f-4) and general single-qubit channels
+(``ChannelError``: thermal relaxation, amplitude / phase damping, Kraus sets and ``reset`` instructions of a device model).
+Pauli channels run on every method; a non-Pauli channel is executed exactly by the density-matrix method (n <= 13) and is
+refused with ``ValueError`` on the trajectory path (norm-dependent Kraus sampling does not fit the Pauli-frame engine) --
+there is no silent fallback.  Errors on multi-qubit gates are not supported.
 """
+import math
+
+import numpy as np
 
 
 class PauliError:
@@ -37,6 +43,127 @@ class PauliError:
 
     def is_ideal(self):
         return self.px == 0 and self.py == 0 and self.pz == 0
+
+    def superop(self):
+        return ChannelError.from_kraus([math.sqrt(max(0.0, 1 - self.px - self.py - self.pz)) * _PAULI_MATS["I"],
+                                        math.sqrt(self.px) * _PAULI_MATS["X"], math.sqrt(self.py) * _PAULI_MATS["Y"],
+                                        math.sqrt(self.pz) * _PAULI_MATS["Z"]]).S
+
+
+_PAULI_MATS = {"I": np.eye(2, dtype=complex), "X": np.array([[0, 1], [1, 0]], dtype=complex),
+               "Y": np.array([[0, -1j], [1j, 0]], dtype=complex), "Z": np.diag([1.0 + 0j, -1.0])}
+
+
+class ChannelError:
+    """General single-qubit channel as a 4 x 4 superoperator S on vec(rho) with index = row + 2 col (the layout of a
+    (row bit, column bit) block of the density-matrix engine): out[r' + 2c'] = sum S[r' + 2c', r + 2c] rho[r, c];
+    for Kraus operators K_k:  S = sum_k conj(K_k) (x) K_k."""
+
+    def __init__(self, superop):
+        S = np.asarray(superop, dtype=np.complex128)
+        if S.shape != (4, 4):
+            raise ValueError("a single-qubit channel is a 4 x 4 superoperator")
+        # trace preservation: sum over r' of S[(r', r'), (r, c)] = delta(r, c)
+        tp = S[0] + S[3]
+        if np.abs(tp - np.array([1, 0, 0, 1])).max() > 1e-9:
+            raise ValueError("channel is not trace preserving")
+        self.S = S
+
+    @classmethod
+    def from_kraus(cls, kraus):
+        S = np.zeros((4, 4), dtype=np.complex128)
+        for K in kraus:
+            K = np.asarray(K, dtype=np.complex128)
+            if K.shape != (2, 2):
+                raise ValueError("only single-qubit (2 x 2) Kraus operators are supported")
+            S += np.kron(np.conj(K), K)
+        return cls(S)
+
+    @property
+    def probs(self):
+        """Hashable identity (used as a cache key beside PauliError.probs)."""
+        return tuple(np.round(self.S.reshape(-1), 15).tolist())
+
+    def compose(self, other):
+        """Channel composition other o self."""
+        So = other.S if isinstance(other, ChannelError) else other.superop()
+        return ChannelError(So @ self.S)
+
+    def is_ideal(self):
+        return np.abs(self.S - np.eye(4)).max() == 0.0
+
+    def as_pauli(self, tol=1e-13):
+        """The PauliError this channel equals, or None: a Pauli mixture has a diagonal Pauli-transfer matrix with
+        non-negative mixture weights."""
+        # Pauli-transfer entries R_ab = tr(P_a E(P_b)) / 2
+        R = np.zeros((4, 4))
+        labels = "IXYZ"
+        for b, lb in enumerate(labels):
+            v = _PAULI_MATS[lb].reshape(-1, order="F")          # vec with index = row + 2 col
+            out = (self.S @ v).reshape(2, 2, order="F")
+            for a, la in enumerate(labels):
+                val = np.trace(_PAULI_MATS[la] @ out) / 2
+                if abs(val.imag) > tol:
+                    return None
+                R[a, b] = val.real
+        if np.abs(R - np.diag(np.diag(R))).max() > tol:
+            return None
+        lx, ly, lz = R[1, 1], R[2, 2], R[3, 3]
+        px, py, pz = (1 + lx - ly - lz) / 4, (1 - lx + ly - lz) / 4, (1 - lx - ly + lz) / 4
+        if min(px, py, pz) < -tol or px + py + pz > 1 + tol:
+            return None
+        return PauliError(max(px, 0.0), max(py, 0.0), max(pz, 0.0))
+
+
+def kraus_error(kraus):
+    """qiskit_aer.noise.kraus_error for single-qubit Kraus sets."""
+    e = ChannelError.from_kraus(kraus)
+    return e.as_pauli() or e
+
+
+def amplitude_damping_error(param_amp, excited_state_population=0.0):
+    """qiskit_aer.noise.amplitude_damping_error: decay 1 -> 0 with probability gamma towards a thermal state with
+    excited-state population p1 (generalised amplitude damping)."""
+    g, p1 = float(param_amp), float(excited_state_population)
+    if not (0 <= g <= 1 and 0 <= p1 <= 1):
+        raise ValueError("amplitude damping parameters out of range")
+    s = math.sqrt(1 - g)
+    ks = [math.sqrt(1 - p1) * np.array([[1, 0], [0, s]]), math.sqrt(1 - p1) * np.array([[0, math.sqrt(g)], [0, 0]]),
+          math.sqrt(p1) * np.array([[s, 0], [0, 1]]), math.sqrt(p1) * np.array([[0, 0], [math.sqrt(g), 0]])]
+    return ChannelError.from_kraus(ks)
+
+
+def phase_damping_error(param_phase):
+    """qiskit_aer.noise.phase_damping_error: off-diagonal elements shrink by sqrt(1 - lambda) (a Pauli-Z mixture)."""
+    lam = float(param_phase)
+    if not 0 <= lam <= 1:
+        raise ValueError("phase damping parameter out of range")
+    return PauliError(0.0, 0.0, (1 - math.sqrt(1 - lam)) / 2)
+
+
+def thermal_relaxation_error(t1, t2, time, excited_state_population=0.0):
+    """qiskit_aer.noise.thermal_relaxation_error: populations relax towards (1 - p1, p1) with probability
+    p_reset = 1 - exp(-time / T1), coherences decay by exp(-time / T2) (T2 <= 2 T1).  Aer builds it as a mixture of
+    {I, Z, reset to 0, reset to 1} for T2 <= T1 and from its Choi matrix otherwise; both are this superoperator."""
+    t1, t2, time, p1 = float(t1), float(t2), float(time), float(excited_state_population)
+    if time < 0 or t1 <= 0 or t2 <= 0:
+        raise ValueError("thermal relaxation needs T1 > 0, T2 > 0, time >= 0")
+    if t2 - 2 * t1 > 0:
+        raise ValueError("thermal relaxation needs T2 <= 2 T1")
+    if not 0 <= p1 <= 1:
+        raise ValueError("excited-state population out of range")
+    p_reset = 1.0 - (math.exp(-time / t1) if math.isfinite(t1) else 1.0)
+    e2 = math.exp(-time / t2) if math.isfinite(t2) else 1.0
+    p0 = 1.0 - p1
+    S = np.zeros((4, 4), dtype=np.complex128)
+    # index = row + 2 col: 0 = rho00, 1 = rho10, 2 = rho01, 3 = rho11
+    S[0, 0] = 1 - p_reset + p_reset * p0
+    S[0, 3] = p_reset * p0
+    S[3, 3] = 1 - p_reset + p_reset * p1
+    S[3, 0] = p_reset * p1
+    S[1, 1] = S[2, 2] = e2
+    e = ChannelError(S)
+    return e.as_pauli() or e
 
 
 class ReadoutError:
@@ -89,7 +216,7 @@ class NoiseModel:
             instructions = [instructions]
         for nm in instructions:
             # adding to an instruction that already has an error composes them
-            self._all[nm] = self._all[nm].compose(error) if nm in self._all else error
+            self._all[nm] = _compose(self._all[nm], error) if nm in self._all else error
             if nm not in self.basis_gates:
                 self.basis_gates.append(nm)
 
@@ -99,7 +226,7 @@ class NoiseModel:
         (q,) = tuple(qubits)
         for nm in instructions:
             key = (nm, int(q))
-            self._local[key] = self._local[key].compose(error) if key in self._local else error
+            self._local[key] = _compose(self._local[key], error) if key in self._local else error
 
     def add_all_qubit_readout_error(self, error, warnings=True):
         self._ro_all = error if isinstance(error, ReadoutError) else ReadoutError(error)
@@ -126,20 +253,69 @@ class NoiseModel:
         return e.probabilities
 
     def lookup(self, name, qubit):
-        """Pauli probabilities (px,py,pz) applied after gate `name` on `qubit`, or None."""
+        """Error applied after gate `name` on `qubit`: Pauli probabilities (px, py, pz), the 4 x 4 superoperator of a
+        non-Pauli channel (numpy array, see ChannelError), or None."""
         e = self._local.get((name, qubit))
         if e is None:
             e = self._all.get(name)
         if e is None or e.is_ideal():
             return None
-        return e.probs
+        return e.S if isinstance(e, ChannelError) else e.probs
+
+    def has_channel_noise(self):
+        """True if some error is not a Pauli mixture (density-matrix method only)."""
+        return any(isinstance(e, ChannelError) and not e.is_ideal()
+                   for e in list(self._all.values()) + list(self._local.values()))
 
     @property
     def noise_instructions(self):
         return sorted(set(self._all) | {k[0] for k in self._local})
 
 
+def _compose(first, then):
+    """Channel composition `then` o `first` of PauliError / ChannelError objects (Pauli o Pauli stays Pauli)."""
+    if isinstance(first, PauliError) and isinstance(then, PauliError):
+        return first.compose(then)
+    a = first if isinstance(first, ChannelError) else ChannelError(first.superop())
+    out = a.compose(then)
+    return out.as_pauli() or out
+
+
 _PAULI_NAMES = {"id": "I", "x": "X", "y": "Y", "z": "Z"}
+_RESET_KRAUS = [np.array([[1, 0], [0, 0]], dtype=complex), np.array([[0, 1], [0, 0]], dtype=complex)]
+
+
+def _complex_matrix(m):
+    """A 2 x 2 matrix from a numpy array, nested complex lists or qiskit's serialised [[re, im], ...] form."""
+    a = np.asarray(m)
+    if a.dtype != object and a.ndim == 3 and a.shape[-1] == 2 and not np.iscomplexobj(a):
+        a = a[..., 0] + 1j * a[..., 1]
+    a = np.asarray(a, dtype=np.complex128)
+    if a.shape != (2, 2):
+        raise ValueError("only single-qubit (2 x 2) noise operators are supported")
+    return a
+
+
+def _instruction_superop(inst):
+    """Superoperator of one noise-circuit instruction of NoiseModel.to_dict(): Pauli gates, 'pauli', 'reset', 'kraus',
+    'unitary'."""
+    name = inst["name"]
+    if len(inst.get("qubits", [0])) != 1:
+        raise ValueError("multi-qubit noise instructions are not supported")
+    if name in _PAULI_NAMES:
+        return ChannelError.from_kraus([_PAULI_MATS[_PAULI_NAMES[name]]]).S
+    if name == "pauli":
+        label = str(inst["params"][0])
+        if label not in _PAULI_MATS:
+            raise ValueError(f"unsupported Pauli string {label!r}")
+        return ChannelError.from_kraus([_PAULI_MATS[label]]).S
+    if name == "reset":
+        return ChannelError.from_kraus(_RESET_KRAUS).S
+    if name == "kraus":
+        return ChannelError.from_kraus([_complex_matrix(k) for k in inst["params"]]).S
+    if name == "unitary":
+        return ChannelError.from_kraus([_complex_matrix(inst["params"][0])]).S
+    raise ValueError(f"noise instruction {name!r} is not supported")
 
 
 def _from_dict(d):
@@ -156,25 +332,33 @@ def _from_dict(d):
             continue
         if err.get("type", "qerror") != "qerror":
             raise ValueError(f"unsupported noise entry type {err.get('type')!r}")
-        acc = {"I": 0.0, "X": 0.0, "Y": 0.0, "Z": 0.0}
-        for circ, p in zip(err["instructions"], err["probabilities"]):
-            label = "I"
-            for inst in circ:
-                name = inst["name"]
-                if len(inst.get("qubits", [0])) != 1:
-                    raise ValueError("multi-qubit noise instructions are not supported")
-                if name in _PAULI_NAMES:
-                    this = _PAULI_NAMES[name]
-                elif name == "pauli":
-                    this = str(inst["params"][0])
+        pauli_only = all(inst["name"] in _PAULI_NAMES or inst["name"] == "pauli"
+                         for circ in err["instructions"] for inst in circ)
+        if pauli_only:
+            # Pauli mixture: probabilities accumulate exactly (no round trip through a superoperator)
+            acc = {"I": 0.0, "X": 0.0, "Y": 0.0, "Z": 0.0}
+            for circ, p in zip(err["instructions"], err["probabilities"]):
+                label = "I"
+                for inst in circ:
+                    if len(inst.get("qubits", [0])) != 1:
+                        raise ValueError("multi-qubit noise instructions are not supported")
+                    this = _PAULI_NAMES[inst["name"]] if inst["name"] in _PAULI_NAMES else str(inst["params"][0])
                     if this not in acc:
                         raise ValueError(f"unsupported Pauli string {this!r}")
-                else:
-                    raise ValueError(f"non-Pauli noise instruction {name!r} is not supported")
-                # product of Paulis modulo phase: codes I=0,X=1,Y=2,Z=3 multiply by xor
-                label = "IXYZ"["IXYZ".index(label) ^ "IXYZ".index(this)]
-            acc[label] += float(p)
-        e = PauliError(acc["X"], acc["Y"], acc["Z"])
+                    # product of Paulis modulo phase: codes I=0,X=1,Y=2,Z=3 multiply by xor
+                    label = "IXYZ"["IXYZ".index(label) ^ "IXYZ".index(this)]
+                acc[label] += float(p)
+            e = PauliError(acc["X"], acc["Y"], acc["Z"])
+        else:
+            # mixture of noise circuits: sum_k p_k (product of the superoperators of circuit k's instructions)
+            S = np.zeros((4, 4), dtype=np.complex128)
+            for circ, p in zip(err["instructions"], err["probabilities"]):
+                Sk = np.eye(4, dtype=np.complex128)
+                for inst in circ:
+                    Sk = _instruction_superop(inst) @ Sk
+                S += float(p) * Sk
+            ch = ChannelError(S)
+            e = ch.as_pauli() or ch
         gate_qubits = err.get("gate_qubits")
         if gate_qubits:
             for gq in gate_qubits:

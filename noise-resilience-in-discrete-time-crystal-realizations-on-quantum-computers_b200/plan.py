@@ -82,6 +82,7 @@ class Program:
         self.measure_orig = {}      # clbit -> index of the measured qubit in the (wide) input circuit: noise-model key
         self.n_sites = 0
         self.dm_segments = []       # ordered segments for the density-matrix engine
+        self.has_channels = False   # non-Pauli channels present: only dm_segments describes the program
         self.rot_layers = 0         # number of non-empty rotation layers (for accounting)
 
     def arrays(self):
@@ -233,6 +234,9 @@ class _Prims:
 
     def noise(self, q, probs):
         self.prims.append(("N", (q,), tuple(probs)))
+
+    def channel(self, q, superop):
+        self.prims.append(("K", (q,), superop))
 
     def u3(self, q, theta, phi, lam, extra=0.0):
         self.global_phase += extra + (phi + lam) / 2
@@ -435,7 +439,8 @@ def lower_to_prims(circuit, noise_model=None):
     """Stage 1 of the compiler: gates -> primitive list on compacted qubits.
 
     Returns (prims, global_phase, measured {clbit: compacted qubit}, used (original qubit of each compacted
-    one), n_clbits).  prims entries: ("R", (q,), theta) | ("D", (q,), a) | ("D", (i, j), b) | ("N", (q,), (px,py,pz)).
+    one), n_clbits).  prims entries: ("R", (q,), theta) | ("D", (q,), a) | ("D", (i, j), b) | ("N", (q,), (px,py,pz)) |
+    ("K", (q,), 4 x 4 superoperator) for a non-Pauli channel (density-matrix programs only).
     """
     circ = as_circuit(circuit)
     for op in circ.ops:
@@ -511,7 +516,10 @@ def lower_to_prims(circuit, noise_model=None):
             b.cx(qs[0], qs[1])
         pr = probs_by_id[id(op)]
         if pr is not None:
-            b.noise(qs[0], pr)
+            if isinstance(pr, tuple):
+                b.noise(qs[0], pr)
+            else:                                       # 4 x 4 superoperator of a non-Pauli channel (noise.ChannelError)
+                b.channel(qs[0], pr)
     return b.prims, b.global_phase, measured, used, circ.num_clbits
 
 
@@ -529,6 +537,12 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True, opti
     """
     prims, global_phase, measured, used, n_clbits = lower_to_prims(circuit, noise_model)
     n = len(used)
+    has_channels = any(typ == "K" for typ, _qs, _v in prims)
+    if has_channels and not want_dm:
+        raise ValueError("non-Pauli noise channels (thermal relaxation, amplitude damping, Kraus, reset) need the "
+                         "density-matrix method: they cannot be sampled as Pauli frames")
+    if has_channels and optimize:
+        raise ValueError("read-out factorisation is not available with non-Pauli noise channels")
 
     # ---- stage 2: read-out analysis and internal bit order (eliminated qubits become the top bits)
     plan = _analyse_readout(prims, n, sorted(set(measured.values()))) if optimize else None
@@ -559,6 +573,8 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True, opti
         in_small = bool(plan) and (idx >= cut or bool(set(qs) & E and (idx not in kinds or kinds[idx][0] in E)))
         dom = small if in_small else main
         bq = tuple(bit_of[q] for q in qs)
+        if typ == "K":
+            continue                                      # density-matrix segments only (prog.has_channels)
         if typ == "R":
             dom.rot(bq[0], val)
         elif typ == "N":
@@ -583,6 +599,7 @@ def compile_circuit(circuit, noise_model=None, want_dm=False, reorder=True, opti
         prog.small = dict(events=sorted(small.events), elim_bits=sorted(bit_of[q] for q in elim),
                           reg_bits=sorted(bit_of[q] for q in plan[1]), first_layer=prog.n_exec_layers,
                           n_layers=n_small_layers)
+    prog.has_channels = has_channels                    # the event arrays then omit the channels: rho path only
     if want_dm:
         prog.dm_segments = _segment_dm([(t, tuple(bit_of[q] for q in qs), v) for t, qs, v in prims])
     return prog

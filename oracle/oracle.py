@@ -149,18 +149,62 @@ class PauliNoise:
     depolarizing_error(p, 1) (fast.py:85): rho -> (1-p) rho + p I/2 == {I: 1-3p/4, X,Y,Z: p/4}.
     """
 
-    def __init__(self, table=None):
+    def __init__(self, table=None, channels=None):
         self.table = dict(table or {})
+        # general single-qubit channels as Kraus sets {name: [K_0, K_1, ...]} (2 x 2): the non-Pauli part of a device
+        # noise model (fast.py:77-78); a gate name carries either a Pauli entry or a Kraus set; density-matrix method only
+        self.channels = {nm: [np.asarray(k, dtype=np.complex128) for k in ks] for nm, ks in (channels or {}).items()}
 
     @classmethod
     def depolarizing(cls, p, names=("u1", "u2", "u3")):
         return cls({nm: (p / 4, p / 4, p / 4) for nm in names})
 
+    @classmethod
+    def thermal_relaxation(cls, t1, t2, time, excited_state_population=0.0, names=("u1", "u2", "u3")):
+        return cls(channels={nm: thermal_relaxation_kraus(t1, t2, time, excited_state_population) for nm in names})
+
     def probs(self, name):
         return self.table.get(name)
 
+    def kraus(self, name):
+        return self.channels.get(name)
+
+    def has_channels(self):
+        return bool(self.channels)
+
     def is_ideal(self):
-        return not any(any(v) for v in self.table.values())
+        return not any(any(v) for v in self.table.values()) and not self.channels
+
+
+def thermal_relaxation_kraus(t1, t2, time, excited_state_population=0.0):
+    """Kraus operators of qiskit-aer's thermal_relaxation_error, restated from its published construction: for T2 <= T1 the
+    mixture {I: p_id, Z: p_z, reset to |0>: p_r0, reset to |1>: p_r1} with p_reset = 1 - exp(-time / T1),
+    p_z = (1 - p_reset) (1 - exp(-time (1/T2 - 1/T1))) / 2, p_r0 = p_reset (1 - p1), p_r1 = p_reset p1; for T1 < T2 <= 2 T1 the
+    Kraus operators obtained from the channel's Choi matrix
+        [[1 - p1 p_reset, 0, 0, exp(-time / T2)], [0, p1 p_reset, 0, 0], [0, 0, p0 p_reset, 0], [exp(-time / T2), 0, 0, 1 - p0 p_reset]]."""
+    p1 = float(excited_state_population)
+    p0 = 1.0 - p1
+    p_reset = 1.0 - np.exp(-time / t1)
+    e2 = np.exp(-time / t2)
+    if t2 <= t1:
+        p_z = (1 - p_reset) * (1 - np.exp(-time * (1.0 / t2 - 1.0 / t1))) / 2
+        p_r0, p_r1 = p_reset * p0, p_reset * p1
+        p_id = 1 - p_z - p_r0 - p_r1
+        I2, Z = np.eye(2), np.diag([1.0, -1.0])
+        P00, P01 = np.array([[1.0, 0], [0, 0]]), np.array([[0, 1.0], [0, 0]])
+        P10, P11 = np.array([[0, 0], [1.0, 0]]), np.array([[0, 0], [0, 1.0]])
+        return [np.sqrt(p_id) * I2, np.sqrt(p_z) * Z, np.sqrt(p_r0) * P00, np.sqrt(p_r0) * P01,
+                np.sqrt(p_r1) * P10, np.sqrt(p_r1) * P11]
+    # Choi matrix C = sum_ij |i><j| (x) E(|i><j|), index (i, a), (j, b) with E(|i><j|)[a, b]
+    choi = np.array([[1 - p1 * p_reset, 0, 0, e2], [0, p1 * p_reset, 0, 0], [0, 0, p0 * p_reset, 0],
+                     [e2, 0, 0, 1 - p0 * p_reset]], dtype=np.complex128)
+    w, v = np.linalg.eigh(choi)
+    ks = []
+    for lam, vec in zip(w, v.T):
+        if lam > 1e-15:
+            # vec index = 2 i + a  ->  K[a, i]
+            ks.append(np.sqrt(lam) * vec.reshape(2, 2).T)
+    return ks
 
 
 def compact_ops(ops, n_qubits):
@@ -174,7 +218,10 @@ def compact_ops(ops, n_qubits):
 
 
 def choose_method(n, shots, noise):
-    """Aer 'automatic' (SURVEY A6): density_matrix iff noise present and shots > 2^n."""
+    """Aer 'automatic' (SURVEY A6): density_matrix iff noise present and shots > 2^n.  Non-Pauli channels always take the
+    density matrix here (Aer would sample Kraus trajectories below that shot count; same outcome distribution)."""
+    if noise is not None and getattr(noise, "has_channels", lambda: False)():
+        return "density_matrix"
     if noise is not None and not noise.is_ideal() and shots > (1 << n):
         return "density_matrix"
     return "statevector"
@@ -261,6 +308,16 @@ def run_density_matrix(ops, n, noise, init=None):
         if name in ("measure", "barrier"):
             continue
         rho = conj_unitary(rho, name, qs, params)
+        ks = noise.kraus(name) if (noise is not None and name in ONE_QUBIT and hasattr(noise, "kraus")) else None
+        if ks is not None:
+            # rho -> sum_k K rho K^dagger on the gate's qubit: K on the row index, conj(K) on the column index
+            q = qs[0]
+            acc = np.zeros_like(rho)
+            for K in ks:
+                r1 = apply_1q(rho.T, K, q).T
+                acc = acc + np.conj(apply_1q(np.conj(r1), K, q))
+            rho = acc
+            continue
         pr = noise.probs(name) if (noise is not None and name in ONE_QUBIT) else None
         if pr is not None and any(pr):
             q = qs[0]

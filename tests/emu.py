@@ -128,3 +128,21 @@ def dm_run(n, flat_segments, rho0=None, reg_passes=True, wide13=True):
     if rc != 0:
         raise ValueError(err.value.decode())
     return rho.reshape(1 << n, 1 << n), {"sweeps": int(info[0]), "reg_passes": int(info[1]), "worst_conflict": int(info[2])}
+
+
+def dm_program(prog, reg_passes=True, wide13=True):
+    """backend.run_density_matrix on the CPU: stretches of R / D / N segments through the emulated dtc_dm_run, non-Pauli
+    channels through the emulated k_dm_superop.  Returns rho [2^n cols, 2^n rows]."""
+    from dtcsim.backend import flatten_dm_segments, split_dm_segments
+    n = prog.n
+    rho = np.zeros(1 << (2 * n), dtype=np.complex128)
+    rho[0] = 1.0
+    for kind, payload in split_dm_segments(prog.dm_segments):
+        if kind == "K":
+            for q, S in payload:
+                Sf = np.ascontiguousarray(np.asarray(S, dtype=np.complex128).reshape(16)).view(np.float64)
+                lib().emu_dm_superop(ctypes.c_int(n), ctypes.c_int(int(q)), _p(Sf, ctypes.c_double),
+                                     rho.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        else:
+            rho = dm_run(n, flatten_dm_segments(payload), rho0=rho, reg_passes=reg_passes, wide13=wide13)[0].reshape(-1).copy()
+    return rho.reshape(1 << n, 1 << n)

@@ -389,3 +389,12 @@ extern "C" int emu_dm_run(int n, int n_seg, const int32_t* seg_type, const int32
     info[0] = sweeps; info[1] = nreg; info[2] = worst;
     return 0;
 }
+
+// k_dm_superop on the CPU: superop = 16 complex numbers, row major, (re, im) pairs
+extern "C" int emu_dm_superop(int n, int q, const double* superop, double* rho_io) {
+    DmSuperop S;
+    for (int k = 0; k < 16; ++k) { S.re[k] = superop[2 * k]; S.im[k] = superop[2 * k + 1]; }
+    double2* rho = reinterpret_cast<double2*>(rho_io);
+    for (long long i = 0; i < (1ll << (2 * n - 2)); ++i) dm_superop_thread(rho, n, q, S, i);
+    return 0;
+}

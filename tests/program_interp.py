@@ -181,6 +181,18 @@ def run_dm(prog, n):
                 zc = (1.0 - 2.0 * _bits(2 * n, i + n)) * (1.0 - 2.0 * _bits(2 * n, j + n))
                 ph *= np.exp(-0.5j * b * (zr - zc))
             rho = rho * ph[None, :]
+        elif seg[0] == "K":
+            # general single-qubit channel: 4 x 4 superoperator on the (row bit q, column bit q) block, index = row + 2 col
+            for q, S in seg[1]:
+                idx = np.arange(d * d, dtype=np.int64)
+                base = idx & ~((1 << q) | (1 << (q + n)))
+                blk = ((idx >> q) & 1) | (((idx >> (q + n)) & 1) << 1)
+                src = [base | ((j & 1) << q) | ((j >> 1) << (q + n)) for j in range(4)]
+                S = np.asarray(S, dtype=np.complex128)
+                new = np.zeros(d * d, dtype=np.complex128)
+                for j in range(4):
+                    new += S[blk, j] * rho[0, src[j]]
+                rho = new[None, :]
         elif seg[0] == "N":
             for q, (px, py, pz) in seg[1]:
                 idx = np.arange(d * d, dtype=np.int64)

@@ -817,6 +817,43 @@ def test_run_expz_sweep_through_qasm_equals_oracle(disorder):
     assert z.max() < family_z(z.size)
 
 
+def test_thermal_relaxation_through_run_vs_oracle(disorder):
+    """Non-Pauli channels of a device-calibrated noise model (thermal relaxation after every u2 / u3, both of Aer's
+    constructions: T2 <= T1 mixture incl. reset, T2 > T1 Choi matrix; fast.py:77-78) through run(): exact density matrix
+    whatever the shot count, probabilities within 1e-10 of the oracle's Kraus evolution, counts bit-identical; combined with a
+    readout error; explicit statevector method refused."""
+    from dtcsim import noise as N
+    for L, t, echo, (t1, t2), shots in ((4, 3, True, (80.0, 100.0), 1024), (4, 2, False, (100.0, 60.0), 1024),
+                                        (6, 2, True, (80.0, 100.0), 16), (7, 1, False, (100.0, 60.0), 64)):
+        hs, phis = disorder[20][0][0][:L], disorder[20][1][0][:L - 1]
+        circ = RC.transpiled(RC.qc_body("vacuum", L, 0.97, hs, phis, t, L // 2, echo))
+        nm = dtcsim.NoiseModel()
+        nm.add_all_qubit_quantum_error(N.thermal_relaxation_error(t1, t2, 4.0, 0.05), ["u1", "u2", "u3"])
+        onoise = O.PauliNoise.thermal_relaxation(t1, t2, 4.0, 0.05)
+        sim = dtcsim.AerSimulator(noise_model=nm, device="GPU")
+        res = sim.run(circ, shots=shots, seed_simulator=5).result()
+        want, info = O.run_counts(RC.ops_of(circ), circ.num_qubits, 1, shots=shots, noise=onoise, seed=5)
+        assert res.data()["method"] == "density_matrix" and info["method"] == "density_matrix"
+        pr = res.data()["probabilities"]
+        assert abs(pr.get("0", 0.0) - info["probabilities"][0]) < 1e-10 and abs(sum(pr.values()) - 1) < 1e-12
+        assert res.get_counts() == want, (L, t, echo)
+    with pytest.raises(ValueError):
+        sim.run(circ, shots=16, method="statevector")
+    # amplitude damping on the kick gates only + a readout error on the ancilla
+    hs, phis = disorder[4][0][0], disorder[4][1][0]
+    circ = RC.transpiled(RC.qc_body("neel", 4, 0.84, hs, phis, 2, 2, True))
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_quantum_error(N.amplitude_damping_error(0.02), ["u3"])
+    nm.add_all_qubit_quantum_error(dtcsim.depolarizing_error(0.05, 1), ["u2"])
+    M = [[0.97, 0.03], [0.08, 0.92]]
+    nm.add_all_qubit_readout_error(M)
+    ks = [np.array([[1, 0], [0, np.sqrt(0.98)]]), np.array([[0, np.sqrt(0.02)], [0, 0]])]
+    onoise = O.PauliNoise({"u2": (0.0125, 0.0125, 0.0125)}, channels={"u3": ks})
+    res = dtcsim.AerSimulator(noise_model=nm).run(circ, shots=512, seed_simulator=9).result()
+    want, _ = O.run_counts(RC.ops_of(circ), circ.num_qubits, 1, shots=512, noise=onoise, seed=9, readout={0: M})
+    assert res.get_counts() == want
+
+
 def test_readout_errors_counts_vs_oracle(disorder):
     """Classical readout errors (the part of device-calibrated noise, fast.py:77-78, that is not a channel on the state):
     counts bit-identical to the oracle under the shared Philox contract on all three execution paths (density matrix,
