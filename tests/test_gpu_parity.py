@@ -835,7 +835,7 @@ def test_thermal_relaxation_through_run_vs_oracle(disorder):
         want, info = O.run_counts(RC.ops_of(circ), circ.num_qubits, 1, shots=shots, noise=onoise, seed=5)
         assert res.data()["method"] == "density_matrix" and info["method"] == "density_matrix"
         pr = res.data()["probabilities"]
-        assert abs(pr.get("0", 0.0) - info["probabilities"][0]) < 1e-10 and abs(sum(pr.values()) - 1) < 1e-12
+        assert abs(pr[0] - info["probabilities"][0]) < 1e-10 and abs(sum(pr.values()) - 1) < 1e-12      # keyed by clbit value
         assert res.get_counts() == want, (L, t, echo)
     with pytest.raises(ValueError):
         sim.run(circ, shots=16, method="statevector")
