@@ -190,3 +190,74 @@ class BackendEstimatorV2:
         data = _DataBin(np.float64(ev), np.float64(math.sqrt(var)), shots)
         return PubResult(data, {"target_precision": precision, "shots": shots, "circuits": len(circuits),
                                 "groups": [b for b, _ in groups]})
+
+
+# ----------------------------------------------------------------------------------- sampler primitive (dtc_qasm.py:138-140)
+class BitArray:
+    """What `result[0].data.<register>` offers in the scripts: get_counts(), num_shots, num_bits."""
+
+    def __init__(self, counts, num_bits):
+        self._counts, self.num_bits = dict(counts), int(num_bits)
+        self.num_shots = int(sum(counts.values()))
+
+    def get_counts(self):
+        return dict(self._counts)
+
+    def get_int_counts(self):
+        return {int(k.replace(" ", ""), 2): v for k, v in self._counts.items()}
+
+
+class _SamplerData:
+    """`data.c`, `data.meas`, ...: this container's circuits carry one classical register, whatever its name."""
+
+    def __init__(self, bits):
+        self._bits = bits
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return self._bits
+
+    def values(self):
+        return [self._bits]
+
+
+class BackendSamplerV2:
+    """Same call surface as qiskit.primitives.BackendSamplerV2 / qiskit_ibm_runtime.SamplerV2 for what dtc_qasm.py uses:
+        sampler.run([circuit], shots=1024).result()[0].data.c.get_counts()          (dtc_qasm.py:138-140)
+    All pubs of a call go through one pipelined `backend.run(list, shots)`.  A pub is a circuit (native, OpenQASM-2 text or
+    qiskit-like) or a tuple (circuit, parameter_values=None, shots=None); per-pub shot counts split the call."""
+
+    def __init__(self, backend=None, mode=None, options=None):
+        self.backend = backend if backend is not None else mode
+        if self.backend is None:
+            raise ValueError("BackendSamplerV2 needs a backend")
+        opts = dict(options or {})
+        self.default_shots = int(opts.get("default_shots", 1024))
+        self.seed_simulator = opts.get("seed_simulator")
+
+    def run(self, pubs, shots=None):
+        circs, nshots = [], []
+        for pub in pubs:
+            if isinstance(pub, (tuple, list)):
+                if len(pub) > 1 and pub[1] is not None and len(np.atleast_1d(pub[1])):
+                    raise ValueError("parameterised circuits are not supported: bind the parameters first")
+                circs.append(as_circuit(pub[0]))
+                nshots.append(int(pub[2]) if len(pub) > 2 and pub[2] is not None else None)
+            else:
+                circs.append(as_circuit(pub))
+                nshots.append(None)
+        nshots = [n if n is not None else (int(shots) if shots is not None else self.default_shots) for n in nshots]
+        results = [None] * len(circs)
+        for n in sorted(set(nshots)):
+            idx = [i for i, m in enumerate(nshots) if m == n]
+            kw = {"shots": n}
+            if self.seed_simulator is not None:
+                kw["seed_simulator"] = [int(self.seed_simulator) + i for i in idx]
+            res = self.backend.run([circs[i] for i in idx], **kw).result()
+            for j, i in enumerate(idx):
+                results[i] = PubResult(_SamplerData(BitArray(res.get_counts(j), circs[i].num_clbits)), {"shots": n})
+        return EstimatorJob(results)
+
+
+SamplerV2 = BackendSamplerV2

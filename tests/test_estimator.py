@@ -187,3 +187,29 @@ def test_run_energy_sweep_vs_exact_energy(disorder):
     # echo circuits: t periods forward and t back
     c = dtcsim.energy_circuit(L, g, hs[0], phis[0], 2, echo=True, transpile=False)
     assert len(c.ops) == 4 * (L + (L - 1) + L)
+
+
+def test_backend_sampler_v2_dtc_qasm_usage(disorder):
+    """dtc_qasm.py:138-140: `SamplerV2(mode=backend).run([qc], shots=1024).result()[0].data.c.get_counts()` with the circuit
+    handed over as OpenQASM-2 text; counts are the backend's (here the oracle-backed stand-in), per-pub shot counts honoured."""
+    from test_dist_cpu import _OracleSim
+
+    class _Sim(_OracleSim):
+        def run(self, circuits, **kw):
+            from dtcsim.ir import as_circuit
+            return super().run([as_circuit(c) for c in circuits], **kw)
+
+    hs, phis = disorder[20][0][0][:4], disorder[20][1][0][:3]
+    c1 = dtcsim.expz_circuit(4, 0.94, hs, phis, 2, "1")
+    c2 = dtcsim.expz_circuit(4, 0.94, hs, phis, 3, "0")
+    sampler = dtcsim.SamplerV2(mode=_Sim(), options={"seed_simulator": 12})
+    res = sampler.run([c1.qasm(), (c2, None, 64)], shots=256).result()
+    a, b = res[0].data.c, res[1].data.meas
+    assert a.num_shots == 256 and b.num_shots == 64 and a.num_bits == 4
+    noise = O.PauliNoise.depolarizing(0.05)
+    want = O.run_counts([o.astuple() for o in c1.ops], 4, 4, shots=256, noise=noise, seed=12)[0]
+    assert a.get_counts() == want and sum(a.get_int_counts().values()) == 256
+    want2 = O.run_counts([o.astuple() for o in c2.ops], 4, 4, shots=64, noise=noise, seed=13)[0]
+    assert b.get_counts() == want2
+    with pytest.raises(ValueError):
+        dtcsim.BackendSamplerV2()
