@@ -125,15 +125,20 @@ def _adaptive_worker(rank, world, port, out):
     hs, phis = _disorder4(3)
     res = D.run_adaptive(Sim(), 4, hs, phis, 3, feedback_gain=0.05, exponential_feedback=True, shots=64, seed_simulator=21,
                          rank=rank, world=world)
+    ez = D.run_expz_sweep(Sim(), 4, 0.94, hs, phis, 3, state="1", shots=64, seed_simulator=8, via_qasm=False,
+                          rank=rank, world=world, chunk=2)
+    en = D.run_energy_sweep(Sim(), 4, 0.97, hs[:2], phis[:2], [0, 2], precision=1 / 16, seed_simulator=4, rank=rank, world=world)
     if rank == 0:
-        out.put((res["forward"].tolist(), res["echo"].tolist(), res["g_history"].tolist(), res["circuits"]))
+        out.put((res["forward"].tolist(), res["echo"].tolist(), res["g_history"].tolist(), res["circuits"],
+                 ez["expz"].tolist(), en["energy_per_site"].tolist(), en["circuits"]))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def test_run_adaptive_two_ranks_equal_one_rank():
-    """Instances dealt over two gloo ranks (three instances: ragged) == one rank."""
+def test_drivers_two_ranks_equal_one_rank():
+    """run_adaptive (instances dealt over two gloo ranks; three instances: ragged), run_expz_sweep and run_energy_sweep
+    (points dealt over the ranks) == one rank, value for value."""
     ctx = mp.get_context("spawn")
     results = []
     for world in (1, 2):
@@ -147,6 +152,8 @@ def test_run_adaptive_two_ranks_equal_one_rank():
             p.join(timeout=60)
             assert p.exitcode == 0
     assert results[0] == results[1] and results[0][3] == 3 * 3 * 2
+    # the same holds for the site-resolved <Z_i(t)> sweep (6 points dealt over the ranks) and the energy sweep (4 points)
+    assert np.array(results[0][4]).shape == (3, 4, 2) and np.array(results[0][5]).shape == (2, 2) and results[0][6] == 8
 
 
 # ----------------------------------------------------------------------------------- dtc_qasm.py driver
