@@ -207,7 +207,7 @@ def run_adaptive(sim, L, hs, phis, T, g_initial=0.84, target_echo=1.0, feedback_
     The steps of one instance depend on each other; what runs in parallel is (a) forward / echo / grid candidates of a step in
     one run(list), (b) parallel="instances": instances dealt over the ranks, one all-reduce at the end, or
     parallel="trajectories": every rank walks the same loop and each circuit's shots are split over the ranks
-    (dist.ShardedSampler; counts identical to one GPU).  Seeds are `seed + 1000003 * instance + 4099 * step + evaluation index`,
+    (dist.ShardedSampler: one Pauli trajectory per shot whatever L; counts identical to one GPU).  Seeds are `seed + 1000003 * instance + 4099 * step + evaluation index`,
     so the result does not depend on the number of ranks.
 
     Returns {"forward", "echo", "g_history": float64 [n_inst, T]; "mean_forward", "mean_echo", "mean_g": [T];
@@ -219,7 +219,9 @@ def run_adaptive(sim, L, hs, phis, T, g_initial=0.84, target_echo=1.0, feedback_
     hs = np.atleast_2d(np.asarray(hs, dtype=np.float64))
     phis = np.atleast_2d(np.asarray(phis, dtype=np.float64))
     n_inst = hs.shape[0]
-    split_shots = parallel == "trajectories" and world > 1
+    # "trajectories" always samples through the trajectory engine (also on one rank), so the result does not depend on the
+    # number of ranks; "instances" goes through run(), whose automatic method takes the exact density matrix for small L
+    split_shots = parallel == "trajectories"
     sampler = D.ShardedSampler(sim, rank, world, group) if split_shots else None
     mine = list(range(n_inst)) if (split_shots or world == 1) else D.deal_units(n_inst, rank, world)
     out = np.zeros((3, n_inst, T), dtype=np.float64)

@@ -109,6 +109,20 @@ def test_optimization_mode_counts_evaluations():
     assert all(g in (0.84, pytest.approx(0.84 + 0.16 / 3), pytest.approx(0.84 + 0.32 / 3), 1.0) for g in res["g_history"][0][1:])
 
 
+class _TrajSim(_OracleSim):
+    """Adds DTCSimulator.sample_trajectories (one Pauli trajectory per shot, shots a..b-1) on top of the oracle."""
+
+    def sample_trajectories(self, circuit, traj_begin, traj_end, seed):
+        from oracle import oracle as O
+        from oracle import philox
+        ops, n, _ = O.compact_ops([o.astuple() for o in circuit.ops], circuit.num_qubits)
+        tr = np.arange(traj_begin, traj_end, dtype=np.uint64)
+        psi = O.run_trajectories(ops, n, O.PauliNoise.depolarizing(0.05), seed, tr)
+        probs = O.outcome_probabilities(np.abs(psi) ** 2, n, O.measured_map(ops), circuit.num_clbits)
+        u = philox.uniform(seed, 0, philox.STREAM_MEASURE, tr)
+        return np.array([O.sample_outcome(np.cumsum(probs[r]), u[r]) for r in range(len(tr))], dtype=np.int64)
+
+
 def _adaptive_worker(rank, world, port, out):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -128,9 +142,13 @@ def _adaptive_worker(rank, world, port, out):
     ez = D.run_expz_sweep(Sim(), 4, 0.94, hs, phis, 3, state="1", shots=64, seed_simulator=8, via_qasm=False,
                           rank=rank, world=world, chunk=2)
     en = D.run_energy_sweep(Sim(), 4, 0.97, hs[:2], phis[:2], [0, 2], precision=1 / 16, seed_simulator=4, rank=rank, world=world)
+    from test_adaptive import _TrajSim
+    tr = D.run_adaptive(_TrajSim(), 4, hs[:1], phis[:1], 3, feedback_gain=0.05, exponential_feedback=False, shots=48,
+                        seed_simulator=2, rank=rank, world=world, parallel="trajectories")
     if rank == 0:
         out.put((res["forward"].tolist(), res["echo"].tolist(), res["g_history"].tolist(), res["circuits"],
-                 ez["expz"].tolist(), en["energy_per_site"].tolist(), en["circuits"]))
+                 ez["expz"].tolist(), en["energy_per_site"].tolist(), en["circuits"],
+                 tr["echo"].tolist(), tr["g_history"].tolist(), tr["circuits"]))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -154,6 +172,8 @@ def test_drivers_two_ranks_equal_one_rank():
     assert results[0] == results[1] and results[0][3] == 3 * 3 * 2
     # the same holds for the site-resolved <Z_i(t)> sweep (6 points dealt over the ranks) and the energy sweep (4 points)
     assert np.array(results[0][4]).shape == (3, 4, 2) and np.array(results[0][5]).shape == (2, 2) and results[0][6] == 8
+    # parallel="trajectories": every rank walks the loop, each circuit's shots are split over the ranks (dist.ShardedSampler)
+    assert results[0][9] == 6 and np.array(results[0][8]).shape == (1, 3)
 
 
 # ----------------------------------------------------------------------------------- dtc_qasm.py driver
