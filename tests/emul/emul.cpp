@@ -341,6 +341,37 @@ extern "C" int emu_dm_run(int n, int n_seg, const int32_t* seg_type, const int32
             const DmRegPass& P = S.R;
             const int threads = 1 << (P.tile_bits - 4);
             std::vector<double2> tile((size_t)1 << P.tile_bits);
+            // (CTA index, tile element) -> global index must be a bijection onto [0, 4^n): the tile bits and the bits the
+            // CTA-index segments land on are disjoint and together are exactly the 2n index bits (no out-of-range access)
+            {
+                u64 cover = 0;
+                bool ok = true;
+                int src_bits = 0;
+                for (int l = 0; l < P.tile_bits; ++l) {
+                    const u64 b = 1ull << P.tb[l];
+                    ok = ok && P.tb[l] >= 0 && P.tb[l] < 2 * n && !(cover & b);
+                    cover |= b;
+                }
+                for (int k = 0; k < P.seg_n; ++k) {
+                    ok = ok && P.seg_src[k] == src_bits;
+                    for (int j = 0; j < P.seg_len[k]; ++j) {
+                        const u64 b = 1ull << (P.seg_dst[k] + j);
+                        ok = ok && P.seg_dst[k] + j < 2 * n && !(cover & b);
+                        cover |= b;
+                    }
+                    src_bits += P.seg_len[k];
+                }
+                if (!ok || cover != ne - 1 || src_bits != 2 * n - P.tile_bits) {
+                    snprintf(errbuf, errlen, "register pass: tile bits and CTA-index segments do not partition the index bits");
+                    return -1;
+                }
+                for (int r = 0; r < P.n_rounds; ++r)
+                    for (int k = 0; k < 4; ++k)
+                        if (P.r[r].hg[k] != (1u << P.tb[P.r[r].hb[k]]) || P.r[r].hp[k] != dm_phys(1 << P.r[r].hb[k])) {
+                            snprintf(errbuf, errlen, "register pass: derived masks of round %d are inconsistent", r);
+                            return -1;
+                        }
+            }
             // every element of the tile must belong to exactly one (thread, register) of every round
             for (int r = 0; r < P.n_rounds; ++r) {
                 std::vector<int> seen((size_t)1 << P.tile_bits, 0);
