@@ -92,6 +92,28 @@ class ChannelError:
     def is_ideal(self):
         return np.abs(self.S - np.eye(4)).max() == 0.0
 
+    def _ptm(self):
+        """Pauli-transfer matrix R_ab = tr(P_a E(P_b)) / 2 (complex in general)."""
+        R = np.zeros((4, 4), dtype=np.complex128)
+        labels = "IXYZ"
+        for b, lb in enumerate(labels):
+            out = (self.S @ _PAULI_MATS[lb].reshape(-1, order="F")).reshape(2, 2, order="F")
+            for a, la in enumerate(labels):
+                R[a, b] = np.trace(_PAULI_MATS[la] @ out) / 2
+        return R
+
+    def pauli_twirl(self):
+        """The Pauli channel obtained by twirling this channel over the Pauli group (its Pauli-transfer matrix restricted to
+        the diagonal): an APPROXIMATION that keeps the decay rates of <X>, <Y>, <Z> and drops the non-unital drift (e.g. the
+        relaxation towards |0>).  Opt-in only (NoiseModel.pauli_twirled): it is what lets a device-like noise model run on the
+        trajectory engine at n > 13; exact results need the density-matrix method."""
+        R = self._ptm().real
+        lx, ly, lz = R[1, 1], R[2, 2], R[3, 3]
+        px, py, pz = (1 + lx - ly - lz) / 4, (1 - lx + ly - lz) / 4, (1 - lx - ly + lz) / 4
+        if min(px, py, pz) < -1e-12:
+            raise ValueError("the Pauli twirl of this channel is not a probability mixture")
+        return PauliError(max(px, 0.0), max(py, 0.0), max(pz, 0.0))
+
     def as_pauli(self, tol=1e-13):
         """The PauliError this channel equals, or None: a Pauli mixture has a diagonal Pauli-transfer matrix with
         non-negative mixture weights."""
@@ -266,6 +288,15 @@ class NoiseModel:
         """True if some error is not a Pauli mixture (density-matrix method only)."""
         return any(isinstance(e, ChannelError) and not e.is_ideal()
                    for e in list(self._all.values()) + list(self._local.values()))
+
+    def pauli_twirled(self):
+        """Copy of this model with every non-Pauli channel replaced by its Pauli twirl (ChannelError.pauli_twirl): an explicit,
+        opt-in approximation for running device-like noise on the trajectory engine; readout errors are kept."""
+        out = NoiseModel(self.basis_gates)
+        out._all = {k: (e.pauli_twirl() if isinstance(e, ChannelError) else e) for k, e in self._all.items()}
+        out._local = {k: (e.pauli_twirl() if isinstance(e, ChannelError) else e) for k, e in self._local.items()}
+        out._ro_all, out._ro_local = self._ro_all, dict(self._ro_local)
+        return out
 
     @property
     def noise_instructions(self):

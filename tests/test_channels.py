@@ -115,3 +115,27 @@ def test_trajectory_path_refuses_channels(disorder):
     nm2 = dtcsim.NoiseModel()
     nm2.add_all_qubit_quantum_error(N.phase_damping_error(0.1), ["u3"])
     assert compile_circuit(circ, nm2).n_sites > 0
+
+
+def test_pauli_twirl_is_explicit_and_matches_closed_form(disorder):
+    """Opt-in approximation: the Pauli twirl of thermal relaxation keeps the decay rates (pX = pY = p_reset / 4,
+    pZ = (1 + lambda_z - 2 e2) / 4 for p1 = 0) and makes the model runnable on the trajectory path; nothing twirls silently."""
+    t1, t2, t = 100.0, 120.0, 6.0
+    e = N.thermal_relaxation_error(t1, t2, t)
+    tw = e.pauli_twirl()
+    pr, e2 = 1 - math.exp(-t / t1), math.exp(-t / t2)
+    assert tw.px == pytest.approx(pr / 4) and tw.py == pytest.approx(pr / 4) and tw.pz == pytest.approx((2 - pr - 2 * e2) / 4)
+    # the twirl of a Pauli mixture is the mixture itself
+    d = N.ChannelError(N.depolarizing_error(0.08, 1).superop()).pauli_twirl()
+    assert d.probs == pytest.approx((0.02, 0.02, 0.02))
+    nm = dtcsim.NoiseModel()
+    nm.add_all_qubit_quantum_error(e, ["u3"])
+    nm.add_all_qubit_readout_error([[0.98, 0.02], [0.05, 0.95]])
+    hs, phis = disorder[4][0][0], disorder[4][1][0]
+    circ = RC.transpiled(RC.qc_body("vacuum", 4, 0.84, hs, phis, 1, 2, False))
+    with pytest.raises(ValueError):
+        compile_circuit(circ, nm)                                        # exact model: trajectories refused
+    tw_nm = nm.pauli_twirled()
+    assert not tw_nm.has_channel_noise() and tw_nm.has_readout_noise() and nm.has_channel_noise()
+    prog = compile_circuit(circ, tw_nm)
+    assert prog.n_sites == 4 and not prog.has_channels
