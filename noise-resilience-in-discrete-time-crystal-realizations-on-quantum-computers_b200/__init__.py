@@ -11,7 +11,7 @@ from .noise import (NoiseModel, ReadoutError, ChannelError, depolarizing_error, 
                     amplitude_damping_error, phase_damping_error, thermal_relaxation_error, as_noise_model)
 from .plan import compile_circuit, Program                                       # noqa: F401
 from .sweeps import (autocorr_circuit, energy_circuit, expz_circuit, feedback_g, floquet_period, optimize_g,   # noqa: F401
-                     run_adaptive, run_energy_sweep, run_expz_sweep, run_sweep, xy_cycle_schedule)
+                     run_adaptive, run_energy_sweep, run_expz_sweep, run_shots_sweep, run_sweep, xy_cycle_schedule)
 from .estimator import BackendEstimatorV2, BackendSamplerV2, SamplerV2, dtc_hamiltonian   # noqa: F401
 
 __version__ = "0.1.0"

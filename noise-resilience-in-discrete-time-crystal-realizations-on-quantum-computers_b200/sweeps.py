@@ -391,3 +391,23 @@ def run_expz_sweep(sim, L, g, hs, phis, T, state="0", shots=1024, seed_simulator
     if world > 1:
         out = D.all_reduce_sum(out.reshape(-1), group, sim.ctx.device).reshape(out.shape)
     return {"expz": out, "mean": out.mean(axis=0), "points": len(pts)}
+
+
+# ----------------------------------------------------------------------------------- echo vs number of shots (shots.py)
+def run_shots_sweep(sim, L, g, hs, phis, t_values, shot_numbers=(100, 1000, 10000, 100000, 1000000), echo=True,
+                    polarization="x", qubit=None, initial_state="vacuum", seed_simulator=1234, rank=0, world=1, group=None):
+    """Instance-averaged (echo) autocorrelation for several shot counts: the outer loop of shots.py (:49,:247-262; one
+    independent sweep per entry of `shot_numbers`, each point one circuit with that many Pauli trajectories -- large counts
+    are batched through the state buffer by run()).  Sweep k uses seeds seed + k * 10007 + point index.
+    Returns {"shots": list, "mean": float64 [len(shot_numbers), len(t_values)] (the `av_autocorr_echo` column of each CSV),
+             "autocorr": [len(shot_numbers), n_inst, len(t_values)], "periods"}."""
+    means, full, periods = [], [], 0
+    for k, n in enumerate(shot_numbers):
+        res = run_sweep(sim, L, [g], hs, phis, t_values, echoes=(bool(echo),), polarizations=(polarization,), qubit=qubit,
+                        initial_state=initial_state, shots=int(n), seed_simulator=int(seed_simulator) + 10007 * k,
+                        rank=rank, world=world, group=group)
+        full.append(res["autocorr"][0, 0, 0])
+        means.append(res["mean"][0, 0, 0])
+        periods += res["periods"]
+    return {"shots": [int(n) for n in shot_numbers], "mean": np.asarray(means), "autocorr": np.asarray(full),
+            "periods": periods}

@@ -208,3 +208,17 @@ def test_run_expz_sweep_layout_and_values(disorder):
             assert np.array_equal(res["expz"][i, :, t - 1], O.compute_z_expectation(counts, L))
             k += 1
     assert np.allclose(res["mean"], res["expz"].mean(axis=0))
+
+
+def test_run_shots_sweep_is_one_sweep_per_shot_count(disorder):
+    """shots.py: the echo column for each shot count = run_sweep with that many shots and its own seed block."""
+    hs, phis = _disorder4()
+    tv = [0, 1, 2]
+    res = dtcsim.run_shots_sweep(_OracleSim(), 4, 0.84, hs, phis, tv, shot_numbers=(16, 128), seed_simulator=3)
+    assert res["shots"] == [16, 128] and res["mean"].shape == (2, 3) and res["autocorr"].shape == (2, 2, 3)
+    for k, n in enumerate((16, 128)):
+        one = dtcsim.run_sweep(_OracleSim(), 4, [0.84], hs, phis, tv, echoes=(True,), shots=n, seed_simulator=3 + 10007 * k)
+        assert np.array_equal(res["autocorr"][k], one["autocorr"][0, 0, 0])
+    assert res["periods"] == (16 + 128) * 2 * 2 * sum(tv)
+    # multiples of 1 / shots: the estimate really comes from that many samples
+    assert np.allclose(res["autocorr"][0] * 16 / 2, np.round(res["autocorr"][0] * 16 / 2))
