@@ -457,7 +457,7 @@ def lower_to_prims(circuit, noise_model=None):
         if noise_model is None or op.name in ("measure", "barrier"):
             return None
         if len(op.qubits) != 1:
-            if any(noise_model.lookup(op.name, q) for q in op.qubits):
+            if any(noise_model.lookup(op.name, q) is not None for q in op.qubits):
                 raise ValueError(f"noise on multi-qubit gate {op.name!r} is not supported")
             return None
         return noise_model.lookup(op.name, op.qubits[0])

@@ -139,3 +139,13 @@ def test_pauli_twirl_is_explicit_and_matches_closed_form(disorder):
     assert not tw_nm.has_channel_noise() and tw_nm.has_readout_noise() and nm.has_channel_noise()
     prog = compile_circuit(circ, tw_nm)
     assert prog.n_sites == 4 and not prog.has_channels
+
+
+def test_errors_on_two_qubit_gates_are_refused(disorder):
+    hs, phis = disorder[4][0][0], disorder[4][1][0]
+    circ = RC.transpiled(RC.qc_body("vacuum", 4, 0.84, hs, phis, 1, 2, False))
+    for err in (dtcsim.depolarizing_error(0.01, 1), N.amplitude_damping_error(0.01)):
+        nm = dtcsim.NoiseModel()
+        nm.add_all_qubit_quantum_error(err, ["cx"])
+        with pytest.raises(ValueError, match="multi-qubit gate"):
+            compile_circuit(circ, nm, want_dm=True)
